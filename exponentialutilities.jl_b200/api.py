@@ -1,0 +1,539 @@
+"""Host-side mirror of the ExponentialUtilities.jl Krylov API over the C ABI.
+
+Same names, argument meaning, defaults and error behaviour as the reference (Julia's ``f!`` is
+spelled ``f_`` here):
+
+    KrylovSubspace, arnoldi, arnoldi_, lanczos_      src/arnoldi.jl
+    expv, expv_, phiv, phiv_                         src/krylov_phiv.jl
+    kiops                                            src/kiops.jl
+    exponential_, phiv_dense                         src/exp_baseexp.jl, src/phi.jl
+
+PyTorch is used only for device memory and streams.  All arithmetic happens in
+libb200krylov.so; if the library or a CUDA device is missing every call raises (no CPU path).
+Vectors may be float64 CUDA tensors (results are CUDA tensors) or NumPy arrays (copied to the
+device, results returned as NumPy arrays).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import ArgumentError, DimensionMismatch, KiopsOpts, KrylovOpts
+
+try:  # torch is the device-memory / stream plumbing
+    import torch
+except Exception as _e:  # pragma: no cover
+    torch = None
+    _torch_err = _e
+
+
+def _need_torch():
+    if torch is None:
+        raise RuntimeError(f"PyTorch is required for device memory: {_torch_err}")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the B200 Krylov engine has no CPU fallback")
+
+
+def _round_up(x, a):
+    return (x + a - 1) // a * a
+
+
+# ------------------------------------------------------------------------------------------
+# engine (handle)
+# ------------------------------------------------------------------------------------------
+class Engine:
+    """One library handle on one device.  Calls run on torch's current stream of that device."""
+
+    def __init__(self, device=None):
+        _need_torch()
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                   (device.index if isinstance(device, torch.device) else int(device)))
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)  # make sure the primary context exists
+            h = C.c_void_p()
+            st = self.lib.b200k_create(C.byref(h), self.device.index,
+                                       C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        _lib.check(st)
+        self.handle = h
+        self._finalizer = weakref.finalize(self, self.lib.b200k_destroy, h)
+
+    def bind_stream(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self.lib.b200k_set_stream(self.handle, C.c_void_p(s))
+
+    def check(self, st):
+        _lib.check(st, self.handle)
+
+    def synchronize(self):
+        self.check(self.lib.b200k_synchronize(self.handle))
+
+    def device_info(self):
+        sm, team, launches = C.c_int(), C.c_int(), C.c_int64()
+        self.check(self.lib.b200k_device_info(self.handle, C.byref(sm), C.byref(team), C.byref(launches)))
+        return {"sm_count": sm.value, "max_team": team.value, "launches": launches.value}
+
+    def set_timing(self, enabled: bool):
+        self.check(self.lib.b200k_set_timing(self.handle, 1 if enabled else 0))
+
+    def last_timing(self):
+        a, b = C.c_float(), C.c_float()
+        self.check(self.lib.b200k_last_timing(self.handle, C.byref(a), C.byref(b)))
+        return {"krylov_ms": a.value, "project_ms": b.value}
+
+
+_engines = {}
+
+
+def get_engine(device=None) -> Engine:
+    _need_torch()
+    idx = torch.cuda.current_device() if device is None else (
+        device.index if isinstance(device, torch.device) else int(device))
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _engines:
+        _engines[idx] = Engine(idx)
+    return _engines[idx]
+
+
+# ------------------------------------------------------------------------------------------
+# operators (docs/src/interfaces.md: size / eltype / mul! / ishermitian / opnorm)
+# ------------------------------------------------------------------------------------------
+class Operator:
+    def __init__(self, engine: Engine, ptr, keep):
+        self.engine = engine
+        self.ptr = ptr
+        self._keep = keep
+        n, nnz, kind, herm, nrm = C.c_int64(), C.c_int64(), C.c_int(), C.c_int(), C.c_double()
+        _lib.check(engine.lib.b200k_op_info(ptr, C.byref(n), C.byref(nnz), C.byref(kind), C.byref(herm),
+                                            C.byref(nrm)))
+        self.n, self.nnz, self.kind = n.value, nnz.value, kind.value
+        self.ishermitian, self.opnorm_inf = bool(herm.value), nrm.value
+        self.shape = (self.n, self.n)
+        self.dtype = np.float64
+        self._finalizer = weakref.finalize(self, engine.lib.b200k_op_destroy, ptr)
+
+    def mul(self, x):
+        """mul!(y, A, x)"""
+        xd, was_np = _to_device(x, self.engine)
+        if xd.numel() != self.n:
+            raise DimensionMismatch("length(x) != size(A, 2)")
+        y = torch.empty_like(xd)
+        self.engine.bind_stream()
+        self.engine.check(self.engine.lib.b200k_op_apply(self.engine.handle, self.ptr, C.c_void_p(xd.data_ptr()),
+                                                         C.c_void_p(y.data_ptr())))
+        return _from_device(y, was_np)
+
+
+def operator(A, engine: Engine | None = None) -> Operator:
+    """Ingest a matrix: scipy.sparse (any format), 2-D NumPy array, 2-D float64 CUDA tensor, or a
+    (rowptr, colind, val) triple of CUDA tensors / NumPy arrays describing 0-based CSR."""
+    if isinstance(A, Operator):
+        return A
+    eng = engine or get_engine()
+    lib = eng.lib
+    eng.bind_stream()
+    ptr = C.c_void_p()
+    try:
+        import scipy.sparse as sp
+    except Exception:  # pragma: no cover
+        sp = None
+    if sp is not None and sp.issparse(A):
+        if A.shape[0] != A.shape[1]:
+            raise DimensionMismatch("operator must be square")
+        A = A.tocsr()
+        if not A.has_canonical_format:
+            A = A.copy()
+            A.sum_duplicates()
+        rp = np.ascontiguousarray(A.indptr, dtype=np.int32)
+        ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+        va = np.ascontiguousarray(A.data, dtype=np.float64)
+        eng.check(lib.b200k_op_csr_create(eng.handle, A.shape[0], va.size, rp.ctypes.data, ci.ctypes.data,
+                                          va.ctypes.data, 0, 1, C.byref(ptr)))
+        return Operator(eng, ptr, None)
+    if isinstance(A, tuple) and len(A) == 3:
+        rp, ci, va = A
+        if torch is not None and isinstance(va, torch.Tensor):
+            rp = rp.to(torch.int32).contiguous()
+            ci = ci.to(torch.int32).contiguous()
+            va = va.to(torch.float64).contiguous()
+            eng.check(lib.b200k_op_csr_create(eng.handle, rp.numel() - 1, va.numel(), C.c_void_p(rp.data_ptr()),
+                                              C.c_void_p(ci.data_ptr()), C.c_void_p(va.data_ptr()), 0, 0,
+                                              C.byref(ptr)))
+            eng.synchronize()
+            return Operator(eng, ptr, None)
+        rp = np.ascontiguousarray(rp, dtype=np.int32)
+        ci = np.ascontiguousarray(ci, dtype=np.int32)
+        va = np.ascontiguousarray(va, dtype=np.float64)
+        eng.check(lib.b200k_op_csr_create(eng.handle, rp.size - 1, va.size, rp.ctypes.data, ci.ctypes.data,
+                                          va.ctypes.data, 0, 1, C.byref(ptr)))
+        return Operator(eng, ptr, None)
+    if torch is not None and isinstance(A, torch.Tensor):
+        if A.dim() != 2 or A.shape[0] != A.shape[1]:
+            raise DimensionMismatch("operator must be square")
+        n = A.shape[0]
+        ld = _round_up(n, 2)
+        At = torch.zeros((n, ld), dtype=torch.float64, device=eng.device)  # row i = column i of A
+        At[:, :n] = A.to(device=eng.device, dtype=torch.float64).t()
+        eng.check(lib.b200k_op_dense_create(eng.handle, n, C.c_void_p(At.data_ptr()), ld, 0, C.byref(ptr)))
+        return Operator(eng, ptr, At)
+    A = np.asarray(A, dtype=np.float64)
+    if A.ndim != 2 or A.shape[0] != A.shape[1]:
+        raise DimensionMismatch("operator must be square")
+    Af = np.asfortranarray(A)
+    eng.check(lib.b200k_op_dense_create(eng.handle, A.shape[0], Af.ctypes.data, A.shape[0], 1, C.byref(ptr)))
+    return Operator(eng, ptr, None)
+
+
+def _to_device(x, eng: Engine):
+    if torch is not None and isinstance(x, torch.Tensor):
+        if x.dtype != torch.float64:
+            raise ArgumentError("only Float64 vectors are supported")
+        if not x.is_cuda:
+            return x.to(eng.device).contiguous(), False
+        return x.contiguous(), False
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    return torch.from_numpy(a).to(eng.device), True
+
+
+def _from_device(x, was_np):
+    return x.cpu().numpy() if was_np else x
+
+
+# ------------------------------------------------------------------------------------------
+# KrylovSubspace (src/arnoldi.jl:50-93)
+# ------------------------------------------------------------------------------------------
+class KrylovSubspace:
+    """m, maxiter, augmented, beta, wasbreakdown, V, H -- V on the device, H on the host.
+
+    V is (n + augmented) x (maxiter + 1) column-major; it is held as a (maxiter + 1, ldv) torch tensor
+    (one basis vector per row, ldv padded to a multiple of 16) and exposed transposed through ``.V``.
+    """
+
+    def __init__(self, n, maxiter=30, augmented=0, engine: Engine | None = None):
+        self.engine = engine or get_engine()
+        self.n = int(n)
+        self.m = int(maxiter)
+        self.maxiter = int(maxiter)
+        self.augmented = int(augmented)
+        self.beta = 0.0
+        self.wasbreakdown = False
+        self.nrows = self.n + self.augmented
+        self.ldv = _round_up(self.nrows, 16)
+        self.Vt = torch.zeros((self.maxiter + 1, self.ldv), dtype=torch.float64, device=self.engine.device)
+        self.H = np.zeros((self.maxiter + 1, self.maxiter + (1 if self.augmented else 0)), order="F")
+
+    @property
+    def V(self):
+        return self.Vt[:, : self.nrows].t()
+
+    def getV(self):
+        return self.Vt[: self.m + 1, : self.nrows].t()
+
+    def getH(self):
+        return self.H[: self.m + 1, : self.m + (1 if self.augmented else 0)]
+
+    def resize(self, maxiter):
+        """Base.resize! (src/arnoldi.jl:80-93): contents are preserved only for augmented subspaces."""
+        isaug = self.augmented != 0
+        Vt = torch.zeros((maxiter + 1, self.ldv), dtype=torch.float64, device=self.engine.device)
+        H = np.zeros((maxiter + 1, maxiter + (1 if isaug else 0)), order="F")
+        if isaug:
+            Vt[: self.Vt.shape[0]] = self.Vt
+            H[: self.H.shape[0], : self.H.shape[1]] = self.H
+        self.Vt, self.H = Vt, H
+        self.m = self.maxiter = int(maxiter)
+        return self
+
+
+def _resolve_op(A, engine=None):
+    if isinstance(A, tuple) and len(A) == 2:  # augmented (A, B)
+        return operator(A[0], engine), A[1]
+    return operator(A, engine), None
+
+
+def arnoldi_(Ks: KrylovSubspace, A, b, *, tol=1.0e-7, m=None, ishermitian=None, opnorm=None, iop=0, init=0,
+             t=float("nan"), mu=float("nan"), l=-1):
+    """arnoldi!(Ks, A, b; tol, m, ishermitian, opnorm, iop, init, t, mu, l) -- src/arnoldi.jl:345-377.
+
+    ``A`` may be ``(A, B)`` and ``b`` may be ``(w, w_aug)`` for the augmented form used by kiops
+    (``w`` is n x numSteps, ``l`` the 1-based column)."""
+    eng = Ks.engine
+    op, B = _resolve_op(A, eng)
+    if m is None:
+        m = min(Ks.maxiter, op.n)
+    herm = op.ishermitian if ishermitian is None else bool(ishermitian)
+    Ks.wasbreakdown = False
+    if m > Ks.maxiter:
+        Ks.resize(m)
+    else:
+        Ks.m = m
+    # checkdims (src/arnoldi.jl:207-220)
+    if isinstance(b, tuple):
+        bw, b_aug = b
+        bd, _ = _to_device(bw, eng)
+        if bd.dim() == 2:
+            if bd.shape[1] != 1 and bd.numel() != op.n:
+                raise DimensionMismatch("length(b') != size(A, 1)")
+            bd = bd[:, l - 1].contiguous() if bd.shape[1] > 1 else bd.reshape(-1)
+        p = int(np.asarray(b_aug).shape[0])
+    else:
+        bd, _ = _to_device(b, eng)
+        bd = bd.reshape(-1)
+        p = 0
+    if not (bd.numel() == op.n == Ks.nrows - p):
+        raise DimensionMismatch(f"length(b) [{bd.numel()}] == size(A,1) [{op.n}] == size(V,1)-p [{Ks.nrows - p}] "
+                                "doesn't hold")
+    opts = KrylovOpts()
+    eng.lib.b200k_krylov_opts_default(C.byref(opts))
+    opts.m, opts.tol, opts.iop, opts.hermitian, opts.init = int(m), float(tol), int(iop), int(herm), int(init)
+    keep = None
+    if p > 0:
+        Bd, _ = _to_device(B, eng)
+        ldb = _round_up(op.n, 2)
+        keep = torch.zeros((p, ldb), dtype=torch.float64, device=eng.device)
+        keep[:, : op.n] = Bd.reshape(op.n, p).t()
+        opts.p, opts.B, opts.ldb, opts.t, opts.mu = p, keep.data_ptr(), ldb, float(t), float(mu)
+        if init == 0:  # the reference also overwrites the caller's w_aug (src/arnoldi.jl:259-266)
+            ba = np.asarray(b_aug)
+            for k in range(1, p + 1):
+                ba[k - 1] = mu if k == p else t ** (p - k) / math.factorial(p - k) * mu
+    beta = C.c_double(Ks.beta)
+    m_out, brk = C.c_int(), C.c_int()
+    eng.bind_stream()
+    st = eng.lib.b200k_arnoldi(eng.handle, op.ptr, C.c_void_p(bd.data_ptr()), C.byref(opts),
+                               C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.maxiter,
+                               Ks.H.ctypes.data_as(_lib.c_double_p), Ks.H.shape[0], C.byref(beta), C.byref(m_out),
+                               C.byref(brk))
+    eng.check(st)
+    Ks.beta = beta.value
+    Ks.m = m_out.value
+    Ks.wasbreakdown = bool(brk.value)
+    return Ks
+
+
+def lanczos_(Ks: KrylovSubspace, A, b, **kw):
+    """lanczos!(Ks, A, b; tol, m, init, t, mu, l) -- src/arnoldi.jl:456-490."""
+    kw.pop("ishermitian", None)
+    return arnoldi_(Ks, A, b, ishermitian=True, **kw)
+
+
+def arnoldi(A, b, *, m=None, ishermitian=None, **kw):
+    """arnoldi(A, b; m = min(30, size(A,1)), ishermitian = ishermitian(A), kw...) -- src/arnoldi.jl:161-180."""
+    op = operator(A)
+    n = int(np.prod(b.shape))
+    if m is None:
+        m = min(30, op.n)
+    Ks = KrylovSubspace(n, m, 0, engine=op.engine)
+    return arnoldi_(Ks, op, b, m=m, ishermitian=ishermitian, **kw)
+
+
+# ------------------------------------------------------------------------------------------
+# expv / phiv (src/krylov_phiv.jl)
+# ------------------------------------------------------------------------------------------
+def expv_(w, t, Ks: KrylovSubspace, *, cache=None):
+    """expv!(w, t, Ks) -- src/krylov_phiv.jl:200-247.  ``w``: float64 CUDA tensor of length size(V,1)."""
+    eng = Ks.engine
+    if not isinstance(t, (int, float, np.floating, np.integer)):
+        raise _lib.UnsupportedError("complex t is not supported by the B200 engine yet")
+    if w.numel() != Ks.nrows:
+        raise DimensionMismatch("Dimension mismatch")
+    eng.bind_stream()
+    st = eng.lib.b200k_expv_ks(eng.handle, float(t), C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.nrows,
+                               Ks.H.ctypes.data_as(_lib.c_double_p), Ks.H.shape[0], Ks.m, Ks.beta,
+                               C.c_void_p(w.data_ptr()))
+    eng.check(st)
+    return w
+
+
+def expv(t, A, b=None, *, mode="happy_breakdown", m=None, tol=1.0e-7, ishermitian=None, iop=0, opnorm=None,
+         cache=None, expmethod=None):
+    """expv(t, A, b; m, tol, ishermitian, iop, ...) or expv(t, Ks) -- src/krylov_phiv.jl:125-168."""
+    if isinstance(A, KrylovSubspace):
+        Ks = A
+        w = torch.empty(Ks.nrows, dtype=torch.float64, device=Ks.engine.device)
+        return expv_(w, t, Ks)
+    if mode != "happy_breakdown":
+        if mode == "error_estimate":
+            raise _lib.UnsupportedError("mode=:error_estimate is not implemented by the B200 engine yet")
+        raise ArgumentError(f"Unknown Krylov iteration termination mode, {mode}")
+    op = operator(A)
+    eng = op.engine
+    bd, was_np = _to_device(b, eng)
+    bd = bd.reshape(-1)
+    if bd.numel() != op.n:
+        raise DimensionMismatch("length(b) != size(A, 1)")
+    if m is None:
+        m = min(30, op.n)
+    opts = KrylovOpts()
+    eng.lib.b200k_krylov_opts_default(C.byref(opts))
+    opts.m, opts.tol, opts.iop = int(m), float(tol), int(iop)
+    opts.hermitian = -1 if ishermitian is None else int(bool(ishermitian))
+    w = torch.empty_like(bd)
+    eng.bind_stream()
+    st = eng.lib.b200k_expv(eng.handle, op.ptr, float(t), C.c_void_p(bd.data_ptr()), C.byref(opts),
+                            C.c_void_p(w.data_ptr()), None, None, None)
+    eng.check(st)
+    return _from_device(w, was_np)
+
+
+def expv_host(t, op: Operator, b_host, w_host, *, m=30, tol=1.0e-7, ishermitian=None, iop=0):
+    """End-to-end call with HOST (ideally pinned) float64 tensors: H2D(b) -> expv -> D2H(w), synchronous."""
+    eng = op.engine
+    opts = KrylovOpts()
+    eng.lib.b200k_krylov_opts_default(C.byref(opts))
+    opts.m, opts.tol, opts.iop = int(min(m, op.n)), float(tol), int(iop)
+    opts.hermitian = -1 if ishermitian is None else int(bool(ishermitian))
+    eng.bind_stream()
+    st = eng.lib.b200k_expv_host(eng.handle, op.ptr, float(t), C.c_void_p(b_host.data_ptr()), C.byref(opts),
+                                 C.c_void_p(w_host.data_ptr()), None, None)
+    eng.check(st)
+    return w_host
+
+
+def phiv_(w, t, Ks: KrylovSubspace, k, *, cache=None, correct=False, errest=False):
+    """phiv!(w, t, Ks, k; correct, errest) -- src/krylov_phiv.jl:607-653.
+
+    ``w``: float64 CUDA tensor holding the column-major nrows x (k+1) result, i.e. of shape (k+1, nrows)."""
+    eng = Ks.engine
+    if w.dim() != 2 or w.shape[1] != Ks.nrows or w.shape[0] != k + 1:
+        raise DimensionMismatch("Dimension mismatch")
+    err = C.c_double()
+    eng.bind_stream()
+    st = eng.lib.b200k_phiv_ks(eng.handle, float(t), C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.nrows,
+                               Ks.H.ctypes.data_as(_lib.c_double_p), Ks.H.shape[0], Ks.m, Ks.beta, int(k),
+                               1 if correct else 0, C.c_void_p(w.data_ptr()), w.stride(0), C.byref(err))
+    eng.check(st)
+    return (w, err.value) if errest else w
+
+
+def phiv(t, A, b=None, k=None, *, cache=None, correct=False, errest=False, m=None, tol=1.0e-7, ishermitian=None,
+         iop=0, opnorm=None):
+    """phiv(t, A, b, k; ...) or phiv(t, Ks, k; ...) -- src/krylov_phiv.jl:563-575.
+
+    Returns the n x (k+1) matrix [phi_0(tA) b ... phi_k(tA) b] (NumPy for NumPy input, otherwise a
+    transposed view of a (k+1, n) CUDA tensor)."""
+    if isinstance(A, KrylovSubspace):
+        Ks, k = A, b
+        was_np = False
+    else:
+        op = operator(A)
+        was_np = not (torch is not None and isinstance(b, torch.Tensor))
+        Ks = arnoldi(op, b, m=m, tol=tol, ishermitian=ishermitian, iop=iop)
+    w = torch.empty((k + 1, Ks.nrows), dtype=torch.float64, device=Ks.engine.device)
+    res = phiv_(w, t, Ks, k, correct=correct, errest=errest)
+    wt = (res[0] if errest else res).t()
+    out = wt.cpu().numpy() if was_np else wt
+    return (out, res[1]) if errest else out
+
+
+def expv_batched(ts, A, B, *, m=30, tol=1.0e-7, ishermitian=None, iop=0):
+    """nb independent expv(t_i, A, B[:, i]) on a shared operator in one launch.  B: n x nb."""
+    op = operator(A)
+    eng = op.engine
+    ts = np.ascontiguousarray(np.asarray(ts, dtype=np.float64).reshape(-1))
+    Bd, was_np = _to_device(B, eng)
+    if Bd.dim() != 2 or Bd.shape[0] != op.n or Bd.shape[1] != ts.size:
+        raise DimensionMismatch("B must be n x nb with nb == length(ts)")
+    nb = ts.size
+    ld = _round_up(op.n, 2)
+    Bt = torch.zeros((nb, ld), dtype=torch.float64, device=eng.device)
+    Bt[:, : op.n] = Bd.t()
+    Wt = torch.empty((nb, ld), dtype=torch.float64, device=eng.device)
+    opts = KrylovOpts()
+    eng.lib.b200k_krylov_opts_default(C.byref(opts))
+    opts.m, opts.tol, opts.iop = int(min(m, op.n)), float(tol), int(iop)
+    opts.hermitian = -1 if ishermitian is None else int(bool(ishermitian))
+    eng.bind_stream()
+    st = eng.lib.b200k_expv_batched(eng.handle, op.ptr, nb, ts.ctypes.data_as(_lib.c_double_p),
+                                    C.c_void_p(Bt.data_ptr()), ld, C.byref(opts), C.c_void_p(Wt.data_ptr()), ld,
+                                    None, None)
+    eng.check(st)
+    W = Wt[:, : op.n].t()
+    return W.cpu().numpy() if was_np else W
+
+
+# ------------------------------------------------------------------------------------------
+# kiops (src/kiops.jl:57-281)
+# ------------------------------------------------------------------------------------------
+def kiops(tau_out, A, u, *, mmin=10, mmax=128, m=None, tol=1.0e-7, opnorm=None, iop=2, ishermitian=None,
+          task1=False):
+    """kiops(tau_out, A, u; mmin, mmax, m, tol, opnorm, iop, ishermitian, task1) -> (w, stats).
+
+    ``w`` is n x numSteps (host NumPy array, as the reference returns a host ``zeros(n, numSteps)``,
+    src/kiops.jl:89) and ``stats = (steps, rejected, krylov_steps, exps, m)``."""
+    op = operator(A)
+    eng = op.engine
+    tau_arr = np.asarray(tau_out, dtype=np.float64)
+    tau_is_row = 1 if (tau_arr.ndim == 2 and tau_arr.shape[0] == 1) else 0
+    numSteps = tau_arr.shape[1] if tau_arr.ndim == 2 else 1
+    tau_flat = np.ascontiguousarray(tau_arr.reshape(-1))
+    ud, _ = _to_device(u, eng)
+    if ud.dim() == 1:
+        ud = ud.reshape(-1, 1)
+    n, ppo = ud.shape
+    if n != op.n:
+        raise DimensionMismatch("size(u, 1) != size(A, 1)")
+    ld = _round_up(n, 2)
+    Ut = torch.zeros((ppo, ld), dtype=torch.float64, device=eng.device)
+    Ut[:, :n] = ud.t()
+    Wt = torch.zeros((numSteps, ld), dtype=torch.float64, device=eng.device)
+    ko = KiopsOpts()
+    eng.lib.b200k_kiops_opts_default(C.byref(ko))
+    ko.mmin, ko.mmax, ko.tol, ko.iop = int(mmin), int(mmax), float(tol), int(iop)
+    ko.m = int(min(mmin, mmax) if m is None else m)
+    ko.hermitian = -1 if ishermitian is None else int(bool(ishermitian))
+    ko.task1 = 1 if task1 else 0
+    stats = (C.c_int64 * 5)()
+    eng.bind_stream()
+    st = eng.lib.b200k_kiops(eng.handle, op.ptr, tau_flat.size, tau_flat.ctypes.data_as(_lib.c_double_p),
+                             tau_is_row, C.c_void_p(Ut.data_ptr()), ld, ppo, C.byref(ko),
+                             C.c_void_p(Wt.data_ptr()), ld, stats)
+    eng.check(st)
+    w = Wt[:, :n].t().cpu().numpy()
+    return w, tuple(int(s) for s in stats)
+
+
+# ------------------------------------------------------------------------------------------
+# small dense (host) -- src/exp_baseexp.jl, src/phi.jl
+# ------------------------------------------------------------------------------------------
+def exponential_(A):
+    """exponential!(A, ExpMethodHigham2005Base()) on a host matrix (returns a new F-ordered array)."""
+    lib = _lib.load()
+    Af = np.array(A, dtype=np.float64, order="F", copy=True)
+    if Af.ndim != 2 or Af.shape[0] != Af.shape[1]:
+        raise DimensionMismatch("matrix is not square")
+    _lib.check(lib.b200k_exponential(Af.shape[0], Af.ctypes.data_as(_lib.c_double_p), max(Af.shape[0], 1)))
+    return Af
+
+
+def phiv_dense(A, v, k):
+    """phiv_dense(A, v, k) -- src/phi.jl:63-66, 84-115 (host)."""
+    lib = _lib.load()
+    Af = np.array(A, dtype=np.float64, order="F", copy=True)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    m = v.shape[0]
+    if Af.shape != (m, m):
+        raise DimensionMismatch("Dimension mismatch")
+    w = np.zeros((m, k + 1), order="F")
+    _lib.check(lib.b200k_phiv_dense(m, Af.ctypes.data_as(_lib.c_double_p), m, v.ctypes.data_as(_lib.c_double_p),
+                                    int(k), w.ctypes.data_as(_lib.c_double_p), m))
+    return w
+
+
+def expv_small(H, t):
+    """y = exp(t*H) e1 exactly as the small dense phase of expv! does it (host); returns (y, branch)
+    with branch 1 = SymTridiagonal eigen, 0 = Higham-2005 Pade (src/krylov_phiv.jl:223-244)."""
+    lib = _lib.load()
+    Hf = np.array(H, dtype=np.float64, order="F", copy=True)
+    m = Hf.shape[0]
+    y = np.zeros(m)
+    br = C.c_int()
+    _lib.check(lib.b200k_expv_small(m, Hf.ctypes.data_as(_lib.c_double_p), m, float(t),
+                                    y.ctypes.data_as(_lib.c_double_p), C.byref(br)))
+    return y, br.value

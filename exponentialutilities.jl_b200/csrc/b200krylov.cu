@@ -1,0 +1,1249 @@
+// b200krylov.cu -- C ABI (include/b200krylov.h) of the B200 Krylov expmv/phiv engine.
+// Host orchestration only: geometry, scratch, launches, the small dense phase on the host H, kiops.
+#include "../../include/b200krylov.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "krylov_kernel.cuh"
+#include "smallmat.hpp"
+
+using namespace b200k;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct HostBuf {  // pinned
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes + 256);
+        if (e == cudaSuccess) cap = bytes + 256;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+inline long long round_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct b200k_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int max_ctas = 0;  // co-resident CTAs of the persistent kernel
+    std::string err;
+    int64_t launches = 0;
+    // scratch (device)
+    DevBuf xbuf, part, partn, bar, wglob, Hd, scal, stat, btail, Y, corr, mvec, betavec, tmp;
+    // scratch (host, pinned)
+    HostBuf Hh, scalh, stath, Yh;
+    // internal Krylov storage for the one-shot calls
+    DevBuf V, bdev, wdev;
+    std::vector<double> H;
+    smallmat::ExpWork expwork;
+    // timing
+    int timing = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float krylov_ms = 0.f, project_ms = 0.f;
+};
+
+struct b200k_operator {
+    b200k_context *ctx = nullptr;
+    int kind = 0;  // 0 CSR, 1 dense
+    long long n = 0, nnz = 0;
+    DevBuf rowptr, colind, val;  // owned, 0-based, padded
+    const double *Ad = nullptr;  // dense: alias (device input) or owned copy
+    DevBuf Aown;
+    long long lda = 0;
+    int max_row_nnz = 0;
+    int is_herm = 0;
+    double opnorm_inf = 0.0;
+};
+
+namespace {
+
+int fail(b200k_context *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define CK(h, call)                                                                                        \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail((h), B200K_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));            \
+    } while (0)
+
+struct Geom {
+    int C = 1, nteams = 1, slice = 16, w_in_smem = 1;
+    size_t smem = 0;
+};
+
+constexpr size_t SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA
+
+// Rows per CTA and shared-memory footprint for a team of C CTAs.
+Geom make_geom(long long n, int C, int nteams) {
+    Geom g;
+    g.C = C;
+    g.nteams = nteams;
+    g.slice = (int)round_up((n + C - 1) / C, 16);
+    if (g.slice < 16) g.slice = 16;
+    const size_t need = sizeof(SmemFixed) + (size_t)g.slice * 8;
+    g.w_in_smem = need <= SMEM_LIMIT ? 1 : 0;
+    g.smem = g.w_in_smem ? need : sizeof(SmemFixed);
+    return g;
+}
+
+Geom single_geom(b200k_context *h, long long n) {
+    int C = (int)std::min<long long>(h->max_ctas, std::max<long long>(1, (n + 15) / 16));
+    return make_geom(n, C, 1);
+}
+
+// Team size for a batch of nb problems: maximise problems in flight x SM use, w slice in shared memory.
+Geom batch_geom(b200k_context *h, long long n, int nb) {
+    Geom best;
+    double best_score = -1.0;
+    for (int C = 1; C <= h->max_ctas; ++C) {
+        int nteams = h->max_ctas / C;
+        if (nteams < 1) break;
+        nteams = std::min(nteams, nb);
+        Geom g = make_geom(n, C, nteams);
+        if (!g.w_in_smem) continue;
+        if ((long long)g.slice * (C - 1) >= n && C > 1) continue;  // empty trailing CTAs
+        const int rounds = (nb + nteams - 1) / nteams;
+        const double score = (double)nb / ((double)rounds * nteams) * ((double)nteams * C / h->max_ctas);
+        if (score > best_score + 1e-12) {
+            best_score = score;
+            best = g;
+        }
+    }
+    if (best_score < 0) best = single_geom(h, n);
+    return best;
+}
+
+struct KrylovCall {
+    b200k_operator *op;
+    const double *b;
+    long long b_stride;
+    int nprob;
+    double *V;
+    long long ldv, V_stride;
+    int m, j0, iop, lanczos;
+    double tol;
+    int p;
+    const double *B;
+    long long ldb;
+    const double *btail_host;
+    Geom g;
+};
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Launch the persistent kernel; results land in h->Hd / h->scal / h->stat (device), ldhd = m + 1.
+int launch_krylov(b200k_context *h, const KrylovCall &c) {
+    b200k_operator *op = c.op;
+    const long long n = op->n;
+    KrylovParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = (int)n;
+    if (op->kind == 0) {
+        P.rowptr = op->rowptr.as<int>();
+        P.colind = op->colind.as<int>();
+        P.val = op->val.as<double>();
+        int ch_rows = op->max_row_nnz > 0 ? CH_NNZ / op->max_row_nnz : NT;
+        ch_rows = std::min(ch_rows, NT) / 32 * 32;
+        if (ch_rows >= 64) {
+            P.op_kind = OP_CSR_STREAM;
+            P.ch_rows = ch_rows;
+        } else {
+            P.op_kind = OP_CSR_WARP;
+            P.ch_rows = 32;
+        }
+    } else {
+        P.op_kind = OP_DENSE;
+        P.Ad = op->Ad;
+        P.lda = op->lda;
+    }
+    P.p = c.p;
+    P.Bm = c.B;
+    P.ldb = c.ldb;
+    P.team_size = c.g.C;
+    P.nteams = c.g.nteams;
+    P.nprob = c.nprob;
+    P.slice = c.g.slice;
+    P.b = c.b;
+    P.b_stride = c.b_stride;
+    P.V = c.V;
+    P.ldv = c.ldv;
+    P.V_stride = c.V_stride;
+    P.m = c.m;
+    P.j0 = c.j0;
+    P.iop = c.iop;
+    P.lanczos = c.lanczos;
+    P.tol = c.tol;
+    P.w_in_smem = c.g.w_in_smem;
+    const int ldhd = c.m + 1;
+    P.ldh = ldhd;
+    P.H_stride = (long long)ldhd * (c.m + 1);
+    P.xlen = round_up(n + c.p, 16);
+
+    bool vec2 = (n % 2 == 0) && (c.ldv % 2 == 0) && (c.V_stride % 2 == 0) && aligned16(c.V) &&
+                (c.j0 != 0 || (aligned16(c.b) && c.b_stride % 2 == 0));
+    if (op->kind == 1) vec2 = vec2 && aligned16(op->Ad) && (op->lda % 2 == 0);
+    P.vec2 = vec2 ? 1 : 0;
+
+    const int nt = c.g.nteams;
+    CK(h, h->xbuf.ensure((size_t)nt * 2 * P.xlen * 8));
+    CK(h, h->part.ensure((size_t)nt * 2 * MAXCOL * CPAD * 8));
+    CK(h, h->partn.ensure((size_t)nt * 4 * CPAD * 8));
+    CK(h, h->bar.ensure((size_t)nt * 4));
+    if (!c.g.w_in_smem) CK(h, h->wglob.ensure((size_t)nt * n * 8));
+    CK(h, h->Hd.ensure((size_t)c.nprob * P.H_stride * 8));
+    CK(h, h->scal.ensure((size_t)c.nprob * 4 * 8));
+    CK(h, h->stat.ensure((size_t)c.nprob * 4 * 4));
+    CK(h, h->btail.ensure(MAXP * 8));
+    P.xbuf = h->xbuf.as<double>();
+    P.part = h->part.as<double>();
+    P.partn = h->partn.as<double>();
+    P.bar = h->bar.as<unsigned>();
+    P.wglob = h->wglob.as<double>();
+    P.Hd = h->Hd.as<double>();
+    P.scal = h->scal.as<double>();
+    P.stat = h->stat.as<int>();
+    P.btail = h->btail.as<double>();
+
+    CK(h, cudaMemsetAsync(P.bar, 0, (size_t)nt * 4, h->stream));
+    CK(h, cudaMemsetAsync(P.Hd, 0, (size_t)c.nprob * P.H_stride * 8, h->stream));
+    CK(h, cudaMemsetAsync(P.scal, 0, (size_t)c.nprob * 4 * 8, h->stream));
+    if (c.p > 0 && c.j0 == 0)
+        CK(h, cudaMemcpyAsync(h->btail.p, c.btail_host, (size_t)c.p * 8, cudaMemcpyHostToDevice, h->stream));
+
+    if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
+    void *args[] = {(void *)&P};
+    CK(h, cudaLaunchCooperativeKernel((const void *)krylov_persistent_kernel, dim3(c.g.C * c.g.nteams), dim3(NT),
+                                      args, c.g.smem, h->stream));
+    if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
+    h->launches += 1;
+    return B200K_OK;
+}
+
+// Copy H / beta / (m, breakdown) of nprob problems to pinned host memory and wait.
+int fetch_krylov(b200k_context *h, int nprob, int m) {
+    const size_t hbytes = (size_t)nprob * (m + 1) * (m + 1) * 8;
+    CK(h, h->Hh.ensure(hbytes));
+    CK(h, h->scalh.ensure((size_t)nprob * 4 * 8));
+    CK(h, h->stath.ensure((size_t)nprob * 4 * 4));
+    CK(h, cudaMemcpyAsync(h->Hh.p, h->Hd.p, hbytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(h->scalh.p, h->scal.p, (size_t)nprob * 4 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(h->stath.p, h->stat.p, (size_t)nprob * 4 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->timing) cudaEventElapsedTime(&h->krylov_ms, h->ev[0], h->ev[1]);
+    return B200K_OK;
+}
+
+// Small dense phase of expv! on the host H (krylov_phiv.jl:223-244): y = exp(t H[1:m,1:m]) e1.
+int expv_small(b200k_context *h, double t, const double *H, int ldh, int m, double *y) {
+    if (smallmat::is_exactly_symmetric(m, H, ldh)) {
+        if (!smallmat::exp_symtridiag_e1(m, H, ldh, t, y))
+            return fail(h, B200K_ESINGULAR, "symmetric tridiagonal eigensolver did not converge");
+        return B200K_OK;
+    }
+    std::vector<double> Hc((size_t)m * m);
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) Hc[(size_t)j * m + i] = t * H[(size_t)j * ldh + i];
+    const int st = smallmat::expm_higham2005base(m, Hc.data(), h->expwork);
+    if (st) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
+    for (int i = 0; i < m; ++i) y[i] = Hc[i];
+    return B200K_OK;
+}
+
+// W (nrows x nc) = beta * V[:, 0:m] * Y (+ corr[c] * V[:, m]); Yhost is m x nc with leading dimension ldy.
+int launch_project(b200k_context *h, const double *V, long long ldv, long long nrows, int m, double beta,
+                   const double *Yhost, int ldy, int nc, double *W, long long ldw, const double *corr_host) {
+    if (m > PROJ_MAXM) return fail(h, B200K_EUNSUPPORTED, "projection supports m <= 256");
+    CK(h, h->Yh.ensure((size_t)m * nc * 8 + (size_t)nc * 8));
+    CK(h, h->Y.ensure((size_t)m * nc * 8));
+    double *yh = h->Yh.as<double>();
+    for (int c = 0; c < nc; ++c)
+        for (int i = 0; i < m; ++i) yh[(size_t)c * m + i] = Yhost[(size_t)c * ldy + i];
+    CK(h, cudaMemcpyAsync(h->Y.p, yh, (size_t)m * nc * 8, cudaMemcpyHostToDevice, h->stream));
+    ProjectParams P;
+    std::memset(&P, 0, sizeof(P));
+    if (corr_host) {
+        CK(h, h->corr.ensure((size_t)nc * 8));
+        double *ch = yh + (size_t)m * nc;
+        for (int c = 0; c < nc; ++c) ch[c] = corr_host[c];
+        CK(h, cudaMemcpyAsync(h->corr.p, ch, (size_t)nc * 8, cudaMemcpyHostToDevice, h->stream));
+        P.corr = h->corr.as<double>();
+    }
+    P.V = V;
+    P.ldv = ldv;
+    P.nrows = nrows;
+    P.Y = h->Y.as<double>();
+    P.ldy = m;
+    P.m = m;
+    P.beta = beta;
+    P.nc = nc;
+    P.W = W;
+    P.ldw = ldw;
+    P.vec2 = (nrows % 2 == 0) && (ldv % 2 == 0) && (ldw % 2 == 0) && aligned16(V) && aligned16(W);
+    const long long units = P.vec2 ? nrows / 2 : nrows;
+    int gx = (int)std::min<long long>((units + PROJ_NT - 1) / PROJ_NT, (long long)h->sm_count * 8);
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, (nc + PROJ_NC - 1) / PROJ_NC, 1);
+    if (h->timing) CK(h, cudaEventRecord(h->ev[2], h->stream));
+    project_kernel<<<grid, PROJ_NT, 0, h->stream>>>(P);
+    CK(h, cudaGetLastError());
+    if (h->timing) CK(h, cudaEventRecord(h->ev[3], h->stream));
+    h->launches += 1;
+    return B200K_OK;
+}
+
+// b_aug of the augmented firststep! (arnoldi.jl:259-266)
+void make_btail(int p, double t, double mu, double *out) {
+    for (int k = 1; k <= p; ++k) {
+        if (k == p) {
+            out[k - 1] = mu;
+        } else {
+            const int i = p - k;
+            double fact = 1.0;
+            for (int q = 2; q <= i; ++q) fact *= q;
+            out[k - 1] = std::pow(t, i) / fact * mu;
+        }
+    }
+}
+
+// Core of arnoldi!/lanczos! shared by b200k_arnoldi, the one-shots and kiops.
+int arnoldi_core(b200k_context *h, b200k_operator *op, const double *b, const b200k_krylov_opts *o, double *V,
+                 long long ldv, int maxiter, double *H, int ldh, double *beta, int *m_out, int *breakdown) {
+    const long long n = op->n;
+    const int p = o->p;
+    const int m = o->m;
+    const int aug = p != 0 ? 1 : 0;
+    if (m < 1) return fail(h, B200K_EARG, "m must be >= 1");
+    if (m > maxiter) return fail(h, B200K_EDIM, "m exceeds Ks.maxiter: resize the KrylovSubspace first");
+    if (m >= MAXCOL) return fail(h, B200K_EUNSUPPORTED, "Krylov dimension m must be < 256");
+    if (p < 0 || p > MAXP) return fail(h, B200K_EUNSUPPORTED, "augmented rows p must be <= 16");
+    if (ldv < n + p) return fail(h, B200K_EDIM, "DimensionMismatch: size(V,1) - p != size(A,1)");
+    if (ldh < m + 1) return fail(h, B200K_EDIM, "H has fewer than m+1 rows");
+    if (o->init < 0 || o->init > m) return fail(h, B200K_EARG, "init must be in 0..m");
+    if (p > 0 && (o->B == nullptr || o->ldb < n)) return fail(h, B200K_EARG, "augmented operator needs B (n x p)");
+    int herm = o->hermitian;
+    if (herm < 0) herm = op->is_herm;
+    *breakdown = 0;
+    *m_out = m;
+    if (o->init == 0) {  // fill!(H, 0) on the getH view (arnoldi.jl:232)
+        for (int j = 0; j < m + aug; ++j)
+            for (int i = 0; i < m + 1; ++i) H[(size_t)j * ldh + i] = 0.0;
+    } else if (*beta == 0.0) {
+        return B200K_OK;  // iszero(Ks.beta) && return Ks (arnoldi.jl:366)
+    }
+    KrylovCall c;
+    c.op = op;
+    c.b = b;
+    c.b_stride = 0;
+    c.nprob = 1;
+    c.V = V;
+    c.ldv = ldv;
+    c.V_stride = 0;
+    c.m = m;
+    c.lanczos = herm ? 1 : 0;
+    // lanczos! ignores `init` for its loop but still skips firststep! when init != 0 (arnoldi.jl:468-480)
+    c.j0 = herm ? (o->init == 0 ? 0 : 1) : o->init;
+    c.iop = o->iop;
+    c.tol = o->tol;
+    c.p = p;
+    c.B = o->B;
+    c.ldb = o->ldb;
+    double btail[MAXP];
+    if (p > 0) make_btail(p, o->t, o->mu, btail);
+    c.btail_host = btail;
+    c.g = single_geom(h, n);
+    int st = launch_krylov(h, c);
+    if (st) return st;
+    st = fetch_krylov(h, 1, m);
+    if (st) return st;
+    const double *Hh = h->Hh.as<double>();
+    const int ldhd = m + 1;
+    if (o->init == 0) *beta = h->scalh.as<double>()[0];
+    if (*beta == 0.0) return B200K_OK;
+    *m_out = h->stath.as<int>()[0];
+    *breakdown = h->stath.as<int>()[1];
+    const int jc0 = c.j0 == 0 ? 0 : c.j0 - 1;
+    for (int jc = jc0; jc < *m_out; ++jc)
+        for (int i = 0; i <= jc + 1; ++i) H[(size_t)jc * ldh + i] = Hh[(size_t)jc * ldhd + i];
+    if (herm) {  // copyto!(@diagview(H, 1), v[1:end-1]) (arnoldi.jl:488)
+        for (int i = 0; i + 1 < m; ++i) H[(size_t)(i + 1) * ldh + i] = H[(size_t)i * ldh + i + 1];
+    }
+    return B200K_OK;
+}
+
+int expv_ks_core(b200k_context *h, double t, const double *V, long long ldv, long long nrows, const double *H,
+                 int ldh, int m, double beta, double *w) {
+    if (m < 1) return fail(h, B200K_EARG, "m must be >= 1");
+    if (ldv < nrows) return fail(h, B200K_EDIM, "Dimension mismatch");
+    if (beta == 0.0) {  // w .= 0
+        CK(h, cudaMemsetAsync(w, 0, (size_t)nrows * 8, h->stream));
+        return B200K_OK;
+    }
+    std::vector<double> y(m);
+    int st = expv_small(h, t, H, ldh, m, y.data());
+    if (st) return st;
+    return launch_project(h, V, ldv, nrows, m, beta, y.data(), m, 1, w, nrows, nullptr);
+}
+
+int phiv_ks_core(b200k_context *h, double t, const double *V, long long ldv, long long nrows, const double *H,
+                 int ldh, int m, double beta, int k, int correct, double *W, long long ldw, double *errest) {
+    if (m < 1 || k < 1) return fail(h, B200K_EARG, "m >= 1 and k >= 1 required");
+    if (ldv < nrows || ldw < nrows) return fail(h, B200K_EDIM, "Dimension mismatch");
+    std::vector<double> Hc((size_t)m * m), e(m, 0.0), C2((size_t)m * (k + 1));
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) Hc[(size_t)j * m + i] = t * H[(size_t)j * ldh + i];
+    e[0] = 1.0;
+    const int st = smallmat::phiv_dense(m, Hc.data(), m, e.data(), k, C2.data(), m, h->expwork);
+    if (st) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
+    const double hlast = H[(size_t)(m - 1) * ldh + m];  // H[end, end] of the (m+1) x m view
+    std::vector<double> corr(k + 1, 0.0);
+    if (correct) {
+        const double betah = beta * hlast * t;
+        for (int i = 1; i <= k; ++i) corr[i - 1] = betah * C2[(size_t)i * m + (m - 1)];
+    }
+    if (errest) *errest = std::fabs(beta * hlast * t * C2[(size_t)k * m + (m - 1)]);
+    if (beta == 0.0) {
+        // the reference multiplies an uninitialised V by zero here; we return zeros
+        for (int c = 0; c <= k; ++c) CK(h, cudaMemsetAsync(W + (size_t)c * ldw, 0, (size_t)nrows * 8, h->stream));
+        return B200K_OK;
+    }
+    return launch_project(h, V, ldv, nrows, m, beta, C2.data(), m, k + 1, W, ldw, correct ? corr.data() : nullptr);
+}
+
+int ensure_internal_ks(b200k_context *h, long long nrows, int m, long long *ldv) {
+    *ldv = round_up(nrows, 16);
+    CK(h, h->V.ensure((size_t)(*ldv) * (m + 1) * 8));
+    h->H.assign((size_t)(m + 2) * (m + 2), 0.0);
+    return B200K_OK;
+}
+
+}  // namespace
+
+// ====================================================================================================
+extern "C" {
+
+int b200k_version(void) { return B200K_VERSION; }
+
+const char *b200k_status_string(int s) {
+    switch (s) {
+        case B200K_OK: return "ok";
+        case B200K_EDIM: return "dimension mismatch";
+        case B200K_EARG: return "invalid argument";
+        case B200K_ESINGULAR: return "singular matrix in the small dense phase";
+        case B200K_ECUDA: return "CUDA error";
+        case B200K_ECOMM: return "communicator error";
+        case B200K_EUNSUPPORTED: return "unsupported configuration";
+        case B200K_ENOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+void b200k_krylov_opts_default(b200k_krylov_opts *o) {
+    std::memset(o, 0, sizeof(*o));
+    o->m = 30;
+    o->tol = 1.0e-7;
+    o->iop = 0;
+    o->hermitian = -1;
+    o->init = 0;
+    o->p = 0;
+    o->B = nullptr;
+    o->ldb = 0;
+    o->t = NAN;
+    o->mu = NAN;
+}
+
+void b200k_kiops_opts_default(b200k_kiops_opts *o) {
+    o->mmin = 10;
+    o->mmax = 128;
+    o->m = 10;
+    o->tol = 1.0e-7;
+    o->iop = 2;
+    o->hermitian = -1;
+    o->task1 = 0;
+    o->opnorm = NAN;
+}
+
+int b200k_create(b200k_handle_t *out, int device, void *stream) {
+    if (!out) return B200K_EARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return B200K_ECUDA;  // no CPU fallback
+    if (device < 0 || device >= ndev) return B200K_EARG;
+    if (cudaSetDevice(device) != cudaSuccess) return B200K_ECUDA;
+    b200k_context *h = new b200k_context();
+    h->device = device;
+    h->stream = (cudaStream_t)stream;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete h;
+        return B200K_ECUDA;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch ||
+        cudaFuncSetAttribute((const void *)krylov_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_LIMIT) != cudaSuccess) {
+        delete h;
+        return B200K_ECUDA;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, krylov_persistent_kernel, NT, SMEM_LIMIT) !=
+            cudaSuccess ||
+        per_sm < 1) {
+        delete h;
+        return B200K_ECUDA;
+    }
+    h->max_ctas = std::min(h->sm_count, CPAD);  // one CTA per SM
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+    *out = h;
+    return B200K_OK;
+}
+
+int b200k_destroy(b200k_handle_t h) {
+    if (!h) return B200K_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
+                      &h->Y, &h->corr, &h->mvec, &h->betavec, &h->tmp, &h->V, &h->bdev, &h->wdev};
+    for (DevBuf *b : bufs) b->release();
+    HostBuf *hb[] = {&h->Hh, &h->scalh, &h->stath, &h->Yh};
+    for (HostBuf *b : hb) b->release();
+    for (int i = 0; i < 4; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+    return B200K_OK;
+}
+
+int b200k_set_stream(b200k_handle_t h, void *stream) {
+    if (!h) return B200K_EARG;
+    h->stream = (cudaStream_t)stream;
+    return B200K_OK;
+}
+
+int b200k_synchronize(b200k_handle_t h) {
+    if (!h) return B200K_EARG;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return B200K_OK;
+}
+
+const char *b200k_last_error(b200k_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+int b200k_device_info(b200k_handle_t h, int *sm_count, int *max_team, int64_t *launches) {
+    if (!h) return B200K_EARG;
+    if (sm_count) *sm_count = h->sm_count;
+    if (max_team) *max_team = h->max_ctas;
+    if (launches) *launches = h->launches;
+    return B200K_OK;
+}
+
+int b200k_set_timing(b200k_handle_t h, int enabled) {
+    if (!h) return B200K_EARG;
+    h->timing = enabled ? 1 : 0;
+    return B200K_OK;
+}
+
+int b200k_last_timing(b200k_handle_t h, float *krylov_ms, float *project_ms) {
+    if (!h) return B200K_EARG;
+    if (h->timing) {
+        cudaEventSynchronize(h->ev[1]);
+        cudaEventElapsedTime(&h->krylov_ms, h->ev[0], h->ev[1]);
+        if (cudaEventQuery(h->ev[3]) == cudaSuccess) cudaEventElapsedTime(&h->project_ms, h->ev[2], h->ev[3]);
+    }
+    if (krylov_ms) *krylov_ms = h->krylov_ms;
+    if (project_ms) *project_ms = h->project_ms;
+    return B200K_OK;
+}
+
+// ---- operators ---------------------------------------------------------------------------------------
+int b200k_op_csr_create(b200k_handle_t h, int64_t n, int64_t nnz, const int32_t *rowptr, const int32_t *colind,
+                        const double *val, int index_base, int location, b200k_op_t *out) {
+    if (!h || !out) return B200K_EARG;
+    *out = nullptr;
+    if (n < 1 || nnz < 0 || !rowptr || (nnz > 0 && (!colind || !val)))
+        return fail(h, B200K_EARG, "invalid CSR description");
+    if (n > 2000000000LL || nnz > 2000000000LL) return fail(h, B200K_EUNSUPPORTED, "int32 CSR indices only");
+    if (index_base != 0 && index_base != 1) return fail(h, B200K_EARG, "index_base must be 0 or 1");
+    CK(h, cudaSetDevice(h->device));
+    b200k_operator *op = new b200k_operator();
+    op->ctx = h;
+    op->kind = 0;
+    op->n = n;
+    op->nnz = nnz;
+    const size_t pad = 64;
+    cudaError_t e = op->rowptr.ensure((size_t)(n + 1 + pad) * 4);
+    if (e == cudaSuccess) e = op->colind.ensure((size_t)(nnz + pad) * 4);
+    if (e == cudaSuccess) e = op->val.ensure((size_t)(nnz + pad) * 8);
+    if (e != cudaSuccess) {
+        delete op;
+        return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+    }
+    const cudaMemcpyKind kind = location == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    cudaMemsetAsync(op->colind.p, 0, op->colind.cap, h->stream);
+    cudaMemsetAsync(op->val.p, 0, op->val.cap, h->stream);
+    cudaMemcpyAsync(op->rowptr.p, rowptr, (size_t)(n + 1) * 4, kind, h->stream);
+    if (nnz > 0) {
+        cudaMemcpyAsync(op->colind.p, colind, (size_t)nnz * 4, kind, h->stream);
+        cudaMemcpyAsync(op->val.p, val, (size_t)nnz * 8, kind, h->stream);
+    }
+    if (index_base == 1) {
+        rebase_kernel<<<256, 256, 0, h->stream>>>(op->rowptr.as<int>(), op->rowptr.as<int>(), n + 1, 1);
+        if (nnz > 0) rebase_kernel<<<1024, 256, 0, h->stream>>>(op->colind.as<int>(), op->colind.as<int>(), nnz, 1);
+    }
+    // row statistics, ishermitian(A), opnorm(A, Inf)
+    e = h->tmp.ensure(64);
+    if (e != cudaSuccess) {
+        delete op;
+        return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(h->tmp.p, 0, 64, h->stream);
+    int *d_max = h->tmp.as<int>();
+    int *d_nonsym = d_max + 1;
+    double *d_norm = reinterpret_cast<double *>(h->tmp.as<char>() + 16);
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4096);
+    csr_analyze_kernel<<<blocks, 256, 0, h->stream>>>((int)n, op->rowptr.as<int>(), op->colind.as<int>(),
+                                                      op->val.as<double>(), d_max, d_nonsym, d_norm);
+    struct {
+        int maxnnz, nonsym;
+        double pad0, norm;
+    } res;
+    char raw[32];
+    e = cudaMemcpyAsync(raw, h->tmp.p, 32, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        delete op;
+        return fail(h, B200K_ECUDA, cudaGetErrorString(e));
+    }
+    std::memcpy(&res.maxnnz, raw, 4);
+    std::memcpy(&res.nonsym, raw + 4, 4);
+    std::memcpy(&res.norm, raw + 16, 8);
+    op->max_row_nnz = res.maxnnz;
+    op->is_herm = res.nonsym ? 0 : 1;
+    op->opnorm_inf = res.norm;
+    h->launches += 1;
+    *out = op;
+    return B200K_OK;
+}
+
+int b200k_op_dense_create(b200k_handle_t h, int64_t n, const double *A, int64_t lda, int location,
+                          b200k_op_t *out) {
+    if (!h || !out) return B200K_EARG;
+    *out = nullptr;
+    if (n < 1 || !A || lda < n) return fail(h, B200K_EARG, "invalid dense description");
+    if (n > 2000000000LL) return fail(h, B200K_EUNSUPPORTED, "n too large");
+    CK(h, cudaSetDevice(h->device));
+    b200k_operator *op = new b200k_operator();
+    op->ctx = h;
+    op->kind = 1;
+    op->n = n;
+    op->nnz = n * n;
+    if (location == 1) {
+        const long long ld = round_up(n, 2);
+        cudaError_t e = op->Aown.ensure((size_t)ld * n * 8);
+        if (e != cudaSuccess) {
+            delete op;
+            return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+        }
+        e = cudaMemcpy2DAsync(op->Aown.p, (size_t)ld * 8, A, (size_t)lda * 8, (size_t)n * 8, (size_t)n,
+                              cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) {
+            delete op;
+            return fail(h, B200K_ECUDA, cudaGetErrorString(e));
+        }
+        op->Ad = op->Aown.as<double>();
+        op->lda = ld;
+    } else {
+        op->Ad = A;  // aliased: the caller keeps the matrix alive (it is 8 n^2 bytes)
+        op->lda = lda;
+    }
+    cudaError_t e = h->tmp.ensure(64);
+    if (e != cudaSuccess) {
+        delete op;
+        return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(h->tmp.p, 0, 64, h->stream);
+    int *d_nonsym = h->tmp.as<int>() + 1;
+    double *d_norm = reinterpret_cast<double *>(h->tmp.as<char>() + 16);
+    dense_analyze_kernel<<<(int)std::min<int64_t>((n + 127) / 128, 2048), 128, 0, h->stream>>>(
+        (int)n, op->Ad, op->lda, d_nonsym, d_norm);
+    char raw[32];
+    e = cudaMemcpyAsync(raw, h->tmp.p, 32, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        delete op;
+        return fail(h, B200K_ECUDA, cudaGetErrorString(e));
+    }
+    int nonsym;
+    double norm;
+    std::memcpy(&nonsym, raw + 4, 4);
+    std::memcpy(&norm, raw + 16, 8);
+    op->is_herm = nonsym ? 0 : 1;
+    op->opnorm_inf = norm;
+    h->launches += 1;
+    *out = op;
+    return B200K_OK;
+}
+
+int b200k_op_destroy(b200k_op_t op) {
+    if (!op) return B200K_OK;
+    if (op->ctx) cudaSetDevice(op->ctx->device);
+    op->rowptr.release();
+    op->colind.release();
+    op->val.release();
+    op->Aown.release();
+    delete op;
+    return B200K_OK;
+}
+
+int b200k_op_info(b200k_op_t op, int64_t *n, int64_t *nnz, int *kind, int *is_hermitian, double *opnorm_inf) {
+    if (!op) return B200K_EARG;
+    if (n) *n = op->n;
+    if (nnz) *nnz = op->nnz;
+    if (kind) *kind = op->kind;
+    if (is_hermitian) *is_hermitian = op->is_herm;
+    if (opnorm_inf) *opnorm_inf = op->opnorm_inf;
+    return B200K_OK;
+}
+
+int b200k_op_apply(b200k_handle_t h, b200k_op_t op, const double *x, double *y) {
+    if (!h || !op || !x || !y) return B200K_EARG;
+    if (op->kind == 0) {
+        const int blocks = (int)std::min<long long>((op->n + 7) / 8, (long long)h->sm_count * 16);
+        csr_apply_kernel<<<blocks, 256, 0, h->stream>>>((int)op->n, op->rowptr.as<int>(), op->colind.as<int>(),
+                                                        op->val.as<double>(), x, y);
+    } else {
+        const int blocks = (int)std::min<long long>((op->n + 63) / 64, (long long)h->sm_count * 8);
+        dense_apply_kernel<<<blocks, 256, 0, h->stream>>>((int)op->n, op->Ad, op->lda, x, y);
+    }
+    CK(h, cudaGetLastError());
+    h->launches += 1;
+    return B200K_OK;
+}
+
+// ---- arnoldi! / expv! / phiv! --------------------------------------------------------------------------
+int b200k_arnoldi(b200k_handle_t h, b200k_op_t op, const double *b, const b200k_krylov_opts *opts, double *V,
+                  int64_t ldv, int maxiter, double *H, int ldh, double *beta, int *m_out, int *breakdown) {
+    if (!h || !op || !b || !opts || !V || !H || !beta || !m_out || !breakdown) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    return arnoldi_core(h, op, b, opts, V, ldv, maxiter, H, ldh, beta, m_out, breakdown);
+}
+
+int b200k_expv_ks(b200k_handle_t h, double t, const double *V, int64_t ldv, int64_t nrows, const double *H,
+                  int ldh, int m, double beta, double *w) {
+    if (!h || !V || !H || !w) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    return expv_ks_core(h, t, V, ldv, nrows, H, ldh, m, beta, w);
+}
+
+int b200k_phiv_ks(b200k_handle_t h, double t, const double *V, int64_t ldv, int64_t nrows, const double *H,
+                  int ldh, int m, double beta, int k, int correct, double *W, int64_t ldw, double *errest) {
+    if (!h || !V || !H || !W) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    return phiv_ks_core(h, t, V, ldv, nrows, H, ldh, m, beta, k, correct, W, ldw, errest);
+}
+
+int b200k_expv(b200k_handle_t h, b200k_op_t op, double t, const double *b, const b200k_krylov_opts *opts,
+               double *w, int *m_out, int *breakdown, double *beta_out) {
+    if (!h || !op || !b || !opts || !w) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    if (opts->p != 0 || opts->init != 0) return fail(h, B200K_EARG, "one-shot expv takes a plain operator, init = 0");
+    b200k_krylov_opts o = *opts;
+    o.m = (int)std::min<long long>(o.m, op->n);
+    long long ldv;
+    int st = ensure_internal_ks(h, op->n, o.m, &ldv);
+    if (st) return st;
+    double beta = 0.0;
+    int mo = 0, bd = 0;
+    const int ldh = o.m + 2;
+    st = arnoldi_core(h, op, b, &o, h->V.as<double>(), ldv, o.m, h->H.data(), ldh, &beta, &mo, &bd);
+    if (st) return st;
+    if (m_out) *m_out = mo;
+    if (breakdown) *breakdown = bd;
+    if (beta_out) *beta_out = beta;
+    return expv_ks_core(h, t, h->V.as<double>(), ldv, op->n, h->H.data(), ldh, mo, beta, w);
+}
+
+int b200k_expv_host(b200k_handle_t h, b200k_op_t op, double t, const double *b_host,
+                    const b200k_krylov_opts *opts, double *w_host, int *m_out, int *breakdown) {
+    if (!h || !op || !b_host || !opts || !w_host) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)op->n * 8;
+    CK(h, h->bdev.ensure(bytes));
+    CK(h, h->wdev.ensure(bytes));
+    CK(h, cudaMemcpyAsync(h->bdev.p, b_host, bytes, cudaMemcpyHostToDevice, h->stream));
+    const int st = b200k_expv(h, op, t, h->bdev.as<double>(), opts, h->wdev.as<double>(), m_out, breakdown, nullptr);
+    if (st) return st;
+    CK(h, cudaMemcpyAsync(w_host, h->wdev.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return B200K_OK;
+}
+
+int b200k_phiv(b200k_handle_t h, b200k_op_t op, double t, const double *b, int k, const b200k_krylov_opts *opts,
+               int correct, double *W, int64_t ldw, double *errest, int *m_out, int *breakdown) {
+    if (!h || !op || !b || !opts || !W) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    if (opts->p != 0 || opts->init != 0) return fail(h, B200K_EARG, "one-shot phiv takes a plain operator, init = 0");
+    b200k_krylov_opts o = *opts;
+    o.m = (int)std::min<long long>(o.m, op->n);
+    long long ldv;
+    int st = ensure_internal_ks(h, op->n, o.m, &ldv);
+    if (st) return st;
+    double beta = 0.0;
+    int mo = 0, bd = 0;
+    const int ldh = o.m + 2;
+    st = arnoldi_core(h, op, b, &o, h->V.as<double>(), ldv, o.m, h->H.data(), ldh, &beta, &mo, &bd);
+    if (st) return st;
+    if (m_out) *m_out = mo;
+    if (breakdown) *breakdown = bd;
+    return phiv_ks_core(h, t, h->V.as<double>(), ldv, op->n, h->H.data(), ldh, mo, beta, k, correct, W, ldw, errest);
+}
+
+// ---- batched independent expv ----------------------------------------------------------------------------
+int b200k_expv_batched(b200k_handle_t h, b200k_op_t op, int nb, const double *t, const double *Bv, int64_t ldbv,
+                       const b200k_krylov_opts *opts, double *W, int64_t ldw, int *m_out, int *breakdown) {
+    if (!h || !op || !t || !Bv || !opts || !W || nb < 1) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    if (opts->p != 0 || opts->init != 0) return fail(h, B200K_EARG, "batched expv takes a plain operator, init = 0");
+    const long long n = op->n;
+    if (ldbv < n || ldw < n) return fail(h, B200K_EDIM, "Dimension mismatch");
+    const int m = (int)std::min<long long>(opts->m, n);
+    if (m < 1 || m >= MAXCOL) return fail(h, B200K_EUNSUPPORTED, "Krylov dimension m must be in 1..255");
+    int herm = opts->hermitian;
+    if (herm < 0) herm = op->is_herm;
+    const long long ldv = round_up(n, 16);
+    const long long vstride = ldv * (m + 1);
+    CK(h, h->V.ensure((size_t)vstride * nb * 8));
+    KrylovCall c;
+    c.op = op;
+    c.b = Bv;
+    c.b_stride = ldbv;
+    c.nprob = nb;
+    c.V = h->V.as<double>();
+    c.ldv = ldv;
+    c.V_stride = vstride;
+    c.m = m;
+    c.j0 = 0;
+    c.iop = opts->iop;
+    c.lanczos = herm ? 1 : 0;
+    c.tol = opts->tol;
+    c.p = 0;
+    c.B = nullptr;
+    c.ldb = 0;
+    c.btail_host = nullptr;
+    c.g = batch_geom(h, n, nb);
+    int st = launch_krylov(h, c);
+    if (st) return st;
+    st = fetch_krylov(h, nb, m);
+    if (st) return st;
+    // small dense phase per problem on the host, then one batched projection launch
+    const int ldhd = m + 1;
+    const size_t hstride = (size_t)ldhd * (m + 1);
+    CK(h, h->Yh.ensure((size_t)nb * m * 8 + (size_t)nb * 16));
+    double *Yh = h->Yh.as<double>();
+    double *betah = Yh + (size_t)nb * m;
+    int *mh = reinterpret_cast<int *>(betah + nb);
+    std::vector<double> Hm((size_t)ldhd * (m + 1));
+    for (int i = 0; i < nb; ++i) {
+        const double beta = h->scalh.as<double>()[i * 4];
+        int mo = h->stath.as<int>()[i * 4 + 0];
+        const int bd = h->stath.as<int>()[i * 4 + 1];
+        if (beta == 0.0) {
+            mo = m;
+        }
+        if (m_out) m_out[i] = mo;
+        if (breakdown) breakdown[i] = beta == 0.0 ? 0 : bd;
+        betah[i] = beta;
+        mh[i] = mo;
+        double *y = Yh + (size_t)i * m;
+        std::fill(y, y + m, 0.0);
+        if (beta == 0.0) continue;
+        std::memcpy(Hm.data(), h->Hh.as<double>() + i * hstride, hstride * 8);
+        if (herm)
+            for (int q = 0; q + 1 < m; ++q) Hm[(size_t)(q + 1) * ldhd + q] = Hm[(size_t)q * ldhd + q + 1];
+        st = expv_small(h, t[i], Hm.data(), ldhd, mo, y);
+        if (st) return st;
+    }
+    CK(h, h->Y.ensure((size_t)nb * m * 8));
+    CK(h, h->betavec.ensure((size_t)nb * 8));
+    CK(h, h->mvec.ensure((size_t)nb * 4));
+    CK(h, cudaMemcpyAsync(h->Y.p, Yh, (size_t)nb * m * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->betavec.p, betah, (size_t)nb * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->mvec.p, mh, (size_t)nb * 4, cudaMemcpyHostToDevice, h->stream));
+    ProjectParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.V = h->V.as<double>();
+    P.ldv = ldv;
+    P.V_stride = vstride;
+    P.nrows = n;
+    P.Y = h->Y.as<double>();
+    P.ldy = m;
+    P.Y_stride = m;
+    P.mvec = h->mvec.as<int>();
+    P.betavec = h->betavec.as<double>();
+    P.m = m;
+    P.nc = 1;
+    P.W = W;
+    P.ldw = ldw;
+    P.W_stride = ldw;
+    P.vec2 = (n % 2 == 0) && (ldw % 2 == 0) && aligned16(W);
+    const long long units = P.vec2 ? n / 2 : n;
+    int gx = (int)std::min<long long>((units + PROJ_NT - 1) / PROJ_NT, 64);
+    if (gx < 1) gx = 1;
+    if (h->timing) CK(h, cudaEventRecord(h->ev[2], h->stream));
+    for (int base = 0; base < nb; base += 32768) {  // gridDim.z limit is 65535
+        const int cnt = std::min(nb - base, 32768);
+        ProjectParams Q = P;
+        Q.V += (long long)base * vstride;
+        Q.Y += (long long)base * m;
+        Q.mvec += base;
+        Q.betavec += base;
+        Q.W += (long long)base * ldw;
+        project_kernel<<<dim3(gx, 1, cnt), PROJ_NT, 0, h->stream>>>(Q);
+        h->launches += 1;
+    }
+    CK(h, cudaGetLastError());
+    if (h->timing) CK(h, cudaEventRecord(h->ev[3], h->stream));
+    return B200K_OK;
+}
+
+// ---- kiops (src/kiops.jl:57-326) -------------------------------------------------------------------------
+int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out, int tau_is_row, const double *U,
+                int64_t ldu, int ppo, const b200k_kiops_opts *ko, double *W, int64_t ldw, int64_t *stats) {
+    if (!h || !op || !tau_out || !U || !ko || !W || ntau < 1 || ppo < 1) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    const long long n = op->n;
+    if (ldu < n || ldw < n) return fail(h, B200K_EDIM, "Dimension mismatch");
+    int p = ppo - 1;
+    const bool pad_col = (p == 0);  // u = [u zero(u)]
+    if (pad_col) p = 1;
+    if (p > MAXP) return fail(h, B200K_EUNSUPPORTED, "kiops supports at most 16 phi columns");
+    const int mmin = ko->mmin, mmax = ko->mmax;
+    int m = ko->m > 0 ? ko->m : std::min(mmin, mmax);
+    if (mmax >= MAXCOL - 1) return fail(h, B200K_EUNSUPPORTED, "mmax must be < 255");
+    int herm = ko->hermitian;
+    if (herm < 0) herm = op->is_herm;
+    const int numSteps = tau_is_row ? ntau : 1;
+    if (numSteps > 1)  // length(w) == size(A,1) fails in checkdims for a multi-column w (arnoldi.jl:217)
+        return fail(h, B200K_EDIM, "DimensionMismatch: kiops with several output times (as in the reference)");
+    const double tau_last = tau_out[ntau - 1];
+    const double sgn = (tau_last > 0) - (tau_last < 0);
+    double tau_now = 0.0;
+    const double tau_end = std::fabs(tau_last);
+    int j = 0;
+
+    // Krylov storage: V (n+p) x (cap+1) grown like resize! (arnoldi.jl:80-93, contents preserved)
+    const long long ldv = round_up(n + p, 16);
+    int cap = m;
+    DevBuf Vbuf, Bbuf;
+    CK(h, Vbuf.ensure((size_t)ldv * (cap + 1) * 8));
+    const int ldh = mmax + 2;
+    std::vector<double> H((size_t)ldh * ldh, 0.0);
+    int Ks_m = m;
+
+    // w = zeros(n, numSteps); w[:, 1] = u[:, 1]
+    CK(h, cudaMemcpyAsync(W, U, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+
+    // normalisation factors (kiops.jl:94-102)
+    double nu = 1.0, mu = 1.0;
+    const long long ldbm = round_up(n, 2);
+    cudaError_t e = Bbuf.ensure((size_t)ldbm * p * 8);
+    if (e != cudaSuccess) {
+        Vbuf.release();
+        return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+    }
+    auto cleanup = [&]() {
+        Vbuf.release();
+        Bbuf.release();
+    };
+    if (pad_col) {
+        cudaMemsetAsync(Bbuf.p, 0, (size_t)ldbm * p * 8, h->stream);
+    } else {
+        const int nblk = 1024;
+        e = h->tmp.ensure((size_t)nblk * 8);
+        if (e != cudaSuccess) {
+            cleanup();
+            return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+        }
+        abs_sum_kernel<<<nblk, 256, 0, h->stream>>>(n, p, U + ldu, ldu, h->tmp.as<double>());
+        std::vector<double> part(nblk);
+        cudaMemcpyAsync(part.data(), h->tmp.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, h->stream);
+        e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) {
+            cleanup();
+            return fail(h, B200K_ECUDA, cudaGetErrorString(e));
+        }
+        double normU = 0.0;
+        for (double v : part) normU += v;
+        if (normU > 0) {
+            const double ex = std::ceil(std::log2(normU));
+            nu = std::exp2(-ex);
+            mu = std::exp2(ex);
+        }
+        flip_scale_kernel<<<1024, 256, 0, h->stream>>>(n, p, U, ldu, nu, Bbuf.as<double>(), ldbm);
+        h->launches += 2;
+    }
+
+    double tau = tau_end;
+    double gamma, gamma_mmax;
+    if (tau_end > 1) {
+        gamma = 0.2;
+        gamma_mmax = 0.1;
+    } else {
+        gamma = 0.9;
+        gamma_mmax = 0.6;
+    }
+    const double delta = 1.4;
+    int oldm = -1;
+    double oldtau = NAN, omega = NAN;
+    bool orderold = true, kestold = true;
+    double order = 0.0, kest = 2.0;
+    int l = 1;
+    int64_t step = 0, reject = 0, ireject = 0, exps = 0;
+    const int64_t krystep = 0;
+    double beta = 0.0;
+    std::vector<double> F, Hc;
+    int status = B200K_OK;
+
+    while (tau_now < tau_end) {
+        const int oldj = Ks_m;
+        if (m > cap) {  // resize!(Ks, m)
+            DevBuf nv;
+            e = nv.ensure((size_t)ldv * (m + 1) * 8);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(nv.p, Vbuf.p, (size_t)ldv * (cap + 1) * 8, cudaMemcpyDeviceToDevice, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) {
+                nv.release();
+                cleanup();
+                return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+            }
+            Vbuf.release();
+            Vbuf = nv;
+            cap = m;
+        }
+        b200k_krylov_opts o;
+        b200k_krylov_opts_default(&o);
+        o.m = m;
+        o.tol = 1.0e-7;  // kiops does not forward its tol to arnoldi! (kiops.jl:138-141)
+        o.iop = ko->iop;
+        o.hermitian = herm;
+        o.init = j;
+        o.p = p;
+        o.B = Bbuf.as<double>();
+        o.ldb = ldbm;
+        o.t = tau_now;
+        o.mu = mu;
+        int mo = 0, bd = 0;
+        status = arnoldi_core(h, op, W + (size_t)(l - 1) * ldw, &o, Vbuf.as<double>(), ldv, cap, H.data(), ldh,
+                              &beta, &mo, &bd);
+        if (status) break;
+        Ks_m = (beta == 0.0) ? m : mo;
+        j = Ks_m;
+        bool happy = j < oldj;
+        // phi_1 column for the error estimate; h_{j+1,j} removed while exponentiating (kiops.jl:149-160)
+        H[(size_t)j * ldh + 0] = 1.0;
+        const double nrm = H[(size_t)(j - 1) * ldh + j];
+        H[(size_t)(j - 1) * ldh + j] = 0.0;
+        const int N = j + 1;
+        F.assign((size_t)N * N, 0.0);
+        for (int c = 0; c < N; ++c)
+            for (int r = 0; r < N; ++r) F[(size_t)c * N + r] = sgn * tau * H[(size_t)c * ldh + r];
+        if (smallmat::expm_higham2005base(N, F.data(), h->expwork)) {
+            status = fail(h, B200K_ESINGULAR, "SingularException(0) in kiops");
+            break;
+        }
+        exps += 1;
+        H[(size_t)(j - 1) * ldh + j] = nrm;
+        double tau_new;
+        int m_new;
+        if (happy) {
+            omega = 0;
+            tau_new = std::min(tau_end - (tau_now + tau), tau);
+            m_new = m;
+            happy = false;
+        } else {
+            const double err = std::fabs(beta * nrm * F[(size_t)j * N + (j - 1)]);
+            const double oldomega = omega;
+            omega = tau_end * err / (tau * ko->tol);
+            if (m == oldm && tau != oldtau && ireject >= 1) {
+                order = std::max(1.0, std::log(omega / oldomega) / std::log(tau / oldtau));
+                orderold = false;
+            } else if (orderold || ireject == 0) {
+                orderold = true;
+                order = j / 4.0;
+            } else {
+                orderold = true;
+            }
+            if (m != oldm && tau == oldtau && ireject >= 1) {
+                kest = std::max(1.1, std::pow(omega / oldomega, 1.0 / (oldm - m)));
+                kestold = false;
+            } else if (kestold || ireject == 0) {
+                kestold = true;
+                kest = 2;
+            } else {
+                kestold = true;
+            }
+            const double remaining_time = omega > delta ? tau_end - tau_now : tau_end - (tau_now + tau);
+            const double same_tau = std::min(remaining_time, tau);
+            double tau_opt = tau * std::pow(gamma / omega, 1.0 / order);
+            tau_opt = std::min(remaining_time, std::max(tau / 5, std::min(5 * tau, tau_opt)));
+            // m_opt = ceil(Int, ...) throws InexactError in Julia for NaN/Inf; clamp instead
+            double mo_d = std::ceil(j + std::log(omega / gamma) / std::log(kest));
+            if (!(mo_d == mo_d)) mo_d = mmax;
+            mo_d = std::max(-1.0e9, std::min(1.0e9, mo_d));
+            int m_opt = (int)mo_d;
+            // quirk kept: `3 ÷ 4 * m` == 0 and `cld(4, 3) * m` == 2m (kiops.jl:210)
+            m_opt = std::max(mmin, std::min(mmax, std::max(0, std::min(m_opt, 2 * m))));
+            if (j == mmax) {
+                if (omega > delta) {
+                    m_new = j;
+                    tau_new = tau * std::pow(gamma_mmax / omega, 1.0 / order);
+                    tau_new = std::min(tau_end - tau_now, std::max(tau / 5, tau_new));
+                } else {
+                    tau_new = tau_opt;
+                    m_new = m;
+                }
+            } else {
+                m_new = m_opt;
+                tau_new = same_tau;
+            }
+        }
+        if (omega <= delta) {  // kiops_update_solution! (kiops.jl:283-326)
+            reject += ireject;
+            step += 1;
+            int blownTs = 0;
+            const double nextT = tau_now + tau;
+            for (int k = l; k <= numSteps; ++k)
+                if (std::fabs(tau_out[k - 1]) < std::fabs(nextT)) blownTs += 1;
+            if (blownTs != 0) {
+                cudaMemcpyAsync(W + (size_t)(l + blownTs - 1) * ldw, W + (size_t)(l - 1) * ldw, (size_t)n * 8,
+                                cudaMemcpyDeviceToDevice, h->stream);
+                for (int k = 0; k < blownTs; ++k) {
+                    const double tauPhantom = tau_out[l + k - 1] - tau_now;
+                    Hc.assign((size_t)j * j, 0.0);
+                    for (int c = 0; c < j; ++c)
+                        for (int r = 0; r < j; ++r) Hc[(size_t)c * j + r] = sgn * tauPhantom * H[(size_t)c * ldh + r];
+                    if (smallmat::expm_higham2005base(j, Hc.data(), h->expwork)) {
+                        status = fail(h, B200K_ESINGULAR, "SingularException(0) in kiops");
+                        break;
+                    }
+                    status = launch_project(h, Vbuf.as<double>(), ldv, n, j, beta, Hc.data(), j, 1,
+                                            W + (size_t)(l + k - 1) * ldw, ldw, nullptr);
+                    if (status) break;
+                }
+                if (status) break;
+                l += blownTs;
+            }
+            status = launch_project(h, Vbuf.as<double>(), ldv, n, j, beta, F.data(), N, 1, W + (size_t)(l - 1) * ldw,
+                                    ldw, nullptr);
+            if (status) break;
+            tau_now += tau;
+            j = 0;
+            ireject = 0;
+        } else {
+            ireject += 1;
+            H[(size_t)j * ldh + 0] = 0.0;
+        }
+        oldtau = tau;
+        tau = tau_new;
+        oldm = m;
+        m = m_new;
+    }
+    if (!status && tau_out[0] != 1 && ko->task1 && ntau == 1) {
+        scale_kernel<<<1024, 256, 0, h->stream>>>(n, W + (size_t)(l - 1) * ldw, std::pow(1.0 / tau_out[l - 1], p));
+        h->launches += 1;
+    }
+    cudaError_t es = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (status) return status;
+    if (es != cudaSuccess) return fail(h, B200K_ECUDA, cudaGetErrorString(es));
+    if (stats) {
+        stats[0] = step;
+        stats[1] = reject;
+        stats[2] = krystep;
+        stats[3] = exps;
+        stats[4] = m;
+    }
+    return B200K_OK;
+}
+
+// ---- small dense (host) ----------------------------------------------------------------------------------
+int b200k_exponential(int n, double *A, int lda) {
+    if (n < 0 || !A || lda < n) return B200K_EARG;
+    std::vector<double> C((size_t)n * n);
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) C[(size_t)j * n + i] = A[(size_t)j * lda + i];
+    smallmat::ExpWork w;
+    const int st = smallmat::expm_higham2005base(n, C.data(), w);
+    if (st) return B200K_ESINGULAR;
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) A[(size_t)j * lda + i] = C[(size_t)j * n + i];
+    return B200K_OK;
+}
+
+int b200k_expv_small(int m, const double *H, int ldh, double t, double *y, int *branch) {
+    if (m < 1 || !H || !y || ldh < m) return B200K_EARG;
+    if (branch) *branch = smallmat::is_exactly_symmetric(m, H, ldh) ? 1 : 0;
+    b200k_context tmp;
+    return expv_small(&tmp, t, H, ldh, m, y);
+}
+
+int b200k_phiv_dense(int m, const double *A, int lda, const double *v, int k, double *w, int ldw) {
+    if (m < 1 || k < 1 || !A || !v || !w || lda < m || ldw < m) return B200K_EARG;
+    smallmat::ExpWork work;
+    const int st = smallmat::phiv_dense(m, A, lda, v, k, w, ldw, work);
+    return st ? B200K_ESINGULAR : B200K_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+/*
+ * b200krylov.h -- C ABI of the B200-native Krylov expmv / phiv engine.
+ *
+ * Drop-in boundary for the hot path of SciML/ExponentialUtilities.jl v1.35.0
+ * (arnoldi!/lanczos! -> expv/phiv -> kiops).  Every entry point below names the reference
+ * interface it replaces (paths relative to the reference repository root).  A Julia host binds
+ * these with `ccall`; the Python host in
+ * exponentialutilities.jl_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, doubles.  No C++ / torch types cross this boundary.
+ *   - "device" pointers are CUDA device pointers owned by the caller; "host" pointers are ordinary
+ *     host memory.  Matrices are column-major with an explicit leading dimension (Julia layout).
+ *   - Every function returns a b200k_status (0 = OK).  Nothing throws across the ABI.  Happy
+ *     breakdown and beta == 0 are NOT errors (reference: src/arnoldi.jl:370-374,
+ *     src/krylov_phiv.jl:206-213); they are reported through out-parameters.
+ *   - One handle <-> one CUDA stream <-> one host thread at a time.
+ *   - There is no CPU fallback: without a CUDA device b200k_create fails with B200K_ECUDA.
+ */
+#ifndef B200KRYLOV_H
+#define B200KRYLOV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200K_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    B200K_OK = 0,
+    B200K_EDIM = 1,         /* DimensionMismatch / "Dimension mismatch" asserts (arnoldi.jl:217, krylov_phiv.jl:205,625) */
+    B200K_EARG = 2,         /* ArgumentError (krylov_phiv.jl:132,221,630) */
+    B200K_ESINGULAR = 3,    /* SingularException(0) from the Pade solve (exp_baseexp.jl:55) */
+    B200K_ECUDA = 4,        /* CUDA runtime failure, or no device */
+    B200K_ECOMM = 5,        /* multi-GPU communicator failure */
+    B200K_EUNSUPPORTED = 6, /* valid in the reference but not implemented here */
+    B200K_ENOMEM = 7
+} b200k_status;
+
+typedef struct b200k_context *b200k_handle_t;
+typedef struct b200k_operator *b200k_op_t;
+
+/* ---- library / handle ------------------------------------------------------------------- */
+int b200k_version(void);
+/* Static description of an error code (never NULL). */
+const char *b200k_status_string(int status);
+/* device: CUDA ordinal; stream: a cudaStream_t (CUstream) or NULL for the legacy default stream. */
+int b200k_create(b200k_handle_t *h, int device, void *stream);
+int b200k_destroy(b200k_handle_t h);
+int b200k_set_stream(b200k_handle_t h, void *stream);
+int b200k_synchronize(b200k_handle_t h);
+/* Message of the last failure on this handle ("" if none). */
+const char *b200k_last_error(b200k_handle_t h);
+/* Number of SMs / CTAs the persistent kernel uses on this device, and kernels launched so far. */
+int b200k_device_info(b200k_handle_t h, int *sm_count, int *max_team, int64_t *launches);
+
+/* ---- operators: the reference's operator interface (docs/src/interfaces.md:9-36) ------------
+ * size / eltype / mul! / ishermitian / opnorm of a concrete fp64 matrix.  The arrays are copied
+ * into library-owned, 0-based, padded device storage ("operator ingestion"), so the caller may
+ * free its copies afterwards.  `location`: 0 = the pointers are device pointers, 1 = host.
+ * `index_base`: 0 (C/SciPy) or 1 (Julia CuSparseMatrixCSR). */
+int b200k_op_csr_create(b200k_handle_t h, int64_t n, int64_t nnz, const int32_t *rowptr,
+                        const int32_t *colind, const double *val, int index_base, int location,
+                        b200k_op_t *op);
+/* Dense column-major n x n with leading dimension lda (mul!(y, A::Matrix, x), arnoldi.jl:185). */
+int b200k_op_dense_create(b200k_handle_t h, int64_t n, const double *A, int64_t lda, int location,
+                          b200k_op_t *op);
+int b200k_op_destroy(b200k_op_t op);
+/* size(A,1), nnz, kind (0 CSR, 1 dense), LinearAlgebra.ishermitian(A), opnorm(A, Inf). */
+int b200k_op_info(b200k_op_t op, int64_t *n, int64_t *nnz, int *kind, int *is_hermitian,
+                  double *opnorm_inf);
+/* y = A x on device vectors (mul!; used by tests and the matrix-free style callers). */
+int b200k_op_apply(b200k_handle_t h, b200k_op_t op, const double *x, double *y);
+
+/* ---- Krylov factorisation: arnoldi! / lanczos! (src/arnoldi.jl:345-377, 456-490) -----------
+ * Keyword arguments of the reference, same names and defaults. */
+typedef struct {
+    int m;         /* requested Krylov dimension (default min(maxiter, n))               */
+    double tol;    /* happy-breakdown threshold, absolute test beta_j < tol (1e-7)        */
+    int iop;       /* incomplete-orthogonalisation length, 0 = full Arnoldi              */
+    int hermitian; /* 1: lanczos!, 0: arnoldi!, -1: LinearAlgebra.ishermitian(A)         */
+    int init;      /* continue an existing factorisation from column init (0 = start)    */
+    /* augmented operator (A, B) of kiops (arnoldi.jl:191-205, 257-279); p = 0: plain    */
+    int p;             /* number of augmented rows                                       */
+    const double *B;   /* device, n x p column-major (u_flip)                            */
+    int64_t ldb;
+    double t;          /* tau_now                                                        */
+    double mu;
+} b200k_krylov_opts;
+void b200k_krylov_opts_default(b200k_krylov_opts *o);
+
+/* arnoldi!(Ks, A, b; ...).  KrylovSubspace fields are passed piecewise (arnoldi.jl:50-61):
+ *   V      device, (n + p) x (maxiter + 1) column-major, leading dimension ldv   (Ks.V)
+ *   H      HOST,   (maxiter + 1) x (maxiter + [p != 0]) column-major, ld ldh     (Ks.H)
+ *   beta   in (init != 0) / out                                                  (Ks.beta)
+ *   m_out, breakdown                                                             (Ks.m, Ks.wasbreakdown)
+ * b: device vector of length n (for the augmented form: the column w[:, l]).
+ * Requires opts->m <= maxiter (the host-side KrylovSubspace does the resize!, arnoldi.jl:357).
+ * Orthogonalisation is classical Gram-Schmidt fused with the mat-vec (the reference uses
+ * sequential modified Gram-Schmidt, arnoldi.jl:301-304); results agree to rounding, see DESIGN.md.
+ * Returns after H, beta, m_out are valid on the host. */
+int b200k_arnoldi(b200k_handle_t h, b200k_op_t op, const double *b, const b200k_krylov_opts *opts,
+                  double *V, int64_t ldv, int maxiter, double *H, int ldh, double *beta,
+                  int *m_out, int *breakdown);
+
+/* expv!(w, t, Ks) (src/krylov_phiv.jl:200-247): w = beta * V[:, 1:m] * exp(t H[1:m,1:m]) e1.
+ * Exactly-symmetric H -> symmetric-tridiagonal eigen branch (:225-229), else Higham-2005 Pade.
+ * nrows = size(V, 1) (n + p).  w: device, nrows. */
+int b200k_expv_ks(b200k_handle_t h, double t, const double *V, int64_t ldv, int64_t nrows,
+                  const double *H, int ldh, int m, double beta, double *w);
+
+/* _phiv!(w, t, Ks, k, cache, correct) (src/krylov_phiv.jl:620-653).  W: device nrows x (k+1),
+ * leading dimension ldw.  errest (may be NULL) receives |beta * h_{m+1,m} * t * C2[m, k+1]|.
+ * H must hold rows 1..m+1 (h_{m+1,m} is read). */
+int b200k_phiv_ks(b200k_handle_t h, double t, const double *V, int64_t ldv, int64_t nrows,
+                  const double *H, int ldh, int m, double beta, int k, int correct, double *W,
+                  int64_t ldw, double *errest);
+
+/* expv(t, A, b; m, tol, iop, ishermitian) one-shot (src/krylov_phiv.jl:125-144): arnoldi + expv!
+ * with library-owned Krylov storage.  b, w: device vectors of length n.  m_out / breakdown /
+ * beta_out may be NULL. */
+int b200k_expv(b200k_handle_t h, b200k_op_t op, double t, const double *b,
+               const b200k_krylov_opts *opts, double *w, int *m_out, int *breakdown,
+               double *beta_out);
+/* Same call with HOST vectors: copies b in and w out on the handle's stream (end-to-end path). */
+int b200k_expv_host(b200k_handle_t h, b200k_op_t op, double t, const double *b_host,
+                    const b200k_krylov_opts *opts, double *w_host, int *m_out, int *breakdown);
+/* phiv(t, A, b, k; correct, errest) one-shot (src/krylov_phiv.jl:563-570). */
+int b200k_phiv(b200k_handle_t h, b200k_op_t op, double t, const double *b, int k,
+               const b200k_krylov_opts *opts, int correct, double *W, int64_t ldw, double *errest,
+               int *m_out, int *breakdown);
+
+/* nb independent expv(t_i, A, b_i) on one shared operator, one launch (batched replicas of
+ * krylov_phiv.jl:125-144).  t: HOST nb; Bv, W: device n x nb column-major.  m_out/breakdown: HOST
+ * arrays of nb ints or NULL. */
+int b200k_expv_batched(b200k_handle_t h, b200k_op_t op, int nb, const double *t, const double *Bv,
+                       int64_t ldbv, const b200k_krylov_opts *opts, double *W, int64_t ldw,
+                       int *m_out, int *breakdown);
+
+/* ---- kiops (src/kiops.jl:57-326) ------------------------------------------------------------ */
+typedef struct {
+    int mmin;       /* 10  */
+    int mmax;       /* 128 */
+    int m;          /* min(mmin, mmax) */
+    double tol;     /* 1e-7 */
+    int iop;        /* 2 */
+    int hermitian;  /* -1: ishermitian(A) */
+    int task1;      /* false */
+    double opnorm;  /* accepted and unused, as in the reference */
+} b200k_kiops_opts;
+void b200k_kiops_opts_default(b200k_kiops_opts *o);
+/* tau_out: HOST, ntau values; numSteps follows the reference (`size(tau_out, 2)`): pass
+ * tau_is_row = 1 for a 1 x ntau row (numSteps = ntau), 0 for a scalar / column (numSteps = 1).
+ * U: device n x ppo (u, ppo = p + 1 columns).  W: device n x numSteps.  stats: HOST int64[5] =
+ * (steps, rejected, krylov_steps(always 0), exps, m). */
+int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out, int tau_is_row,
+                const double *U, int64_t ldu, int ppo, const b200k_kiops_opts *opts, double *W,
+                int64_t ldw, int64_t *stats);
+
+/* ---- small dense matrix functions (host, m <= ~130) ----------------------------------------- */
+/* exponential!(A, ExpMethodHigham2005Base()) in place (src/exp_baseexp.jl:112-161). */
+int b200k_exponential(int n, double *A, int lda);
+/* The small dense phase of expv! on its own (src/krylov_phiv.jl:223-244): y = exp(t*H[1:m,1:m]) e1,
+ * taking the SymTridiagonal eigen branch when H[1:m,1:m] is exactly symmetric, else the Pade branch.
+ * branch (may be NULL) receives 1 for the symmetric branch, 0 for Pade. */
+int b200k_expv_small(int m, const double *H, int ldh, double t, double *y, int *branch);
+/* phiv_dense!(w, A, v, k) (src/phi.jl:84-115): w is m x (k+1), ldw. */
+int b200k_phiv_dense(int m, const double *A, int lda, const double *v, int k, double *w, int ldw);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+/* Device time in ms of the last Krylov-factorisation kernel and of the last projection kernel
+ * (CUDA events on the handle's stream; valid after a synchronising call). */
+int b200k_last_timing(b200k_handle_t h, float *krylov_ms, float *project_ms);
+/* Enable (1) / disable (0) the event timing above; off by default. */
+int b200k_set_timing(b200k_handle_t h, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200KRYLOV_H */

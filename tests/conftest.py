@@ -1,0 +1,53 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def laplacian2d(nx, ny):
+    """2-D 5-point Laplacian (Dirichlet, stencil -4 / +1) on an nx x ny grid, CSR int32."""
+    import scipy.sparse as sp
+    ex, ey = np.ones(nx), np.ones(ny)
+    Tx = sp.diags([ex[:-1], -2 * ex, ex[:-1]], [-1, 0, 1])
+    Ty = sp.diags([ey[:-1], -2 * ey, ey[:-1]], [-1, 0, 1])
+    A = (sp.kron(sp.identity(ny), Tx) + sp.kron(Ty, sp.identity(nx))).tocsr()
+    A.indices = A.indices.astype(np.int32)
+    A.indptr = A.indptr.astype(np.int32)
+    return A
+
+
+def convdiff2d(nx, ny, c=0.3):
+    """Non-symmetric convection-diffusion: Laplacian + c * (0.5 on the +1 diagonal, -0.5 on the -1)."""
+    import scipy.sparse as sp
+    n = nx * ny
+    A = laplacian2d(nx, ny)
+    Cm = sp.diags([-0.5 * np.ones(n - 1), 0.5 * np.ones(n - 1)], [-1, 1])
+    return (A + c * Cm).tocsr()
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+@pytest.fixture(scope="session")
+def eu():
+    import eu_b200
+    return eu_b200
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    return O
