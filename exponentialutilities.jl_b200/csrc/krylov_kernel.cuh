@@ -205,7 +205,7 @@ __device__ __forceinline__ void csr_issue_chunk(const KrylovParams &P, Ctx &cx, 
 
 // w[0..nrows) = xscale * (A x)[slice] (+ xscale * B x_tail for the augmented operator); tail rows shift.
 template <int VEC>
-__device__ __forceinline__ void matvec_phase(const KrylovParams &P, Ctx &cx, const double *__restrict__ xsrc,
+__device__ __forceinline__ void matvec_phase(const KrylovParams &P, Ctx &cx, const double *xsrc,
                                              double xscale) {
     SmemFixed *S = cx.S;
     const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
@@ -642,6 +642,7 @@ __device__ void krylov_body(const KrylovParams &P, SmemFixed *S, double *ws_smem
                 }
                 if (p > 0 && tm.rank == 0 && tid < p) vn[n + tid] = S->wtail[tid] / beta;
             }
+            __syncthreads();  // the next mat-vec overwrites the w slice that was just read
             xsrc = xout;
             xscale = 1.0 / beta;
             beta_prev = beta;

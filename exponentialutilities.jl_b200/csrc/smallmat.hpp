@@ -163,7 +163,8 @@ inline void balance(int n, double *A, Balance &bal) {
 
 // X <- (D P) X (D P)^{-1}: undo the scaling, then the permutations in reverse order.
 inline void unbalance(int n, double *X, const Balance &bal) {
-    for (int j = bal.ilo; j <= bal.ihi; ++j) {
+    // ilo == ihi: the block is 1 x 1 and scale[ilo] holds a permutation index, not a factor (xGEBAK).
+    for (int j = bal.ilo; j <= bal.ihi && bal.ilo < bal.ihi; ++j) {
         const double s = bal.scale[j];
         if (s == 1.0) continue;
         for (int q = 0; q < n; ++q) X[(size_t)q * n + j] *= s;  // row j

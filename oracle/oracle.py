@@ -74,6 +74,17 @@ def _dot(x, y):
     return float(_blas.ddot(x, y))
 
 
+def _axpy(a, x, y):
+    """axpy!(a, x, y): y += a*x in place (OpenBLAS daxpy for real contiguous columns)."""
+    if (not np.iscomplexobj(x) and not np.iscomplexobj(y) and not np.iscomplexobj(a)
+            and x.dtype == np.float64 and y.dtype == np.float64):
+        out = _blas.daxpy(x, y, a=a)
+        if out is not y and not np.shares_memory(out, y):
+            y[...] = out
+    else:
+        y += a * x
+
+
 def _nrm2(x):
     if np.iscomplexobj(x):
         return float(_blas.dznrm2(x))
@@ -184,7 +195,7 @@ def _arnoldi_step(j, iop, A, V, H, n, p):
     for i in range(max(1, j - iop + 1), j + 1):
         alpha = _coeff(_dot(V[:, i - 1], y), hreal)
         H[i - 1, j - 1] = alpha
-        y -= alpha * V[:, i - 1]
+        _axpy(-alpha, V[:, i - 1], y)
     beta = _nrm2(y)
     H[j, j - 1] = beta
     with np.errstate(all="ignore"):
@@ -235,9 +246,9 @@ def _lanczos_step(j, A, V, H, n, p):
     alpha = _dot(x, y)
     alpha = alpha.real if np.iscomplexobj(alpha) else alpha
     H[j - 1, j - 1] = alpha
-    y -= alpha * x
+    _axpy(-alpha, x, y)
     if j > 1:
-        y -= H[j - 1, j - 2] * V[:, j - 2]
+        _axpy(-H[j - 1, j - 2], V[:, j - 2], y)
     beta = _nrm2(y)
     H[j, j - 1] = beta
     with np.errstate(all="ignore"):

@@ -1,0 +1,113 @@
+"""CPU-only checks of the product boundary: the shared library loads, exports every symbol that
+include/b200krylov.h declares, fails loudly without a GPU, and its host-side small dense functions
+(the part of the path that runs on the host by design) match the oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from conftest import ROOT, relerr
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "b200krylov.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200k_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(eu):
+    lib = eu.load()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    out = subprocess.run(["nm", "-D", "--defined-only", eu.lib_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\sT\s+(b200k_\w+)", out))
+    for s in syms:
+        assert s in exported, f"{s} declared in include/b200krylov.h but not exported"
+        assert hasattr(lib, s)
+    from importlib import import_module
+    protos = import_module("eu_b200._lib").PROTOTYPES
+    assert set(protos) == set(syms), set(protos) ^ set(syms)
+
+
+def test_no_cpu_fallback(eu):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        eu.expv(1.0, np.eye(4), np.ones(4))
+    # the raw ABI also refuses: no device -> B200K_ECUDA
+    import ctypes as C
+    h = C.c_void_p()
+    assert eu.load().b200k_create(C.byref(h), 0, None) == 4
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "exponentialutilities.jl_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                assert "oracle" not in open(os.path.join(dp, f)).read().lower().replace("checked against the cpu oracle", ""), f
+
+
+def test_exponential_matches_oracle_all_branches(eu, oracle):
+    rng = np.random.default_rng(11)
+    for scale in (300.0, 40.0, 3.0, 1.5, 0.5, 0.1, 0.005, 0.0):
+        A = rng.standard_normal((34, 34))
+        A *= scale / np.linalg.norm(A, 1)
+        E = eu.exponential_(A)
+        assert relerr(E, oracle.exponential_higham2005base(A)) < 1e-12
+        if scale <= 40:
+            assert relerr(E, sla.expm(A)) < 1e-11
+
+
+def test_exponential_badly_scaled_uses_balancing(eu, oracle):
+    rng = np.random.default_rng(12)
+    A = rng.standard_normal((12, 12))
+    D = np.diag(2.0 ** rng.integers(-20, 20, 12))
+    B = D @ A @ np.linalg.inv(D)
+    assert relerr(eu.exponential_(B), oracle.exponential_higham2005base(B)) < 1e-10
+    # upper Hessenberg with an isolated eigenvalue exercises the permutation phase
+    Hh = np.triu(rng.standard_normal((9, 9)), -1)
+    Hh[5, 4] = 0.0
+    Hh[8, :8] = 0.0
+    assert relerr(eu.exponential_(Hh), sla.expm(Hh)) < 1e-12
+
+
+def test_expv_small_branches(eu, oracle):
+    rng = np.random.default_rng(13)
+    m = 30
+    d = rng.standard_normal(m) - 4
+    e = np.abs(rng.standard_normal(m - 1)) + 0.5
+    Tm = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    y, br = eu.expv_small(Tm, 0.7)
+    assert br == 1
+    assert relerr(y, sla.expm(0.7 * Tm)[:, 0]) < 1e-13
+    Hn = np.triu(rng.standard_normal((m, m)), -1)
+    y, br = eu.expv_small(Hn, 0.2)
+    assert br == 0
+    assert relerr(y, oracle.exponential_higham2005base(0.2 * Hn)[:, 0]) < 1e-13
+    # 1 x 1 and 2 x 2 edge cases
+    y, _ = eu.expv_small(np.array([[-3.0]]), 2.0)
+    assert abs(y[0] - np.exp(-6.0)) < 1e-15
+    y, br = eu.expv_small(np.array([[1.0, 2.0], [2.0, -1.0]]), 0.5)
+    assert br == 1 and relerr(y, sla.expm(0.5 * np.array([[1.0, 2.0], [2.0, -1.0]]))[:, 0]) < 1e-14
+
+
+def test_phiv_dense_matches_oracle(eu, oracle):
+    rng = np.random.default_rng(14)
+    for m, k in ((5, 1), (10, 4), (30, 4), (20, 10)):
+        H = np.triu(rng.standard_normal((m, m)), -1)
+        v = rng.standard_normal(m)
+        assert relerr(eu.phiv_dense(H, v, k), oracle.phiv_dense(H, v, k)) < 1e-12
+
+
+def test_error_mapping(eu):
+    with pytest.raises(eu.DimensionMismatch):
+        eu.exponential_(np.zeros((3, 4)))
+    with pytest.raises(eu.DimensionMismatch):
+        eu.phiv_dense(np.zeros((3, 3)), np.zeros(4), 2)
+    import eu_b200._lib as L
+    assert L.load().b200k_status_string(3).decode().startswith("singular")

@@ -1,0 +1,244 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the Python host mirror) against the CPU oracle
+on identical seeded inputs.  Tolerance: relative 2-norm error <= 1e-10 (fp64), the bar of BASELINE.json.
+Run on the B200 box with `pytest -m gpu`."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+import scipy.sparse as sp
+
+from conftest import convdiff2d, laplacian2d, relerr
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def gpu(eu):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (no CPU fallback exists)")
+    eng = eu.get_engine()
+    assert eng.device_info()["sm_count"] > 0
+    return eu
+
+
+# ---- reference test "Arnoldi & Krylov" (test/basictests.jl:515-574) on the GPU path --------------------
+def test_reference_arnoldi_krylov_suite(gpu, oracle):
+    eu, O = gpu, oracle
+    rng = np.random.default_rng(0)
+    n, m, K = 20, 5, 4
+    A = rng.standard_normal((n, n))
+    t = 1e-2
+    b = rng.standard_normal(n)
+    direct = sla.expm(t * A) @ b
+    w = eu.expv(t, A, b, m=m)
+    assert relerr(w, direct) < 1.5e-8                       # the reference's own assertion
+    assert relerr(w, O.expv(t, A, b, m=m)) < RTOL           # parity with the restated reference
+    wk, st = eu.kiops(t, A, b)
+    wo, so = O.kiops(t, A, b)
+    assert relerr(wk, direct[:, None]) < 1.5e-8 and relerr(wk, wo) < RTOL and st == so
+    Ks = eu.arnoldi(A, b, m=m)
+    Ko = O.arnoldi(A, b, m=m)
+    W = eu.phiv(t, Ks, K).cpu().numpy()
+    assert relerr(W, O.phiv_ks(t, Ko, K)) < RTOL
+    # happy breakdown: A = v v' is idempotent -> Ks.m == 2
+    v = rng.standard_normal(n)
+    v /= np.linalg.norm(v)
+    Ks = eu.arnoldi(np.outer(v, v), b)
+    assert Ks.m == 2 and Ks.wasbreakdown
+    # zero input -> exactly zero output, Arnoldi and Lanczos
+    z = np.zeros(n)
+    assert np.linalg.norm(eu.expv(t, np.outer(v, v), z, m=m, ishermitian=False)) == 0.0
+    S = rng.standard_normal((n, n))
+    S = S + S.T
+    assert np.linalg.norm(eu.expv(t, S, z, m=m)) == 0.0
+    # Arnoldi vs Lanczos vs kiops agree on a Hermitian matrix and a 1e-10 perturbation
+    Sp = S + 1e-10 * rng.standard_normal((n, n))
+    w = eu.expv(t, S, b, m=m)
+    assert relerr(eu.expv(t, Sp, b, m=m), w) < 1.5e-8
+    assert relerr(eu.kiops(t, S, b, m=m)[0][:, 0], w) < 1.5e-8
+    assert relerr(w, O.expv(t, S, b, m=m)) < RTOL
+    # tridiagonal phiv
+    n = 30
+    T3 = np.diag(np.ones(n - 1), -1) + np.diag(30 * np.ones(n)) + np.diag(np.ones(n - 1), 1)
+    Q = eu.phiv(0.1, T3, np.ones(n), 10)
+    assert relerr(Q[:, 1], np.linalg.solve(0.1 * T3, (sla.expm(0.1 * T3) - np.eye(n)) @ np.ones(n))) < 1.5e-8
+
+
+def test_kiops_multi_column_matches_oracle(gpu, oracle):
+    rng = np.random.default_rng(5)
+    n, t = 20, 1e-2
+    A = rng.standard_normal((n, n))
+    b = rng.standard_normal(n)
+    U = np.stack([b * (1 / t) ** i for i in range(4)], 1)
+    w, st = gpu.kiops(t, A, U)
+    wo, so = oracle.kiops(t, A, U)
+    assert st == so
+    # u has columns of magnitude 1e6: the result is conditioned at ~1e-10 relative to |u|, compare absolutely
+    assert np.linalg.norm(w - wo) / np.abs(U).max() < 1e-12
+
+
+# ---- BASELINE configs --------------------------------------------------------------------------------------
+def test_C1_dense_512(gpu, oracle):
+    n = 512
+    b = np.random.default_rng(1).standard_normal(n)
+    for scale in (1 / np.sqrt(n), 1.0):  # the unscaled variant exercises 4 squarings
+        A = np.random.default_rng(0).standard_normal((n, n)) * scale
+        assert relerr(gpu.expv(1.0, A, b, m=30), oracle.expv(1.0, A, b, m=30)) < RTOL
+    import torch
+    At = torch.from_numpy(A).cuda()
+    bt = torch.from_numpy(b).cuda()
+    w = gpu.expv(1.0, At, bt, m=30)  # device-resident operator and vector
+    assert w.is_cuda and relerr(w.cpu().numpy(), oracle.expv(1.0, A, b, m=30)) < RTOL
+
+
+@pytest.mark.parametrize("nx,ny", [(40, 50), (37, 41), (300, 400), (1000, 1000)])
+def test_C2_laplacian_arnoldi_and_lanczos(gpu, oracle, nx, ny):
+    A = laplacian2d(nx, ny)
+    b = np.random.default_rng(0).standard_normal(nx * ny)
+    op = gpu.operator(A)
+    assert op.ishermitian and abs(op.opnorm_inf - 8.0) < 1e-14
+    w_l = gpu.expv(1.0, op, b, m=30)                       # default dispatch -> Lanczos
+    w_a = gpu.expv(1.0, op, b, m=30, ishermitian=False)    # full Arnoldi: the fused CGS kernel
+    assert relerr(w_l, oracle.expv(1.0, A, b, m=30)) < RTOL
+    assert relerr(w_a, oracle.expv(1.0, A, b, m=30, ishermitian_=False)) < RTOL
+
+
+def test_C2_nonsymmetric_convection_diffusion(gpu, oracle):
+    A = convdiff2d(300, 400)
+    b = np.random.default_rng(0).standard_normal(120000)
+    op = gpu.operator(A)
+    assert not op.ishermitian
+    assert relerr(gpu.expv(1.0, op, b, m=30), oracle.expv(1.0, A, b, m=30)) < RTOL
+    assert relerr(gpu.expv(1.0, op, b, m=30, iop=2), oracle.expv(1.0, A, b, m=30, iop=2)) < RTOL
+
+
+def test_C3_phiv_dense(gpu, oracle):
+    n = 2048  # C3 is n = 16384; the oracle's dense mat-vecs keep this test at a size that runs in seconds
+    A = np.random.default_rng(2).standard_normal((n, n)) / np.sqrt(n) * 4
+    b = np.random.default_rng(3).standard_normal(n)
+    W, e = gpu.phiv(1.0, A, b, 4, m=30, correct=True, errest=True)
+    Wo, eo = oracle.phiv(1.0, A, b, 4, m=30, correct=True, errest=True)
+    assert relerr(W, Wo) < RTOL and abs(e - eo) <= 1e-10 * abs(eo)
+    W = gpu.phiv(1.0, A, b, 4, m=30)
+    assert relerr(W, oracle.phiv(1.0, A, b, 4, m=30)) < RTOL
+
+
+def test_C4_kiops_laplacian(gpu, oracle):
+    A = laplacian2d(250, 400)
+    u = np.stack([np.random.default_rng(4).standard_normal(100000),
+                  np.random.default_rng(5).standard_normal(100000)], 1)
+    op = gpu.operator(A)
+    for herm in (True, False):  # Lanczos-in-kiops (reference default) and IOP-2
+        w, st = gpu.kiops(1.0, op, u, ishermitian=herm)
+        wo, so = oracle.kiops(1.0, A, u, ishermitian_=herm)
+        assert st == so, (st, so)
+        assert relerr(w, wo) < RTOL
+
+
+def test_C5_batched_expv(gpu, oracle):
+    A = laplacian2d(250, 400)
+    n, nb = 100000, 24
+    B = np.random.default_rng(6).standard_normal((n, nb))
+    ts = np.random.default_rng(7).uniform(0.1, 1.0, nb)
+    op = gpu.operator(A)
+    for herm in (True, False):
+        W = gpu.expv_batched(ts, op, B, m=30, ishermitian=herm)
+        for i in (0, 7, nb - 1):
+            assert relerr(W[:, i], oracle.expv(ts[i], A, B[:, i], m=30, ishermitian_=herm)) < RTOL
+    # zero columns inside a batch give exactly zero
+    B[:, 3] = 0.0
+    W = gpu.expv_batched(ts, op, B, m=30)
+    assert np.linalg.norm(W[:, 3]) == 0.0
+    assert relerr(W[:, 4], oracle.expv(ts[4], A, B[:, 4], m=30)) < RTOL
+
+
+# ---- factorisation-level parity, continuation, layouts ---------------------------------------------------
+def test_krylov_factorisation_H_V(gpu, oracle):
+    A = convdiff2d(40, 50)
+    b = np.random.default_rng(3).standard_normal(2000)
+    for iop in (0, 2, 5):
+        Ks = gpu.arnoldi(A, b, m=20, iop=iop)
+        Ko = oracle.arnoldi(A, b, m=20, iop=iop)
+        assert Ks.m == Ko.m and Ks.beta == pytest.approx(Ko.beta, rel=1e-14)
+        assert np.abs(Ks.getH() - Ko.getH()).max() < 1e-11
+        assert np.abs(Ks.getV().cpu().numpy() - Ko.getV()).max() < 1e-11
+    L = laplacian2d(40, 50)
+    Ks = gpu.arnoldi(L, b, m=20)
+    Ko = oracle.arnoldi(L, b, m=20)
+    H = Ks.getH()
+    assert np.array_equal(H[:20, :20], H[:20, :20].T)  # mirrored exactly -> the eigen branch is taken
+    assert np.abs(H - Ko.getH()).max() < 1e-11
+    # the basis is orthonormal and satisfies the Arnoldi relation A V_m = V_{m+1} H
+    Ks = gpu.arnoldi(A, b, m=20)
+    V = Ks.getV().cpu().numpy()
+    assert np.abs(V.T @ V - np.eye(21)).max() < 1e-10
+    assert np.abs(A @ V[:, :20] - V @ Ks.getH()).max() < 1e-10
+
+
+def test_arnoldi_continuation_init(gpu, oracle):
+    """arnoldi!(...; init = j) resumes an existing factorisation (src/arnoldi.jl:360-368)."""
+    A = convdiff2d(30, 30)
+    b = np.random.default_rng(9).standard_normal(900)
+    Ks = gpu.KrylovSubspace(900, 20)
+    gpu.arnoldi_(Ks, A, b, m=10, ishermitian=False)
+    H10 = Ks.H.copy()
+    gpu.arnoldi_(Ks, A, b, m=20, ishermitian=False, init=10)
+    Ko = oracle.KrylovSubspace(900, 20)
+    oracle.arnoldi_(Ko, A, b, m=20, ishermitian_=False)
+    assert np.abs(Ks.getH() - Ko.getH()).max() < 1e-11
+    assert np.abs(H10[:10, :9] - Ks.H[:10, :9]).max() == 0.0
+    w = gpu.expv(0.7, Ks)
+    assert relerr(w.cpu().numpy(), oracle.expv_ks(0.7, Ko)) < RTOL
+
+
+def test_dimension_errors(gpu):
+    A = laplacian2d(10, 10)
+    with pytest.raises(gpu.DimensionMismatch):
+        gpu.expv(1.0, A, np.ones(99))
+    Ks = gpu.KrylovSubspace(101, 10)
+    with pytest.raises(gpu.DimensionMismatch):
+        gpu.arnoldi_(Ks, A, np.ones(100))
+    with pytest.raises(gpu.ArgumentError):
+        gpu.expv(1.0, A, np.ones(100), mode="nonsense")
+
+
+def test_operator_mul_and_long_rows(gpu, oracle):
+    """mul! parity, and an operator with long rows (warp-per-row mat-vec path) through expv."""
+    rng = np.random.default_rng(21)
+    n = 3000
+    A = sp.random(n, n, density=0.05, random_state=3, format="csr") - 6 * sp.identity(n)
+    A = A.tocsr()
+    x = rng.standard_normal(n)
+    op = gpu.operator(A)
+    assert relerr(op.mul(x), A @ x) < 1e-13
+    assert relerr(gpu.expv(0.5, op, x, m=25), oracle.expv(0.5, A, x, m=25)) < RTOL
+    D = rng.standard_normal((300, 300))
+    assert relerr(gpu.operator(D).mul(x[:300]), D @ x[:300]) < 1e-13
+
+
+def test_run_to_run_determinism(gpu):
+    A = convdiff2d(200, 200)
+    b = np.random.default_rng(0).standard_normal(40000)
+    op = gpu.operator(A)
+    w1 = gpu.expv(1.0, op, b, m=30)
+    w2 = gpu.expv(1.0, op, b, m=30)
+    assert np.array_equal(w1, w2)
+
+
+def test_full_size_properties_C2(gpu):
+    """Size-independent properties at the full C2 size: linearity in b and the semigroup identity
+    exp(tA) exp(sA) b = exp((t+s)A) b (converged Krylov, so it holds to solver accuracy)."""
+    import torch
+    A = laplacian2d(1000, 1000)
+    op = gpu.operator(A)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    b1 = torch.randn(10 ** 6, dtype=torch.float64, device="cuda", generator=g)
+    b2 = torch.randn(10 ** 6, dtype=torch.float64, device="cuda", generator=g)
+    for herm in (True, False):
+        w1 = gpu.expv(0.5, op, b1, m=30, ishermitian=herm)
+        w2 = gpu.expv(0.5, op, b2, m=30, ishermitian=herm)
+        w12 = gpu.expv(0.5, op, 2.0 * b1 - 3.0 * b2, m=30, ishermitian=herm)
+        assert float(torch.linalg.norm(w12 - (2.0 * w1 - 3.0 * w2)) / torch.linalg.norm(w12)) < 1e-9
+        ww = gpu.expv(0.25, op, gpu.expv(0.25, op, b1, m=30, ishermitian=herm), m=30, ishermitian=herm)
+        assert float(torch.linalg.norm(ww - w1) / torch.linalg.norm(w1)) < 1e-9

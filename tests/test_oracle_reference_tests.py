@@ -1,0 +1,116 @@
+"""Pin the CPU oracle to the reference's own analytic assertions for the hot path
+(/root/reference/test/basictests.jl; Julia RNG streams are irrelevant, NumPy seeds are used)."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+import scipy.sparse as sp
+
+from conftest import laplacian2d, relerr
+
+SQRT_EPS = np.sqrt(np.finfo(float).eps)  # isapprox default rtol
+
+
+def phis_dense(A, b, K):
+    """[phi_0(A) b, ..., phi_K(A) b] through scipy.linalg.expm of the Sidje block matrix (independent of oracle)."""
+    n = A.shape[0]
+    M = np.zeros((n + K, n + K))
+    M[:n, :n] = A
+    M[:n, n] = b
+    for i in range(n, n + K - 1):
+        M[i, i + 1] = 1
+    E = sla.expm(M)
+    return np.stack([E[:n, :n] @ b] + [E[:n, n + i] for i in range(K)], 1)
+
+
+def test_arnoldi_and_krylov(oracle):
+    """test/basictests.jl:515-574 "Arnoldi & Krylov"."""
+    O = oracle
+    rng = np.random.default_rng(0)
+    n, m, K = 20, 5, 4
+    A = rng.standard_normal((n, n))
+    t = 1e-2
+    b = rng.standard_normal(n)
+    direct = sla.expm(t * A) @ b
+    assert relerr(O.expv(t, A, b, m=m), direct) < SQRT_EPS                     # :524
+    assert relerr(O.kiops(t, A, b)[0][:, 0], direct) < SQRT_EPS                # :526
+    W = phis_dense(t * A, b, K)
+    Ks = O.arnoldi(A, b, m=m)
+    assert relerr(O.phiv_ks(t, Ks, K), W) < SQRT_EPS                           # :527-534
+    U = np.stack([b * (1 / t) ** i for i in range(K)], 1)
+    assert relerr(O.kiops(t, A, U)[0][:, 0], W[:, :K].sum(1)) < SQRT_EPS       # :535-536
+    v = rng.standard_normal(n)
+    v /= np.linalg.norm(v)
+    P = np.outer(v, v)
+    assert O.arnoldi(P, b).m == 2                                              # :544-547 happy breakdown
+    z = np.zeros(n)
+    assert np.linalg.norm(O.expv(t, P, z, m=m)) == 0.0                         # :550-553
+    S = rng.standard_normal((n, n))
+    S = S + S.T
+    Sp = S + 1e-10 * rng.standard_normal((n, n))
+    w = O.expv(t, S, b, m=m)
+    assert relerr(O.expv(t, Sp, b, m=m), w) < SQRT_EPS                         # :556-562
+    assert relerr(O.kiops(t, S, b, m=m)[0][:, 0], w) < SQRT_EPS
+    assert np.linalg.norm(O.expv(t, S, z, m=m)) == 0.0                         # :565-566
+    n = 30
+    T3 = np.diag(np.ones(n - 1), -1) + np.diag(30 * np.ones(n)) + np.diag(np.ones(n - 1), 1)
+    t = 0.1
+    Q = O.phiv(t, T3, np.ones(n), 10)
+    ref = np.linalg.solve(t * T3, (sla.expm(t * T3) - np.eye(n)) @ np.ones(n))
+    assert relerr(Q[:, 1], ref) < SQRT_EPS                                     # :569-573
+
+
+def test_hermitian_arnoldi_vs_lanczos_H(oracle):
+    """test/basictests.jl:731-754: arnoldi! and lanczos! give the same H (real symmetric restatement)."""
+    O = oracle
+    n, m = 100, 15
+    rng = np.random.default_rng(3)
+    d = rng.standard_normal(n)
+    e = rng.standard_normal(n - 1)
+    A = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    b = rng.standard_normal(n)
+    Ka = O.arnoldi(A, b, m=m, ishermitian_=False)
+    Kl = O.arnoldi(A, b, m=m, ishermitian_=True)
+    assert np.abs(Ka.getH() - Kl.getH()).max() < 1e-12
+
+
+def test_matrix_free_interface(oracle):
+    """test/basictests.jl:786-816: expv(...; m = n) reproduces exp(tA)b to 1e-12 on a small operator."""
+    O = oracle
+    n = 10
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((n, n)) / 4
+    b = rng.standard_normal(n)
+    w = O.expv(0.3, A, b, m=n)
+    assert np.abs(w - sla.expm(0.3 * A) @ b).max() < 1e-12
+
+
+def test_small_exp_all_pade_branches(oracle):
+    """test/basictests.jl:952-974: every Pade branch (C13, C9, C7, C5, C3), n = 40, relerr < 1e-11."""
+    rng = np.random.default_rng(7)
+    for scale in (3.0, 1.5, 0.5, 0.1, 0.005):
+        A = rng.standard_normal((40, 40))
+        A *= scale / np.linalg.norm(A, 1)
+        assert relerr(oracle.exponential_higham2005base(A), sla.expm(A)) < 1e-11
+
+
+def test_sparse_laplacian_converged_vs_expm_multiply(oracle):
+    """Converged Krylov on the C2-style operator agrees with scipy's independent expm_multiply."""
+    from scipy.sparse.linalg import expm_multiply
+    A = laplacian2d(30, 20)
+    b = np.random.default_rng(0).standard_normal(600)
+    ref = expm_multiply(A.tocsc(), b)
+    assert relerr(oracle.expv(1.0, A, b, m=30), ref) < 1e-12                    # Lanczos dispatch
+    assert relerr(oracle.expv(1.0, A, b, m=30, ishermitian_=False), ref) < 1e-12
+
+
+def test_kiops_quirks_and_stats(oracle):
+    """stats = (steps, rejected, krystep == 0, exps, m) and the Hermitian/IOP agreement (basictests.jl:560-562)."""
+    A = laplacian2d(12, 10)
+    u = np.random.default_rng(4).standard_normal((120, 2))
+    w1, s1 = oracle.kiops(1.0, A, u, ishermitian_=True)
+    w2, s2 = oracle.kiops(1.0, A, u, ishermitian_=False)
+    assert s1[2] == 0 and s2[2] == 0
+    assert relerr(w1, w2) < 1e-6
+    W = phis_dense(1.0 * A.toarray(), u[:, 0], 1)  # exp(A) u0 + phi_1(A) u1
+    M = phis_dense(1.0 * A.toarray(), u[:, 1], 2)
+    assert relerr(w2[:, 0], W[:, 0] + M[:, 1]) < 1e-6
