@@ -73,6 +73,7 @@ PROTOTYPES = {
     "b200k_phiv_dense": (C.c_int, [C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int]),
     "b200k_last_timing": (C.c_int, [C.c_void_p, c_float_p, c_float_p]),
     "b200k_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200k_last_kernel": (C.c_int, [C.c_void_p, c_int_p]),
 }
 
 _lib = None

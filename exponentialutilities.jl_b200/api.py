@@ -81,6 +81,12 @@ class Engine:
     def set_timing(self, enabled: bool):
         self.check(self.lib.b200k_set_timing(self.handle, 1 if enabled else 0))
 
+    def last_kernel(self):
+        """'ldg' (krylov_persistent_kernel) or 'tma' (krylov_tma_kernel) for the last factorisation."""
+        w = C.c_int()
+        self.check(self.lib.b200k_last_kernel(self.handle, C.byref(w)))
+        return {1: "ldg", 2: "tma"}.get(w.value, "none")
+
     def last_timing(self):
         a, b = C.c_float(), C.c_float()
         self.check(self.lib.b200k_last_timing(self.handle, C.byref(a), C.byref(b)))

@@ -7,12 +7,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "aux_kernels.cuh"
 #include "krylov_kernel.cuh"
+#include "krylov_kernel_tma.cuh"
 #include "smallmat.hpp"
 
 using namespace b200k;
@@ -75,6 +77,8 @@ struct b200k_context {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     int max_ctas = 0;  // co-resident CTAs of the persistent kernel
+    int force_ldg = 0; // B200K_KERNEL=ldg: use the LDG kernel even where the TMA-ring kernel applies
+    int last_kernel = 0;  // 1 = LDG kernel, 2 = TMA-ring kernel
     std::string err;
     int64_t launches = 0;
     // scratch (device)
@@ -262,10 +266,52 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
     if (c.p > 0 && c.j0 == 0)
         CK(h, cudaMemcpyAsync(h->btail.p, c.btail_host, (size_t)c.p * 8, cudaMemcpyHostToDevice, h->stream));
 
+    // ---- kernel selection: TMA-ring kernel whenever the layout allows 16-byte-aligned bulk copies ----
+    size_t smem = c.g.smem;
+    const void *kern = (const void *)krylov_persistent_kernel;
+    int threads = NT;
+    if (vec2 && !h->force_ldg) {
+        const size_t fixed = sizeof(SmemTma);
+        const size_t extra = op->kind == 1 ? (size_t)NTC * 2 * 8 : 0;
+        size_t wsb = (size_t)round_up((long long)c.g.slice * 8, 128);
+        int nslot = (int)((SMEM_LIMIT - fixed - extra - wsb) / SLOT_BYTES);
+        P.w_in_smem = 1;
+        if (SMEM_LIMIT < fixed + extra + wsb || nslot < 3) {  // slice too large: w lives in HBM/L2 scratch
+            P.w_in_smem = 0;
+            wsb = 0;
+            nslot = (int)((SMEM_LIMIT - fixed - extra) / SLOT_BYTES);
+        }
+        nslot = std::min(nslot, MAXSLOT);
+        P.nslot = nslot;
+        const int ntk0 = (c.g.slice + TILE_ROWS_MAX - 1) / TILE_ROWS_MAX;
+        P.tile_rows = (int)round_up((c.g.slice + ntk0 - 1) / ntk0, 16);
+        if (op->kind == 0) {
+            const int mrn = std::max(op->max_row_nnz, 1);
+            int ch_rows = (int)((SLOT_BYTES - 12 * 8 - 16) / (12LL * mrn + 4));
+            ch_rows = std::min(ch_rows, NTC) / 32 * 32;
+            if (ch_rows >= 64) {
+                P.op_kind = OP_CSR_STREAM;
+                P.ch_rows = ch_rows;
+                P.nnz_cap = (int)round_up((long long)ch_rows * mrn + 8, 4);
+            } else {
+                P.op_kind = OP_CSR_WARP;
+                P.ch_rows = 32;
+            }
+        }
+        P.dscratch_off = (int)(fixed + wsb + (size_t)nslot * SLOT_BYTES);
+        smem = fixed + wsb + (size_t)nslot * SLOT_BYTES + extra;
+        if (!P.w_in_smem) CK(h, h->wglob.ensure((size_t)nt * n * 8));
+        P.wglob = h->wglob.as<double>();
+        kern = (const void *)krylov_tma_kernel;
+        threads = NT2;
+        h->last_kernel = 2;
+    } else {
+        h->last_kernel = 1;
+    }
+
     if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
     void *args[] = {(void *)&P};
-    CK(h, cudaLaunchCooperativeKernel((const void *)krylov_persistent_kernel, dim3(c.g.C * c.g.nteams), dim3(NT),
-                                      args, c.g.smem, h->stream));
+    CK(h, cudaLaunchCooperativeKernel(kern, dim3(c.g.C * c.g.nteams), dim3(threads), args, smem, h->stream));
     if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
     h->launches += 1;
     return B200K_OK;
@@ -543,6 +589,14 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
         delete h;
         return B200K_ECUDA;
     }
+    if (cudaFuncSetAttribute((const void *)krylov_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_LIMIT) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, krylov_tma_kernel, NT2, SMEM_LIMIT) != cudaSuccess ||
+        per_sm < 1) {
+        delete h;
+        return B200K_ECUDA;
+    }
+    if (const char *env = std::getenv("B200K_KERNEL")) h->force_ldg = std::strcmp(env, "ldg") == 0 ? 1 : 0;
     h->max_ctas = std::min(h->sm_count, CPAD);  // one CTA per SM
     for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
     *out = h;
@@ -589,6 +643,12 @@ int b200k_device_info(b200k_handle_t h, int *sm_count, int *max_team, int64_t *l
 int b200k_set_timing(b200k_handle_t h, int enabled) {
     if (!h) return B200K_EARG;
     h->timing = enabled ? 1 : 0;
+    return B200K_OK;
+}
+
+int b200k_last_kernel(b200k_handle_t h, int *which) {
+    if (!h || !which) return B200K_EARG;
+    *which = h->last_kernel;
     return B200K_OK;
 }
 

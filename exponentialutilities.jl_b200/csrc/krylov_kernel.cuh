@@ -88,6 +88,11 @@ struct KrylovParams {
     unsigned *bar;  // [nteams]
     double *wglob;  // [nteams][n] when the w slice does not fit in shared memory
     int w_in_smem;
+    // TMA-ring kernel (krylov_kernel_tma.cuh) only
+    int nnz_cap;       // nnz capacity of one ring slot holding a CSR chunk (val | colind | rowptr segment)
+    int nslot;         // ring depth
+    int tile_rows;     // rows per basis tile (multiple of 16, <= 4096)
+    int dscratch_off;  // byte offset of the dense mat-vec reduction scratch in dynamic shared memory
 };
 
 struct __align__(128) SmemFixed {

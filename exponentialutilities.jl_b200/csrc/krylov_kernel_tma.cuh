@@ -1,0 +1,632 @@
+// krylov_kernel_tma.cuh -- v2 of the persistent fused Arnoldi / Lanczos / IOP kernel: warp-specialised,
+// everything that comes from HBM (CSR chunks AND the basis slice) is streamed by one producer warp through
+// a shared-memory ring of 32 KB slots with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) and
+// full/empty mbarriers; 16 consumer warps compute out of shared memory.
+//
+// Why (profiles/r1_v1_*): the LDG version kept only 16 warps x 8 loads in flight per SM and sat at 40 % DRAM
+// utilisation, stalled on long_scoreboard and on the two team barriers per step.  With the ring, bytes in
+// flight are set by the ring depth (up to 160 KB per SM) instead of by registers, and the producer runs
+// ahead of the consumers across phase boundaries and team barriers (the next phase's first tiles land
+// while the CTAs are still synchronising).
+//
+// Same algorithm, same reduction order, same team-barrier protocol and the same outputs as
+// krylov_kernel.cuh (which remains the path for odd n / odd ldv / unaligned bases).  Reference semantics:
+// src/arnoldi.jl:230-308, 345-377, 388-403, 456-490.
+//
+// Tile schedule of step j (identical on the producer and on the consumers of a CTA):
+//   [A chunks 0..nch-1]                       (CSR stream only; val | colind | rowptr segment per slot)
+//   [dots : for cb in lo..hi step 8 : for k in 0..ntk-1 : for u < nb : basis tile (col cb+u, rows k)]
+//   [update: for k in 0..ntk-1 : for col = uhi..ulo : basis tile (col, rows k)]
+// A basis tile of column c may only be fetched once the consumers have written that column
+// (cols_ready > c, published after a generic->async proxy fence).
+#pragma once
+#include "krylov_kernel.cuh"
+
+namespace b200k {
+
+constexpr int NTC = 512;                         // consumer threads (16 warps)
+constexpr int NT2 = NTC + 32;                    // + 1 producer warp
+constexpr int SLOT_BYTES = 32768;
+constexpr int MAXSLOT = 6;
+constexpr int TILE_ROWS_MAX = SLOT_BYTES / 8;    // 4096 rows per basis tile
+constexpr int PPT = TILE_ROWS_MAX / 2 / NTC;     // row pairs per consumer thread per tile (4)
+constexpr int MAXCH2 = 64;                       // chunk-table capacity
+
+struct __align__(128) SmemTma {
+    uint64_t full[MAXSLOT];
+    uint64_t empty[MAXSLOT];
+    double hs[MAXCOL];
+    double red[2][NW][CB];
+    double redn[NW];
+    double wtail[MAXP];
+    double xtail[MAXP];
+    int chunk_a0[MAXCH2];
+    int chunk_cnt[MAXCH2];
+    int slot_a0[MAXSLOT];
+    volatile int cols_ready;  // number of complete basis columns of the current problem
+    volatile int stop_seq;    // consumers finished local problem #stop_seq (1-based)
+};
+
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void team_barrier_c(Team &tm) {
+    consumer_sync();
+    if (threadIdx.x == 0) {
+        tm.target += (unsigned)tm.C;
+        __threadfence();
+        atomicAdd(tm.bar, 1u);
+        while ((int)(ld_acquire_u32(tm.bar) - tm.target) < 0) {
+        }
+        __threadfence();
+    }
+    consumer_sync();
+}
+
+struct Ring {
+    unsigned char *base;
+    int nslot;
+    int slot;
+    unsigned phase;
+    __device__ __forceinline__ void advance() {
+        if (++slot == nslot) {
+            slot = 0;
+            phase ^= 1u;
+        }
+    }
+    __device__ __forceinline__ unsigned char *ptr() const { return base + (size_t)slot * SLOT_BYTES; }
+};
+
+struct TmaGeom {
+    int r0, nrows;  // this CTA's slice
+    int nch;        // CSR chunks in the slice
+    int ntk;        // basis tiles per column in the slice
+    int TR;         // rows per basis tile
+};
+
+// ---------------------------------------------------------------------------------------------------
+// producer (one lane)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool prod_acquire(SmemTma *S, const Ring &rg, int seq) {
+    while (!mbar_try_wait(&S->empty[rg.slot], rg.phase ^ 1u)) {
+        if (S->stop_seq >= seq) return false;
+    }
+    return true;
+}
+
+__device__ void producer_problem(const KrylovParams &P, SmemTma *S, Ring &rg, const TmaGeom &G, const double *V,
+                                 int seq, unsigned &issued) {
+    const long long ldv = P.ldv;
+    const int jstart = P.j0 == 0 ? 1 : P.j0;
+    const int iopw = P.iop > 0 ? P.iop : P.m;
+    const int nnz_cap = P.nnz_cap;
+    bool stopped = false;
+    for (int j = jstart; j <= P.m && !stopped; ++j) {
+        const int jc = j - 1;
+        if (P.op_kind == OP_CSR_STREAM) {
+            for (int c = 0; c < G.nch; ++c) {
+                if (!prod_acquire(S, rg, seq)) { stopped = true; break; }
+                const int rs = G.r0 + c * P.ch_rows;
+                const int re = min(G.r0 + G.nrows, rs + P.ch_rows);
+                int a0, cnt;
+                if (G.nch <= MAXCH2) {
+                    a0 = S->chunk_a0[c];
+                    cnt = S->chunk_cnt[c];
+                } else {
+                    const int e0 = P.rowptr[rs], e1 = P.rowptr[re];
+                    a0 = e0 & ~3;
+                    cnt = ((e1 + 3) & ~3) - a0;
+                }
+                const int rpc = (re - rs + 1 + 3) & ~3;
+                S->slot_a0[rg.slot] = a0;
+                unsigned char *dst = rg.ptr();
+                mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)cnt * 12u + (uint32_t)rpc * 4u);
+                if (cnt > 0) {
+                    bulk_g2s(dst, P.val + a0, (uint32_t)cnt * 8u, &S->full[rg.slot]);
+                    bulk_g2s(dst + (size_t)nnz_cap * 8, P.colind + a0, (uint32_t)cnt * 4u, &S->full[rg.slot]);
+                }
+                bulk_g2s(dst + (size_t)nnz_cap * 12, P.rowptr + rs, (uint32_t)rpc * 4u, &S->full[rg.slot]);
+                rg.advance();
+                ++issued;
+            }
+            if (stopped) break;
+        }
+        const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
+        const int hi = jc;
+        const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
+        for (int cb = lo; cb <= hi && !stopped; cb += CB) {
+            const int nb = min(CB, hi - cb + 1);
+            for (int k = 0; k < G.ntk && !stopped; ++k) {
+                const int rows = min(G.TR, G.nrows - k * G.TR);
+                for (int u = 0; u < nb; ++u) {
+                    const int col = cb + u;
+                    while (S->cols_ready <= col) {
+                        if (S->stop_seq >= seq) { stopped = true; break; }
+                    }
+                    if (stopped || !prod_acquire(S, rg, seq)) { stopped = true; break; }
+                    mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 8u);
+                    bulk_g2s(rg.ptr(), V + (long long)col * ldv + G.r0 + (long long)k * G.TR, (uint32_t)rows * 8u,
+                             &S->full[rg.slot]);
+                    rg.advance();
+                    ++issued;
+                }
+            }
+        }
+        for (int k = 0; k < G.ntk && !stopped; ++k) {
+            const int rows = min(G.TR, G.nrows - k * G.TR);
+            for (int col = hi; col >= ulo; --col) {
+                if (!prod_acquire(S, rg, seq)) { stopped = true; break; }
+                mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 8u);
+                bulk_g2s(rg.ptr(), V + (long long)col * ldv + G.r0 + (long long)k * G.TR, (uint32_t)rows * 8u,
+                         &S->full[rg.slot]);
+                rg.advance();
+                ++issued;
+            }
+        }
+    }
+    // the consumers decide when the problem is over (m steps, happy breakdown, or beta == 0)
+    while (S->stop_seq < seq) {
+    }
+    // every copy that was issued must have landed before the ring is re-initialised / the CTA exits
+    const unsigned ns = (unsigned)rg.nslot;
+    const unsigned first = issued > ns ? issued - ns : 0u;
+    for (unsigned t = first; t < issued; ++t) mbar_wait(&S->full[t % ns], (t / ns) & 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// consumers (512 threads)
+// ---------------------------------------------------------------------------------------------------
+struct Cons {
+    SmemTma *S;
+    double *ws;
+    int tid, lane, warp;
+    Ring rg;
+    __device__ __forceinline__ void wait_full() { mbar_wait(&S->full[rg.slot], rg.phase); }
+    __device__ __forceinline__ void release() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S->empty[rg.slot]);
+        rg.advance();
+    }
+};
+
+__device__ __forceinline__ void block_sum_to_c(Cons &cx, double v, double *out) {
+    v = warp_sum(v);
+    if (cx.lane == 0) cx.S->redn[cx.warp] = v;
+    consumer_sync();
+    if (cx.tid == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += cx.S->redn[w];
+        *out = s;
+    }
+}
+
+__device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *xsrc, double xscale) {
+    SmemTma *S = cx.S;
+    const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
+    const int n = P.n, p = P.p;
+    double *ws = cx.ws;
+    if (p > 0) {
+        if (tid < p) S->xtail[tid] = xsrc[n + tid];
+        consumer_sync();
+        if (tid < p) S->wtail[tid] = (tid < p - 1) ? S->xtail[tid + 1] * xscale : 0.0;
+    }
+    if (P.op_kind == OP_CSR_STREAM) {
+        const int nnz_cap = P.nnz_cap;
+        for (int c = 0; c < G.nch; ++c) {
+            const int rl = c * P.ch_rows + tid;
+            const bool active = tid < P.ch_rows && rl < G.nrows;
+            cx.wait_full();
+            if (active) {
+                const unsigned char *base = cx.rg.ptr();
+                const double *vs = reinterpret_cast<const double *>(base);
+                const int *cs = reinterpret_cast<const int *>(base + (size_t)nnz_cap * 8);
+                const int *rp = reinterpret_cast<const int *>(base + (size_t)nnz_cap * 12);
+                const int a0 = S->slot_a0[cx.rg.slot];
+                const int e0 = rp[tid] - a0, e1 = rp[tid + 1] - a0;
+                double sum = 0.0;
+                for (int e = e0; e < e1; ++e) sum = fma(vs[e], xsrc[cs[e]], sum);
+                if (p > 0) {
+                    const double *brow = P.Bm + (G.r0 + rl);
+                    for (int k = 0; k < p; ++k) sum = fma(brow[(long long)k * P.ldb], S->xtail[k], sum);
+                }
+                ws[rl] = sum * xscale;
+            }
+            cx.release();
+        }
+    } else if (P.op_kind == OP_CSR_WARP) {
+        for (int rl = warp; rl < G.nrows; rl += NW) {
+            const int row = G.r0 + rl;
+            const int e0 = P.rowptr[row], e1 = P.rowptr[row + 1];
+            double sum = 0.0;
+            for (int e = e0 + lane; e < e1; e += 32) sum = fma(ld_ro1(P.val + e), xsrc[P.colind[e]], sum);
+            sum = warp_sum(sum);
+            if (lane == 0) {
+                if (p > 0)
+                    for (int k = 0; k < p; ++k) sum = fma(P.Bm[row + (long long)k * P.ldb], S->xtail[k], sum);
+                ws[rl] = sum * xscale;
+            }
+        }
+    } else {  // dense column-major (direct 16-byte loads; the ring is used for the basis only)
+        const int units = G.nrows / 2;
+        int RL = 32;
+        while (RL < units && RL < NTC) RL <<= 1;
+        const int Gc = NTC / RL;
+        const int ul = tid % RL, g = tid / RL;
+        // NTC*2 doubles of reduction scratch behind the ring (the ring slots may have basis tiles in flight)
+        double *dscratch = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(S) + P.dscratch_off);
+        for (int ubase = 0; ubase < units; ubase += RL) {
+            const int u = ubase + ul;
+            const bool valid = u < units;
+            double a0 = 0.0, a1 = 0.0;
+            if (valid) {
+                const double *ap = P.Ad + G.r0 + 2LL * u;
+#pragma unroll 8
+                for (int c = g; c < n; c += Gc) {
+                    const double xc = xsrc[c];
+                    const double2 a2 = ld_ro2(ap + (long long)c * P.lda);
+                    a0 = fma(a2.x, xc, a0);
+                    a1 = fma(a2.y, xc, a1);
+                }
+            }
+            dscratch[(g * RL + ul) * 2 + 0] = a0;
+            dscratch[(g * RL + ul) * 2 + 1] = a1;
+            consumer_sync();
+            if (g == 0 && valid) {
+                double s0 = 0.0, s1 = 0.0;
+                for (int q = 0; q < Gc; ++q) {
+                    s0 += dscratch[(q * RL + ul) * 2 + 0];
+                    s1 += dscratch[(q * RL + ul) * 2 + 1];
+                }
+                const int rl = 2 * u;
+                if (p > 0) {
+                    for (int k = 0; k < p; ++k) {
+                        s0 = fma(P.Bm[G.r0 + rl + (long long)k * P.ldb], S->xtail[k], s0);
+                        s1 = fma(P.Bm[G.r0 + rl + 1 + (long long)k * P.ldb], S->xtail[k], s1);
+                    }
+                }
+                ws[rl] = s0 * xscale;
+                ws[rl + 1] = s1 * xscale;
+            }
+            consumer_sync();
+        }
+    }
+    consumer_sync();
+}
+
+__device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
+                             int lo, int hi, double *part) {
+    SmemTma *S = cx.S;
+    const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
+    const double2 *ws2 = reinterpret_cast<const double2 *>(cx.ws);
+    int batch = 0;
+    for (int cb = lo; cb <= hi; cb += CB, ++batch) {
+        const int nb = min(CB, hi - cb + 1);
+        double acc[CB];
+#pragma unroll
+        for (int u = 0; u < CB; ++u) acc[u] = 0.0;
+        for (int k = 0; k < G.ntk; ++k) {
+            const int pairs = min(G.TR, G.nrows - k * G.TR) >> 1;
+            const int pbase = (k * G.TR) >> 1;
+            double2 wr[PPT];
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) {
+                const int idx = tid + q * NTC;
+                wr[q] = idx < pairs ? ws2[pbase + idx] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < CB; ++u) {
+                if (u < nb) {
+                    cx.wait_full();
+                    const double2 *vt = reinterpret_cast<const double2 *>(cx.rg.ptr());
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        const int idx = tid + q * NTC;
+                        if (idx < pairs) {
+                            const double2 v2 = vt[idx];
+                            acc[u] = fma(v2.x, wr[q].x, fma(v2.y, wr[q].y, acc[u]));
+                        }
+                    }
+                    cx.release();
+                }
+            }
+        }
+        if (P.p > 0 && tm.rank == 0 && tid == 0) {  // augmented tail rows (direct loads)
+#pragma unroll
+            for (int u = 0; u < CB; ++u)
+                if (u < nb)
+                    for (int kk = 0; kk < P.p; ++kk)
+                        acc[u] = fma(V[(long long)(cb + u) * P.ldv + P.n + kk], S->wtail[kk], acc[u]);
+        }
+        const double r = warp_reduce8(acc, lane);
+        const int buf = batch & 1;
+        if ((lane & 3) == 0) S->red[buf][warp][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = r;
+        consumer_sync();
+        if (tid < nb) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += S->red[buf][w][tid];
+            part[(long long)(cb - lo + tid) * CPAD + tm.rank] = s;
+        }
+    }
+}
+
+__device__ double update_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
+                                 int ulo, int uhi, double *xout) {
+    SmemTma *S = cx.S;
+    const int tid = cx.tid;
+    double2 *ws2 = reinterpret_cast<double2 *>(cx.ws);
+    double2 *xo2 = reinterpret_cast<double2 *>(xout + G.r0);
+    const double *hs = S->hs;
+    double nrm = 0.0;
+    for (int k = 0; k < G.ntk; ++k) {
+        const int pairs = min(G.TR, G.nrows - k * G.TR) >> 1;
+        const int pbase = (k * G.TR) >> 1;
+        double2 wr[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            const int idx = tid + q * NTC;
+            wr[q] = idx < pairs ? ws2[pbase + idx] : make_double2(0.0, 0.0);
+        }
+        for (int col = uhi; col >= ulo; --col) {
+            const double hc = hs[col - ulo];
+            cx.wait_full();
+            const double2 *vt = reinterpret_cast<const double2 *>(cx.rg.ptr());
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) {
+                const int idx = tid + q * NTC;
+                if (idx < pairs) {
+                    const double2 v2 = vt[idx];
+                    wr[q].x = fma(-hc, v2.x, wr[q].x);
+                    wr[q].y = fma(-hc, v2.y, wr[q].y);
+                }
+            }
+            cx.release();
+        }
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            const int idx = tid + q * NTC;
+            if (idx < pairs) {
+                ws2[pbase + idx] = wr[q];
+                xo2[pbase + idx] = wr[q];
+                nrm = fma(wr[q].x, wr[q].x, fma(wr[q].y, wr[q].y, nrm));
+            }
+        }
+    }
+    if (P.p > 0 && tid < P.p) {
+        double wt = S->wtail[tid];
+        for (int c = uhi; c >= ulo; --c) wt = fma(-hs[c - ulo], V[(long long)c * P.ldv + P.n + tid], wt);
+        S->wtail[tid] = wt;
+        if (tm.rank == 0) {
+            xout[P.n + tid] = wt;
+            nrm = fma(wt, wt, nrm);
+        }
+    }
+    return nrm;
+}
+
+// One problem on the consumer side.  Mirrors krylov_body<2> of krylov_kernel.cuh.
+__device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom &G, Team &tm, int prob, int nlocal,
+                                 double *xb0, double *xb1, double *part0, double *partn0) {
+    SmemTma *S = cx.S;
+    const int tid = cx.tid;
+    const int n = P.n, p = P.p;
+    double *V = P.V + (long long)prob * P.V_stride;
+    double *Hd = P.Hd + (long long)prob * P.H_stride;
+    const double *b = P.b + (long long)prob * P.b_stride;
+    const long long ldv = P.ldv;
+    const int ldh = P.ldh;
+    const int units = G.nrows >> 1;
+    double2 *ws2 = reinterpret_cast<double2 *>(cx.ws);
+    const double *xsrc;
+    double xscale;
+    int jstart;
+    int m_out = P.m, breakdown = 0;
+
+    if (P.j0 == 0) {  // firststep! (arnoldi.jl:230-250 / 257-279)
+        double nrm = 0.0;
+        for (int i = tid; i < units; i += NTC) {
+            const double2 b2 = reinterpret_cast<const double2 *>(b + G.r0)[i];
+            ws2[i] = b2;
+            if (p > 0) reinterpret_cast<double2 *>(xb0 + G.r0)[i] = b2;
+            nrm = fma(b2.x, b2.x, fma(b2.y, b2.y, nrm));
+        }
+        if (p > 0 && tm.rank == 0 && tid < p) {
+            const double bt = P.btail[tid];
+            xb0[n + tid] = bt;
+            nrm = fma(bt, bt, nrm);
+        }
+        double *pslot = partn0 + (2 + (nlocal & 1)) * CPAD;
+        block_sum_to_c(cx, nrm, pslot + tm.rank);
+        team_barrier_c(tm);
+        const double beta = sqrt(team_sum(pslot, tm.C, cx.lane));
+        if (tm.rank == 0 && tid == 0) P.scal[prob * 4] = beta;
+        if (beta == 0.0) {
+            if (tm.rank == 0 && tid == 0) {
+                P.stat[prob * 4 + 0] = P.m;
+                P.stat[prob * 4 + 1] = 0;
+            }
+            return;
+        }
+        if (p == 0) {
+            const double inv = 1.0 / beta;
+            for (int i = tid; i < units; i += NTC) {
+                double2 b2 = ws2[i];
+                b2.x *= inv;
+                b2.y *= inv;
+                reinterpret_cast<double2 *>(V + G.r0)[i] = b2;
+            }
+            xsrc = b;
+        } else {
+            for (int i = tid; i < units; i += NTC) {
+                double2 b2 = ws2[i];
+                b2.x /= beta;
+                b2.y /= beta;
+                reinterpret_cast<double2 *>(V + G.r0)[i] = b2;
+            }
+            if (tm.rank == 0 && tid < p) V[n + tid] = P.btail[tid] / beta;
+            xsrc = xb0;
+        }
+        fence_proxy_async();
+        consumer_sync();
+        if (tid == 0) S->cols_ready = 1;
+        xscale = 1.0 / beta;
+        jstart = 1;
+    } else {
+        xsrc = V + (long long)(P.j0 - 1) * ldv;
+        xscale = 1.0;
+        jstart = P.j0;
+    }
+
+    double beta_prev = 0.0;
+    const int iopw = P.iop > 0 ? P.iop : P.m;
+    for (int j = jstart; j <= P.m; ++j) {
+        const int jc = j - 1;
+        const int par = j & 1;
+        double *xout = par ? xb1 : xb0;
+        double *part = part0 + (long long)par * MAXCOL * CPAD;
+        double *partn = partn0 + par * CPAD;
+
+        matvec_phase_c(P, cx, G, xsrc, xscale);
+
+        const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
+        const int hi = jc;
+        dots_phase_c(P, cx, G, tm, V, lo, hi, part);
+        team_barrier_c(tm);
+
+        const int nc = hi - lo + 1;
+        const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
+        for (int ci = cx.warp; ci < nc; ci += NW) {
+            const double s = team_sum(part + (long long)ci * CPAD, tm.C, cx.lane);
+            if (cx.lane == 0) {
+                S->hs[lo + ci - ulo] = s;
+                if (tm.rank == 0) Hd[(long long)jc * ldh + lo + ci] = s;
+            }
+        }
+        if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = beta_prev;
+        consumer_sync();
+
+        const double nrm = update_phase_c(P, cx, G, tm, V, ulo, hi, xout);
+        block_sum_to_c(cx, nrm, partn + tm.rank);
+        team_barrier_c(tm);
+
+        const double beta = sqrt(team_sum(partn, tm.C, cx.lane));
+        if (tm.rank == 0 && tid == 0) Hd[(long long)jc * ldh + jc + 1] = beta;
+        {
+            double *vn = V + (long long)(jc + 1) * ldv;
+            for (int i = tid; i < units; i += NTC) {
+                double2 w2 = ws2[i];
+                w2.x /= beta;
+                w2.y /= beta;
+                reinterpret_cast<double2 *>(vn + G.r0)[i] = w2;
+            }
+            if (p > 0 && tm.rank == 0 && tid < p) vn[n + tid] = S->wtail[tid] / beta;
+        }
+        fence_proxy_async();  // the producer's TMA reads of this column must see these generic-proxy stores
+        consumer_sync();
+        if (tid == 0) S->cols_ready = jc + 2;
+        xsrc = xout;
+        xscale = 1.0 / beta;
+        beta_prev = beta;
+        if (beta < P.tol) {
+            m_out = j;
+            breakdown = 1;
+            break;
+        }
+    }
+    if (tm.rank == 0 && tid == 0) {
+        P.stat[prob * 4 + 0] = m_out;
+        P.stat[prob * 4 + 1] = breakdown;
+    }
+}
+
+__global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constant__ KrylovParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemTma *S = reinterpret_cast<SmemTma *>(smem_raw);
+    const size_t ws_bytes = P.w_in_smem ? (((size_t)P.slice * 8 + 127) & ~(size_t)127) : 0;
+    double *ws_smem = reinterpret_cast<double *>(smem_raw + sizeof(SmemTma));
+    unsigned char *ring = smem_raw + sizeof(SmemTma) + ws_bytes;
+
+    const int tid = threadIdx.x;
+    const int team = blockIdx.x / P.team_size;
+    Team tm;
+    tm.rank = blockIdx.x % P.team_size;
+    tm.C = P.team_size;
+    tm.bar = P.bar + team;
+    tm.target = 0;
+    TmaGeom G;
+    G.r0 = min(P.n, tm.rank * P.slice);
+    G.nrows = min(P.n, G.r0 + P.slice) - G.r0;
+    G.TR = P.tile_rows;
+    G.ntk = (G.nrows + G.TR - 1) / G.TR;
+    G.nch = P.op_kind == OP_CSR_STREAM ? (G.nrows + P.ch_rows - 1) / P.ch_rows : 0;
+
+    if (G.nch > 0 && G.nch <= MAXCH2) {
+        for (int c = tid; c < G.nch; c += NT2) {
+            const int rs = G.r0 + c * P.ch_rows;
+            const int re = min(G.r0 + G.nrows, rs + P.ch_rows);
+            const int e0 = P.rowptr[rs], e1 = P.rowptr[re];
+            const int a0 = e0 & ~3;
+            S->chunk_a0[c] = a0;
+            S->chunk_cnt[c] = ((e1 + 3) & ~3) - a0;
+        }
+    }
+    if (tid == 0) {
+        for (int s = 0; s < P.nslot; ++s) {
+            mbar_init(&S->full[s], 1);
+            mbar_init(&S->empty[s], NW);
+        }
+        S->cols_ready = P.j0;  // continuation: columns 0..j0-1 already exist
+        S->stop_seq = 0;
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    double *xb0 = P.xbuf + (long long)team * 2 * P.xlen;
+    double *xb1 = xb0 + P.xlen;
+    double *part0 = P.part + (long long)team * 2 * MAXCOL * CPAD;
+    double *partn0 = P.partn + (long long)team * 4 * CPAD;
+
+    const bool is_producer = tid >= NTC;
+    Cons cx;
+    cx.S = S;
+    cx.ws = P.w_in_smem ? ws_smem : (P.wglob + (long long)team * P.n + G.r0);
+    cx.tid = tid;
+    cx.lane = tid & 31;
+    cx.warp = tid >> 5;
+
+    int nlocal = -1;
+    for (int prob = team; prob < P.nprob; prob += P.nteams) {
+        ++nlocal;
+        if (is_producer) {
+            if (tid == NTC) {
+                Ring rg{ring, P.nslot, 0, 0u};
+                unsigned issued = 0;
+                producer_problem(P, S, rg, G, P.V + (long long)prob * P.V_stride, nlocal + 1, issued);
+            }
+            __syncwarp();
+        } else {
+            cx.rg = Ring{ring, P.nslot, 0, 0u};
+            consumer_problem(P, cx, G, tm, prob, nlocal, xb0, xb1, part0, partn0);
+            consumer_sync();
+            if (tid == 0) S->stop_seq = nlocal + 1;
+        }
+        // CTA-wide resynchronisation: the ring is re-initialised between problems
+        __syncthreads();
+        if (prob + P.nteams < P.nprob) {
+            if (tid == 0) {
+                for (int s = 0; s < P.nslot; ++s) {
+                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S->full[s])) : "memory");
+                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S->empty[s])) : "memory");
+                    mbar_init(&S->full[s], 1);
+                    mbar_init(&S->empty[s], NW);
+                }
+                S->cols_ready = P.j0;
+                mbar_fence_init();
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace b200k

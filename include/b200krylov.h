@@ -175,6 +175,10 @@ int b200k_phiv_dense(int m, const double *A, int lda, const double *v, int k, do
 int b200k_last_timing(b200k_handle_t h, float *krylov_ms, float *project_ms);
 /* Enable (1) / disable (0) the event timing above; off by default. */
 int b200k_set_timing(b200k_handle_t h, int enabled);
+/* Which Krylov kernel the last factorisation used: 1 = LDG kernel (krylov_persistent_kernel, any layout),
+ * 2 = TMA-ring kernel (krylov_tma_kernel; needs even n / ldv and 16-byte aligned bases).  The environment
+ * variable B200K_KERNEL=ldg, read at b200k_create, forces 1 (A/B measurements). */
+int b200k_last_kernel(b200k_handle_t h, int *which);
 
 #ifdef __cplusplus
 }
