@@ -1,0 +1,76 @@
+"""Timings of the other BASELINE configs on one GPU (C3 dense phiv, C5 batched share, C4 kiops single GPU).
+Usage: python scripts/bench_configs.py [c3] [c5] [c4] [c2var]"""
+import sys, os, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np, torch
+import eu_b200 as eu
+from conftest import laplacian2d, convdiff2d
+
+which = set(sys.argv[1:]) or {"c3", "c5", "c4", "c2var"}
+PEAK = 6544.0
+eng = eu.get_engine()
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+def kernel_ms(fn, reps=5):
+    eng.set_timing(True); ks = []
+    for _ in range(reps):
+        fn(); torch.cuda.synchronize(); ks.append(eng.last_timing()["krylov_ms"])
+    eng.set_timing(False)
+    return float(np.mean(ks))
+
+out = {}
+if "c2var" in which:
+    n = 10**6
+    A = convdiff2d(1000, 1000); op = eu.operator(A)
+    b = torch.randn(n, dtype=torch.float64, device="cuda")
+    f = lambda: eu.expv(1.0, op, b, m=30)
+    ms = timeit(f); k = kernel_ms(f)
+    S_A = 12 * A.nnz + 4 * (n + 1); B = 30 * (S_A + 16 * n) + 8 * n * 30 * 31 + 16 * n
+    out["c2_convdiff_arnoldi"] = {"ms": ms, "kernel_ms": k, "gbs": B / k / 1e6, "frac": B / k / 1e6 / PEAK, "kernel": eng.last_kernel()}
+    f = lambda: eu.expv(1.0, op, b, m=30, iop=2)
+    ms = timeit(f); k = kernel_ms(f)
+    out["c2_convdiff_iop2"] = {"ms": ms, "kernel_ms": k}
+if "c3" in which:
+    n = 16384
+    g = torch.Generator(device="cuda").manual_seed(2)
+    A = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g) / 128
+    b = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    op = eu.operator(A); del A
+    Ks = eu.KrylovSubspace(n, 30)
+    W = torch.empty((5, n), dtype=torch.float64, device="cuda")
+    def f():
+        eu.arnoldi_(Ks, op, b, m=30, ishermitian=False)
+        eu.phiv_(W, 1.0, Ks, 4)
+    ms = timeit(f, reps=5, warm=2); k = kernel_ms(f, 3)
+    B = 30 * (8 * n * n + 16 * n) + 8 * n * 30 * 31 + 16 * n
+    out["c3_phiv_dense16384"] = {"ms": ms, "phiv_per_s": 1e3 / ms, "kernel_ms": k, "gbs": B / k / 1e6, "frac": B / k / 1e6 / PEAK, "kernel": eng.last_kernel()}
+if "c5" in which:
+    A = laplacian2d(250, 400); n = 100000; nb = 128
+    op = eu.operator(A)
+    B_ = torch.randn(n, nb, dtype=torch.float64, device="cuda")
+    ts = np.random.default_rng(7).uniform(0.1, 1.0, nb)
+    for herm, name in ((False, "arnoldi"), (True, "lanczos")):
+        f = lambda: eu.expv_batched(ts, op, B_, m=30, ishermitian=herm)
+        ms = timeit(f, reps=5, warm=2); k = kernel_ms(f, 3)
+        S_A = 12 * A.nnz + 4 * (n + 1)
+        per = (30 * (S_A + 16 * n) + 8 * n * 30 * 31 + 16 * n) if not herm else (30 * (S_A + 24 * n) + 16 * n)
+        out[f"c5_batched128_{name}"] = {"ms": ms, "expv_per_s_per_gpu": nb * 1e3 / ms, "kernel_ms": k,
+                                        "alg_gbs_kernel": nb * per / k / 1e6, "kernel": eng.last_kernel()}
+if "c4" in which:
+    A = laplacian2d(2500, 4000); n = 10**7
+    op = eu.operator(A)
+    u = torch.stack([torch.randn(n, dtype=torch.float64, device="cuda"), torch.randn(n, dtype=torch.float64, device="cuda")], 1)
+    for herm in (True, False):
+        t0 = time.time(); w, st = eu.kiops(1.0, op, u, ishermitian=herm); torch.cuda.synchronize(); dt = time.time() - t0
+        t0 = time.time(); w, st = eu.kiops(1.0, op, u, ishermitian=herm); torch.cuda.synchronize(); dt = time.time() - t0
+        out[f"c4_kiops_1gpu_herm{int(herm)}"] = {"s": dt, "stats": st}
+print(json.dumps(out, indent=1))
