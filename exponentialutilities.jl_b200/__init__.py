@@ -10,7 +10,7 @@ The product is ``libb200krylov.so`` (hand-written sm_100a CUDA behind the C ABI 
 ``include/b200krylov.h``); this package is the thin ctypes host layer mirroring the reference's
 function names, keywords and error behaviour.
 """
-from . import _lib, build  # noqa: F401
+from . import _lib, build, parallel  # noqa: F401
 from ._lib import (ArgumentError, DimensionMismatch, SingularException, UnsupportedError,  # noqa: F401
                    lib_path, load)
 from .api import (Engine, KrylovSubspace, Operator, arnoldi, arnoldi_, expv, expv_, expv_batched,  # noqa: F401

@@ -28,6 +28,7 @@ class KiopsOpts(C.Structure):
     _fields_ = [
         ("mmin", C.c_int), ("mmax", C.c_int), ("m", C.c_int), ("tol", C.c_double),
         ("iop", C.c_int), ("hermitian", C.c_int), ("task1", C.c_int), ("opnorm", C.c_double),
+        ("normU", C.c_double),
     ]
 
 
@@ -68,6 +69,12 @@ PROTOTYPES = {
                                      C.POINTER(KrylovOpts), C.c_void_p, C.c_int64, c_int_p, c_int_p]),
     "b200k_kiops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_double_p, C.c_int, C.c_void_p, C.c_int64,
                               C.c_int, C.POINTER(KiopsOpts), C.c_void_p, C.c_int64, c_int64_p]),
+    "b200k_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200k_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200k_comm_destroy": (C.c_int, [C.c_void_p]),
+    "b200k_op_csr_create_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "b200k_exponential": (C.c_int, [C.c_int, c_double_p, C.c_int]),
     "b200k_expv_small": (C.c_int, [C.c_int, c_double_p, C.c_int, C.c_double, c_double_p, c_int_p]),
     "b200k_phiv_dense": (C.c_int, [C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int]),

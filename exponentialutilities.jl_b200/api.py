@@ -468,7 +468,7 @@ def expv_batched(ts, A, B, *, m=30, tol=1.0e-7, ishermitian=None, iop=0):
 # kiops (src/kiops.jl:57-281)
 # ------------------------------------------------------------------------------------------
 def kiops(tau_out, A, u, *, mmin=10, mmax=128, m=None, tol=1.0e-7, opnorm=None, iop=2, ishermitian=None,
-          task1=False):
+          task1=False, _normU=None):
     """kiops(tau_out, A, u; mmin, mmax, m, tol, opnorm, iop, ishermitian, task1) -> (w, stats).
 
     ``w`` is n x numSteps (host NumPy array, as the reference returns a host ``zeros(n, numSteps)``,
@@ -495,6 +495,8 @@ def kiops(tau_out, A, u, *, mmin=10, mmax=128, m=None, tol=1.0e-7, opnorm=None, 
     ko.m = int(min(mmin, mmax) if m is None else m)
     ko.hermitian = -1 if ishermitian is None else int(bool(ishermitian))
     ko.task1 = 1 if task1 else 0
+    if _normU is not None:  # row-sharded callers supply the global norm(u[:, 2:end], 1)
+        ko.normU = float(_normU)
     stats = (C.c_int64 * 5)()
     eng.bind_stream()
     st = eng.lib.b200k_kiops(eng.handle, op.ptr, tau_flat.size, tau_flat.ctypes.data_as(_lib.c_double_p),

@@ -139,7 +139,7 @@ __global__ void csr_analyze_kernel(int n, const int *rowptr, const int *colind, 
             const double v = val[e];
             s += fabs(v);
             const int c = colind[e];
-            if (c == r) continue;
+            if (c == r || c >= n) continue;  // c >= n: halo column of a row-sharded block
             // find the transposed entry (c, r): sum duplicates, absent means 0
             double vt = 0.0;
             const int f0 = rowptr[c], f1 = rowptr[c + 1];

@@ -95,7 +95,28 @@ struct b200k_context {
     float krylov_ms = 0.f, project_ms = 0.f;
 };
 
+struct b200k_comm {
+    b200k_context *ctx = nullptr;
+    int rank = 0, nranks = 1;
+    long long xlen = 0;
+    int cpad = 0;
+    size_t bytes = 0;
+    void *local = nullptr;
+    void *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool connected = false;
+    unsigned bar_base = 0;  // arrivals accumulated by all previous launches (identical on every rank)
+    // layout of each rank's buffer: [256 B barrier word][part 2*MAXCOL*cpad][partn 4*cpad][xbuf 2*xlen] doubles
+    unsigned *bar_of(int r) const { return reinterpret_cast<unsigned *>(peer[r]); }
+    double *part_of(int r) const { return reinterpret_cast<double *>(reinterpret_cast<char *>(peer[r]) + 256); }
+    double *partn_of(int r) const { return part_of(r) + (size_t)2 * MAXCOL * cpad; }
+    double *xbuf_of(int r) const { return partn_of(r) + (size_t)4 * cpad; }
+};
+
 struct b200k_operator {
+    b200k_comm *comm = nullptr;  // row-sharded operator
+    long long nhalo = 0;
+    DevBuf send_row, send_peer, send_pos, send_ofs;
+    std::vector<int> send_row_host;
     b200k_context *ctx = nullptr;
     int kind = 0;  // 0 CSR, 1 dense
     long long n = 0, nnz = 0;
@@ -260,7 +281,53 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
     P.stat = h->stat.as<int>();
     P.btail = h->btail.as<double>();
 
-    CK(h, cudaMemsetAsync(P.bar, 0, (size_t)nt * 4, h->stream));
+    // team spanning GPUs (row-sharded operator) or a single GPU (peer tables point at the local buffers)
+    b200k_comm *cm = op->comm;
+    P.nranks = 1;
+    P.myrank = 0;
+    P.nhalo = 0;
+    P.cpad = CPAD;
+    P.peer_part[0] = P.part;
+    P.peer_partn[0] = P.partn;
+    P.peer_bar[0] = P.bar;
+    P.peer_xbuf[0] = P.xbuf;
+    unsigned bar_base = 0;
+    if (cm) {
+        if (!cm->connected) return fail(h, B200K_ECOMM, "communicator is not connected");
+        if (!vec2 || h->force_ldg || c.nprob != 1 || c.g.nteams != 1)
+            return fail(h, B200K_EUNSUPPORTED, "row-sharded operators need even nloc/ldv, 16-byte aligned vectors, one problem");
+        if (n + op->nhalo + c.p > cm->xlen) return fail(h, B200K_EDIM, "communicator gather buffer (xlen) too small");
+        P.nranks = cm->nranks;
+        P.myrank = cm->rank;
+        P.nhalo = (int)op->nhalo;
+        P.cpad = cm->cpad;
+        P.xlen = cm->xlen;
+        for (int r = 0; r < cm->nranks; ++r) {
+            P.peer_part[r] = cm->part_of(r);
+            P.peer_partn[r] = cm->partn_of(r);
+            P.peer_bar[r] = cm->bar_of(r);
+            P.peer_xbuf[r] = cm->xbuf_of(r);
+        }
+        // halo push ranges per CTA slice
+        std::vector<int> ofs(c.g.C + 1, 0);
+        const std::vector<int> &sr = op->send_row_host;
+        for (int q = 0; q <= c.g.C; ++q) {
+            const long long bound = std::min<long long>(n, (long long)q * c.g.slice);
+            ofs[q] = (int)(std::lower_bound(sr.begin(), sr.end(), (int)bound) - sr.begin());
+        }
+        ofs[c.g.C] = (int)sr.size();
+        CK(h, op->send_ofs.ensure((size_t)(c.g.C + 1) * 4));
+        CK(h, cudaMemcpyAsync(op->send_ofs.p, ofs.data(), (size_t)(c.g.C + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));  // ofs is a stack vector
+        P.send_row = op->send_row.as<int>();
+        P.send_peer = op->send_peer.as<int>();
+        P.send_pos = op->send_pos.as<int>();
+        P.send_ofs = op->send_ofs.as<int>();
+        bar_base = cm->bar_base;
+    } else {
+        CK(h, cudaMemsetAsync(P.bar, 0, (size_t)nt * 4, h->stream));
+    }
+    P.bar_base = bar_base;
     CK(h, cudaMemsetAsync(P.Hd, 0, (size_t)c.nprob * P.H_stride * 8, h->stream));
     CK(h, cudaMemsetAsync(P.scal, 0, (size_t)c.nprob * 4 * 8, h->stream));
     if (c.p > 0 && c.j0 == 0)
@@ -449,10 +516,21 @@ int arnoldi_core(b200k_context *h, b200k_operator *op, const double *b, const b2
     if (p > 0) make_btail(p, o->t, o->mu, btail);
     c.btail_host = btail;
     c.g = single_geom(h, n);
+    if (op->comm && c.g.C != h->max_ctas)
+        return fail(h, B200K_EUNSUPPORTED, "row-sharded operators need at least 16 rows per CTA on every rank");
     int st = launch_krylov(h, c);
     if (st) return st;
     st = fetch_krylov(h, 1, m);
     if (st) return st;
+    if (op->comm) {  // the multi-GPU barrier counters are never reset: account for this launch's arrivals
+        const double b0 = o->init == 0 ? h->scalh.as<double>()[0] : *beta;
+        unsigned nbar = 1;  // firststep! barrier, or the halo staging barrier of a resumed factorisation
+        if (b0 != 0.0) {
+            const int js = c.j0 == 0 ? 1 : c.j0;
+            nbar += 2u * (unsigned)(h->stath.as<int>()[0] - js + 1);
+        }
+        op->comm->bar_base += nbar * (unsigned)(c.g.C * op->comm->nranks);
+    }
     const double *Hh = h->Hh.as<double>();
     const int ldhd = m + 1;
     if (o->init == 0) *beta = h->scalh.as<double>()[0];
@@ -558,6 +636,7 @@ void b200k_kiops_opts_default(b200k_kiops_opts *o) {
     o->hermitian = -1;
     o->task1 = 0;
     o->opnorm = NAN;
+    o->normU = NAN;
 }
 
 int b200k_create(b200k_handle_t *out, int device, void *stream) {
@@ -798,6 +877,10 @@ int b200k_op_dense_create(b200k_handle_t h, int64_t n, const double *A, int64_t 
 int b200k_op_destroy(b200k_op_t op) {
     if (!op) return B200K_OK;
     if (op->ctx) cudaSetDevice(op->ctx->device);
+    op->send_row.release();
+    op->send_peer.release();
+    op->send_pos.release();
+    op->send_ofs.release();
     op->rowptr.release();
     op->colind.release();
     op->val.release();
@@ -1068,6 +1151,14 @@ int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out
     };
     if (pad_col) {
         cudaMemsetAsync(Bbuf.p, 0, (size_t)ldbm * p * 8, h->stream);
+    } else if (ko->normU == ko->normU) {  // supplied by the caller (row-sharded: the global 1-norm)
+        if (ko->normU > 0) {
+            const double ex = std::ceil(std::log2(ko->normU));
+            nu = std::exp2(-ex);
+            mu = std::exp2(ex);
+        }
+        flip_scale_kernel<<<1024, 256, 0, h->stream>>>(n, p, U, ldu, nu, Bbuf.as<double>(), ldbm);
+        h->launches += 1;
     } else {
         const int nblk = 1024;
         e = h->tmp.ensure((size_t)nblk * 8);
@@ -1274,6 +1365,107 @@ int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out
         stats[2] = krystep;
         stats[3] = exps;
         stats[4] = m;
+    }
+    return B200K_OK;
+}
+
+// ---- row sharding across GPUs -----------------------------------------------------------------------------
+int b200k_comm_create(b200k_handle_t h, int rank, int nranks, int64_t xlen, unsigned char *handle_out,
+                      b200k_comm_t *out) {
+    if (!h || !handle_out || !out) return B200K_EARG;
+    *out = nullptr;
+    if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return fail(h, B200K_EARG, "1 <= nranks <= 8");
+    if (xlen < 16) return fail(h, B200K_EARG, "xlen too small");
+    CK(h, cudaSetDevice(h->device));
+    b200k_comm *cm = new b200k_comm();
+    cm->ctx = h;
+    cm->rank = rank;
+    cm->nranks = nranks;
+    cm->xlen = round_up(xlen, 16);
+    cm->cpad = (int)round_up((long long)h->max_ctas * nranks, 32);
+    cm->bytes = 256 + sizeof(double) * ((size_t)2 * MAXCOL * cm->cpad + (size_t)4 * cm->cpad + (size_t)2 * cm->xlen);
+    cudaError_t e = cudaMalloc(&cm->local, cm->bytes);
+    if (e == cudaSuccess) e = cudaMemset(cm->local, 0, cm->bytes);
+    cudaIpcMemHandle_t hd;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hd, cm->local);
+    if (e != cudaSuccess) {
+        if (cm->local) cudaFree(cm->local);
+        delete cm;
+        return fail(h, B200K_ECOMM, std::string("comm_create: ") + cudaGetErrorString(e));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200K_IPC_HANDLE_BYTES, "IPC handle size");
+    std::memcpy(handle_out, &hd, sizeof(hd));
+    cm->peer[rank] = cm->local;
+    *out = cm;
+    return B200K_OK;
+}
+
+int b200k_comm_connect(b200k_comm_t cm, const unsigned char *all_handles) {
+    if (!cm || !all_handles) return B200K_EARG;
+    b200k_context *h = cm->ctx;
+    CK(h, cudaSetDevice(h->device));
+    for (int r = 0; r < cm->nranks; ++r) {
+        if (r == cm->rank) continue;
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, all_handles + (size_t)r * B200K_IPC_HANDLE_BYTES, sizeof(hd));
+        cudaError_t e = cudaIpcOpenMemHandle(&cm->peer[r], hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return fail(h, B200K_ECOMM, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " +
+                                            cudaGetErrorString(e));
+    }
+    cm->connected = true;
+    return B200K_OK;
+}
+
+int b200k_comm_destroy(b200k_comm_t cm) {
+    if (!cm) return B200K_OK;
+    if (cm->ctx) {
+        cudaSetDevice(cm->ctx->device);
+        cudaStreamSynchronize(cm->ctx->stream);
+    }
+    for (int r = 0; r < cm->nranks; ++r)
+        if (r != cm->rank && cm->peer[r]) cudaIpcCloseMemHandle(cm->peer[r]);
+    if (cm->local) cudaFree(cm->local);
+    delete cm;
+    return B200K_OK;
+}
+
+int b200k_op_csr_create_sharded(b200k_handle_t h, b200k_comm_t cm, int64_t nloc, int64_t nhalo, int64_t nnz,
+                                const int32_t *rowptr, const int32_t *colind, const double *val, int index_base,
+                                int location, int is_hermitian, int64_t nsend, const int32_t *send_row,
+                                const int32_t *send_peer, const int32_t *send_pos, b200k_op_t *out) {
+    if (!h || !cm || !out) return B200K_EARG;
+    if (nhalo < 0 || nsend < 0 || (nsend > 0 && (!send_row || !send_peer || !send_pos)))
+        return fail(h, B200K_EARG, "invalid halo description");
+    if (nloc % 2 != 0) return fail(h, B200K_EUNSUPPORTED, "row-sharded blocks need an even number of rows");
+    int st = b200k_op_csr_create(h, nloc, nnz, rowptr, colind, val, index_base, location, out);
+    if (st) return st;
+    b200k_operator *op = *out;
+    op->comm = cm;
+    op->nhalo = nhalo;
+    op->is_herm = is_hermitian ? 1 : 0;  // the local block cannot decide symmetry of the global operator
+    for (int64_t i = 0; i < nsend; ++i) {
+        if (send_row[i] < 0 || send_row[i] >= nloc || send_peer[i] < 0 || send_peer[i] >= cm->nranks ||
+            (i > 0 && send_row[i] < send_row[i - 1])) {
+            b200k_op_destroy(op);
+            *out = nullptr;
+            return fail(h, B200K_EARG, "send list must be sorted by row with valid peers");
+        }
+    }
+    op->send_row_host.assign(send_row, send_row + nsend);
+    const size_t bytes = (size_t)std::max<int64_t>(nsend, 1) * 4;
+    cudaError_t e = op->send_row.ensure(bytes);
+    if (e == cudaSuccess) e = op->send_peer.ensure(bytes);
+    if (e == cudaSuccess) e = op->send_pos.ensure(bytes);
+    if (e == cudaSuccess && nsend > 0) {
+        cudaMemcpy(op->send_row.p, send_row, (size_t)nsend * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(op->send_peer.p, send_peer, (size_t)nsend * 4, cudaMemcpyHostToDevice);
+        e = cudaMemcpy(op->send_pos.p, send_pos, (size_t)nsend * 4, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        b200k_op_destroy(op);
+        *out = nullptr;
+        return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
     }
     return B200K_OK;
 }

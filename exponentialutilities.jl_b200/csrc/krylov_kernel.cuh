@@ -93,6 +93,22 @@ struct KrylovParams {
     int nslot;         // ring depth
     int tile_rows;     // rows per basis tile (multiple of 16, <= 4096)
     int dscratch_off;  // byte offset of the dense mat-vec reduction scratch in dynamic shared memory
+    // row sharding across GPUs (krylov_kernel_tma.cuh; nranks == 1: single GPU, peers point to local buffers).
+    // Every CTA of every GPU writes its partial sums into the inbox of EVERY GPU (peer stores over NVLink) and
+    // arrives on every GPU's barrier word with a system-scope atomic: the all-reduce is the team barrier.
+    int nranks;
+    int myrank;
+    unsigned bar_base;      // barrier arrivals accumulated by earlier launches (multi-GPU counters are never reset)
+    int nhalo;              // remote x entries this GPU gathers (appended after the n local entries)
+    int cpad;               // row length of the partial-sum tables: round_up(team_size * nranks, 32)
+    double *peer_part[8];   // [2][MAXCOL][cpad] on each GPU
+    double *peer_partn[8];  // [4][cpad]
+    unsigned *peer_bar[8];
+    double *peer_xbuf[8];   // [2][xlen]: gather source incl. the halo landing zone [nloc, nloc + nhalo)
+    const int *send_row;    // halo push list sorted by local row: row, destination rank, position in its xbuf
+    const int *send_peer;
+    const int *send_pos;
+    const int *send_ofs;    // [team_size + 1] range of the list owned by each CTA slice
 };
 
 struct __align__(128) SmemFixed {

@@ -50,15 +50,33 @@ struct __align__(128) SmemTma {
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-__device__ __forceinline__ void team_barrier_c(Team &tm) {
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Team barrier.  Single GPU: the cooperative-groups grid-sync protocol on one counter.  Row-sharded over
+// several GPUs: every CTA arrives on the counter of EVERY GPU with a system-scope atomic over NVLink after a
+// system-scope fence, and waits on its own GPU's counter -- this is also what publishes the partial sums and
+// halo values that were pushed to the peers before the barrier (the fused all-reduce / halo exchange).
+__device__ __forceinline__ void team_barrier_c(Team &tm, const KrylovParams &P) {
     consumer_sync();
     if (threadIdx.x == 0) {
-        tm.target += (unsigned)tm.C;
-        __threadfence();
-        atomicAdd(tm.bar, 1u);
-        while ((int)(ld_acquire_u32(tm.bar) - tm.target) < 0) {
+        tm.target += (unsigned)(tm.C * P.nranks);
+        if (P.nranks == 1) {
+            __threadfence();
+            atomicAdd(tm.bar, 1u);
+            while ((int)(ld_acquire_u32(tm.bar) - tm.target) < 0) {
+            }
+            __threadfence();
+        } else {
+            __threadfence_system();
+            for (int r = 0; r < P.nranks; ++r) atomicAdd_system(P.peer_bar[r], 1u);
+            while ((int)(ld_acquire_sys_u32(tm.bar) - tm.target) < 0) {
+            }
+            __threadfence_system();
         }
-        __threadfence();
     }
     consumer_sync();
 }
@@ -189,7 +207,8 @@ struct Cons {
     }
 };
 
-__device__ __forceinline__ void block_sum_to_c(Cons &cx, double v, double *out) {
+// CTA-wide deterministic sum; thread 0 stores it at offset `off` of the norm table of every GPU.
+__device__ __forceinline__ void block_sum_to_c(const KrylovParams &P, Cons &cx, double v, long long off) {
     v = warp_sum(v);
     if (cx.lane == 0) cx.S->redn[cx.warp] = v;
     consumer_sync();
@@ -197,8 +216,17 @@ __device__ __forceinline__ void block_sum_to_c(Cons &cx, double v, double *out) 
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) s += cx.S->redn[w];
-        *out = s;
+        for (int r = 0; r < P.nranks; ++r) P.peer_partn[r][off] = s;
     }
+}
+
+// Push this CTA's rows that other GPUs gather (halo) into their gather buffers (peer stores over NVLink).
+__device__ __forceinline__ void push_halo(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm,
+                                          long long xoff) {
+    if (P.nranks == 1) return;
+    const int e1 = P.send_ofs[tm.rank + 1];
+    for (int e = P.send_ofs[tm.rank] + cx.tid; e < e1; e += NTC)
+        P.peer_xbuf[P.send_peer[e]][xoff + P.send_pos[e]] = cx.ws[P.send_row[e] - G.r0];
 }
 
 __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *xsrc, double xscale) {
@@ -207,7 +235,7 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
     const int n = P.n, p = P.p;
     double *ws = cx.ws;
     if (p > 0) {
-        if (tid < p) S->xtail[tid] = xsrc[n + tid];
+        if (tid < p) S->xtail[tid] = xsrc[n + P.nhalo + tid];
         consumer_sync();
         if (tid < p) S->wtail[tid] = (tid < p - 1) ? S->xtail[tid + 1] * xscale : 0.0;
     }
@@ -295,7 +323,7 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
 }
 
 __device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
-                             int lo, int hi, double *part) {
+                             int lo, int hi, long long part_off) {
     SmemTma *S = cx.S;
     const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
     const double2 *ws2 = reinterpret_cast<const double2 *>(cx.ws);
@@ -331,7 +359,7 @@ __device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
                 }
             }
         }
-        if (P.p > 0 && tm.rank == 0 && tid == 0) {  // augmented tail rows (direct loads)
+        if (P.p > 0 && tm.rank == 0 && P.myrank == 0 && tid == 0) {  // augmented tail rows (direct loads)
 #pragma unroll
             for (int u = 0; u < CB; ++u)
                 if (u < nb)
@@ -346,7 +374,8 @@ __device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) s += S->red[buf][w][tid];
-            part[(long long)(cb - lo + tid) * CPAD + tm.rank] = s;
+            const long long off = part_off + (long long)(cb - lo + tid) * P.cpad + P.myrank * tm.C + tm.rank;
+            for (int r = 0; r < P.nranks; ++r) P.peer_part[r][off] = s;
         }
     }
 }
@@ -398,8 +427,8 @@ __device__ double update_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom 
         for (int c = uhi; c >= ulo; --c) wt = fma(-hs[c - ulo], V[(long long)c * P.ldv + P.n + tid], wt);
         S->wtail[tid] = wt;
         if (tm.rank == 0) {
-            xout[P.n + tid] = wt;
-            nrm = fma(wt, wt, nrm);
+            xout[P.n + P.nhalo + tid] = wt;
+            if (P.myrank == 0) nrm = fma(wt, wt, nrm);
         }
     }
     return nrm;
@@ -407,7 +436,7 @@ __device__ double update_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom 
 
 // One problem on the consumer side.  Mirrors krylov_body<2> of krylov_kernel.cuh.
 __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom &G, Team &tm, int prob, int nlocal,
-                                 double *xb0, double *xb1, double *part0, double *partn0) {
+                                 double *xb0, double *xb1, long long xoff0, long long part0, long long partn0) {
     SmemTma *S = cx.S;
     const int tid = cx.tid;
     const int n = P.n, p = P.p;
@@ -422,24 +451,32 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
     double xscale;
     int jstart;
     int m_out = P.m, breakdown = 0;
+    const int ctot = tm.C * P.nranks;                 // CTAs of the (possibly multi-GPU) team
+    const int gcta = P.myrank * tm.C + tm.rank;       // this CTA's index in it
+    const bool sharded = P.nranks > 1;
+    const bool via_xb0 = p > 0 || sharded;            // first gather source must carry tail / halo entries
+    const double *lpart = P.peer_part[P.myrank];      // this GPU's inboxes
+    const double *lpartn = P.peer_partn[P.myrank];
+    const int xt = n + P.nhalo;                       // offset of the augmented tail in the gather buffers
 
     if (P.j0 == 0) {  // firststep! (arnoldi.jl:230-250 / 257-279)
         double nrm = 0.0;
         for (int i = tid; i < units; i += NTC) {
             const double2 b2 = reinterpret_cast<const double2 *>(b + G.r0)[i];
             ws2[i] = b2;
-            if (p > 0) reinterpret_cast<double2 *>(xb0 + G.r0)[i] = b2;
+            if (via_xb0) reinterpret_cast<double2 *>(xb0 + G.r0)[i] = b2;
             nrm = fma(b2.x, b2.x, fma(b2.y, b2.y, nrm));
         }
         if (p > 0 && tm.rank == 0 && tid < p) {
             const double bt = P.btail[tid];
-            xb0[n + tid] = bt;
-            nrm = fma(bt, bt, nrm);
+            xb0[xt + tid] = bt;
+            if (P.myrank == 0) nrm = fma(bt, bt, nrm);
         }
-        double *pslot = partn0 + (2 + (nlocal & 1)) * CPAD;
-        block_sum_to_c(cx, nrm, pslot + tm.rank);
-        team_barrier_c(tm);
-        const double beta = sqrt(team_sum(pslot, tm.C, cx.lane));
+        const long long pslot = partn0 + (long long)(2 + (nlocal & 1)) * P.cpad;
+        block_sum_to_c(P, cx, nrm, pslot + gcta);
+        push_halo(P, cx, G, tm, xoff0);
+        team_barrier_c(tm, P);
+        const double beta = sqrt(team_sum(lpartn + pslot, ctot, cx.lane));
         if (tm.rank == 0 && tid == 0) P.scal[prob * 4] = beta;
         if (beta == 0.0) {
             if (tm.rank == 0 && tid == 0) {
@@ -456,7 +493,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
                 b2.y *= inv;
                 reinterpret_cast<double2 *>(V + G.r0)[i] = b2;
             }
-            xsrc = b;
+            xsrc = via_xb0 ? xb0 : b;
         } else {
             for (int i = tid; i < units; i += NTC) {
                 double2 b2 = ws2[i];
@@ -473,7 +510,21 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         xscale = 1.0 / beta;
         jstart = 1;
     } else {
-        xsrc = V + (long long)(P.j0 - 1) * ldv;
+        const double *vj = V + (long long)(P.j0 - 1) * ldv;
+        if (sharded) {  // the resumed column has no halo: stage it in the gather buffer and push the halo
+            for (int i = tid; i < units; i += NTC) {
+                const double2 v2 = reinterpret_cast<const double2 *>(vj + G.r0)[i];
+                ws2[i] = v2;
+                reinterpret_cast<double2 *>(xb0 + G.r0)[i] = v2;
+            }
+            if (p > 0 && tm.rank == 0 && tid < p) xb0[xt + tid] = vj[n + tid];
+            consumer_sync();
+            push_halo(P, cx, G, tm, xoff0);
+            team_barrier_c(tm, P);
+            xsrc = xb0;
+        } else {
+            xsrc = vj;
+        }
         xscale = 1.0;
         jstart = P.j0;
     }
@@ -484,20 +535,21 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         const int jc = j - 1;
         const int par = j & 1;
         double *xout = par ? xb1 : xb0;
-        double *part = part0 + (long long)par * MAXCOL * CPAD;
-        double *partn = partn0 + par * CPAD;
+        const long long xoff = xoff0 + (par ? P.xlen : 0);
+        const long long part = part0 + (long long)par * MAXCOL * P.cpad;
+        const long long partn = partn0 + (long long)par * P.cpad;
 
         matvec_phase_c(P, cx, G, xsrc, xscale);
 
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
         const int hi = jc;
         dots_phase_c(P, cx, G, tm, V, lo, hi, part);
-        team_barrier_c(tm);
+        team_barrier_c(tm, P);
 
         const int nc = hi - lo + 1;
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
         for (int ci = cx.warp; ci < nc; ci += NW) {
-            const double s = team_sum(part + (long long)ci * CPAD, tm.C, cx.lane);
+            const double s = team_sum(lpart + part + (long long)ci * P.cpad, ctot, cx.lane);
             if (cx.lane == 0) {
                 S->hs[lo + ci - ulo] = s;
                 if (tm.rank == 0) Hd[(long long)jc * ldh + lo + ci] = s;
@@ -507,10 +559,11 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         consumer_sync();
 
         const double nrm = update_phase_c(P, cx, G, tm, V, ulo, hi, xout);
-        block_sum_to_c(cx, nrm, partn + tm.rank);
-        team_barrier_c(tm);
+        block_sum_to_c(P, cx, nrm, partn + gcta);
+        push_halo(P, cx, G, tm, xoff);  // after block_sum's CTA barrier: the whole w slice is in place
+        team_barrier_c(tm, P);
 
-        const double beta = sqrt(team_sum(partn, tm.C, cx.lane));
+        const double beta = sqrt(team_sum(lpartn + partn, ctot, cx.lane));
         if (tm.rank == 0 && tid == 0) Hd[(long long)jc * ldh + jc + 1] = beta;
         {
             double *vn = V + (long long)(jc + 1) * ldv;
@@ -552,8 +605,8 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
     Team tm;
     tm.rank = blockIdx.x % P.team_size;
     tm.C = P.team_size;
-    tm.bar = P.bar + team;
-    tm.target = 0;
+    tm.bar = P.peer_bar[P.myrank] + team;
+    tm.target = P.bar_base;
     TmaGeom G;
     G.r0 = min(P.n, tm.rank * P.slice);
     G.nrows = min(P.n, G.r0 + P.slice) - G.r0;
@@ -582,10 +635,11 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
     }
     __syncthreads();
 
-    double *xb0 = P.xbuf + (long long)team * 2 * P.xlen;
+    const long long xoff0 = (long long)team * 2 * P.xlen;
+    double *xb0 = P.peer_xbuf[P.myrank] + xoff0;
     double *xb1 = xb0 + P.xlen;
-    double *part0 = P.part + (long long)team * 2 * MAXCOL * CPAD;
-    double *partn0 = P.partn + (long long)team * 4 * CPAD;
+    const long long part0 = (long long)team * 2 * MAXCOL * P.cpad;
+    const long long partn0 = (long long)team * 4 * P.cpad;
 
     const bool is_producer = tid >= NTC;
     Cons cx;
@@ -607,7 +661,7 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
             __syncwarp();
         } else {
             cx.rg = Ring{ring, P.nslot, 0, 0u};
-            consumer_problem(P, cx, G, tm, prob, nlocal, xb0, xb1, part0, partn0);
+            consumer_problem(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
             consumer_sync();
             if (tid == 0) S->stop_seq = nlocal + 1;
         }

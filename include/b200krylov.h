@@ -149,6 +149,7 @@ typedef struct {
     int hermitian;  /* -1: ishermitian(A) */
     int task1;      /* false */
     double opnorm;  /* accepted and unused, as in the reference */
+    double normU;   /* norm(u[:, 2:end], 1); NaN = computed by the library (row-sharded callers pass the global sum) */
 } b200k_kiops_opts;
 void b200k_kiops_opts_default(b200k_kiops_opts *o);
 /* tau_out: HOST, ntau values; numSteps follows the reference (`size(tau_out, 2)`): pass
@@ -158,6 +159,34 @@ void b200k_kiops_opts_default(b200k_kiops_opts *o);
 int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out, int tau_is_row,
                 const double *U, int64_t ldu, int ppo, const b200k_kiops_opts *opts, double *W,
                 int64_t ldw, int64_t *stats);
+
+/* ---- row sharding of ONE vector across the GPUs of a node (one process per GPU) --------------------------
+ * No reference equivalent (the reference has no distributed code); this is how
+ * arnoldi!/expv/phiv/kiops scale past one GPU.  Rank r owns a contiguous block of rows of every vector and of
+ * the operator; H, beta and the p augmented rows are replicated (every rank computes bitwise identical values).
+ * Per Krylov step the only exchanges are (i) the halo entries of the gather vector and (ii) the <= m+1 partial
+ * inner products / the norm.  Both are done INSIDE the persistent kernel: every CTA stores its contributions
+ * straight into the peers' buffers (peer-mapped memory over NVLink) and the team barrier is extended across
+ * GPUs with system-scope atomics -- there is no NCCL call on the data path.  The host only exchanges the
+ * 64-byte CUDA IPC handles once (torch.distributed / MPI / anything). */
+typedef struct b200k_comm *b200k_comm_t;
+#define B200K_IPC_HANDLE_BYTES 64
+/* Allocate this rank's peer-visible buffer (barrier word, partial-sum inboxes, two gather buffers of xlen
+ * doubles: nloc local entries | halo landing zone | augmented tail) and return its IPC handle.  xlen must be
+ * the same on every rank (max over ranks of nloc + nhalo, plus 16). */
+int b200k_comm_create(b200k_handle_t h, int rank, int nranks, int64_t xlen, unsigned char *handle_out,
+                      b200k_comm_t *comm);
+/* all_handles: nranks x 64 bytes in rank order.  Maps every peer's buffer (cudaIpcOpenMemHandle). */
+int b200k_comm_connect(b200k_comm_t comm, const unsigned char *all_handles);
+int b200k_comm_destroy(b200k_comm_t comm);
+/* This rank's row block of a CSR operator.  colind are LOCAL gather indices: [0, nloc) = own rows,
+ * [nloc, nloc + nhalo) = the rank's sorted list of remote columns.  The send list (HOST arrays, sorted by
+ * send_row) names, for every own row some other rank gathers, the destination rank and the position in its
+ * gather buffer.  is_hermitian: LinearAlgebra.ishermitian of the GLOBAL operator (cannot be decided locally). */
+int b200k_op_csr_create_sharded(b200k_handle_t h, b200k_comm_t comm, int64_t nloc, int64_t nhalo, int64_t nnz,
+                                const int32_t *rowptr, const int32_t *colind, const double *val, int index_base,
+                                int location, int is_hermitian, int64_t nsend, const int32_t *send_row,
+                                const int32_t *send_peer, const int32_t *send_pos, b200k_op_t *op);
 
 /* ---- small dense matrix functions (host, m <= ~130) ----------------------------------------- */
 /* exponential!(A, ExpMethodHigham2005Base()) in place (src/exp_baseexp.jl:112-161). */

@@ -1,0 +1,99 @@
+"""Row-sharded expv / kiops across the GPUs of one node: parity against the CPU oracle, then timings.
+Launch:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+             scripts/sharded_check.py [parity] [c2] [c4]"""
+import os, sys, time, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import eu_b200 as eu
+from conftest import laplacian2d, convdiff2d, relerr
+
+rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+which = set(sys.argv[1:]) or {"parity"}
+P = eu.parallel
+
+def log(*a):
+    if rank == 0: print(*a, flush=True)
+
+def gather_rows(x_local, ranges):
+    """all ranks' row blocks -> full vector on every rank (test plumbing)"""
+    outs = [torch.empty(r[1], dtype=torch.float64, device="cuda") for r in ranges]
+    dist.all_gather(outs, x_local.contiguous())
+    return torch.cat(outs).cpu().numpy()
+
+def make(A, herm):
+    n = A.shape[0]
+    ranges = P.row_partition(n, world)
+    r0, nl = ranges[rank]
+    sop = P.ShardedOperator(P.local_block(A, r0, nl), r0, n, ishermitian=herm)
+    return sop, ranges, r0, nl
+
+if "parity" in which:
+    from oracle import oracle as O
+    for name, A, herm in (("laplacian 200x240", laplacian2d(200, 240), True), ("convdiff 200x240", convdiff2d(200, 240), False)):
+        n = A.shape[0]
+        sop, ranges, r0, nl = make(A, herm)
+        b = np.random.default_rng(0).standard_normal(n)
+        bl = torch.from_numpy(b[r0:r0 + nl]).cuda()
+        for h in ([True, False] if herm else [False]):
+            w = eu.expv(1.0, sop.op, bl, m=30, ishermitian=h)
+            wf = gather_rows(w, ranges)
+            if rank == 0:
+                print(f"[{name}] expv herm={h} relerr {relerr(wf, O.expv(1.0, A, b, m=30, ishermitian_=h)):.3e}", flush=True)
+        # arnoldi continuation + phiv on the sharded basis
+        Ks = eu.KrylovSubspace(nl, 20, engine=sop.engine)
+        eu.arnoldi_(Ks, sop.op, bl, m=10, ishermitian=False)
+        eu.arnoldi_(Ks, sop.op, bl, m=20, ishermitian=False, init=10)
+        Ko = O.KrylovSubspace(n, 20); O.arnoldi_(Ko, A, b, m=20, ishermitian_=False)
+        Wl = eu.phiv(0.5, Ks, 3)
+        Wf = np.stack([gather_rows(Wl[:, c].contiguous(), ranges) for c in range(4)], 1)
+        if rank == 0:
+            print(f"[{name}] continuation H err {np.abs(Ks.getH() - Ko.getH()).max():.2e}  phiv relerr {relerr(Wf, O.phiv_ks(0.5, Ko, 3)):.3e}", flush=True)
+        # kiops (augmented operator, replicated tail rows)
+        u = np.random.default_rng(4).standard_normal((n, 2))
+        for h in ([True, False] if herm else [False]):
+            wl, st = P.kiops_sharded(1.0, sop, torch.from_numpy(u[r0:r0 + nl]).cuda(), ishermitian=h)
+            wf = gather_rows(torch.from_numpy(np.ascontiguousarray(wl[:, 0])).cuda(), ranges)
+            if rank == 0:
+                wo, so = O.kiops(1.0, A, u, ishermitian_=h)
+                print(f"[{name}] kiops herm={h} relerr {relerr(wf, wo[:, 0]):.3e} stats {st} vs {so}", flush=True)
+        dist.barrier(); sop.close()
+
+def timed(fn, reps, warm=3):
+    for _ in range(warm): fn()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+if "c2" in which:
+    A = laplacian2d(1000, 1000); n = 10**6
+    sop, ranges, r0, nl = make(A, True)
+    bl = torch.randn(nl, dtype=torch.float64, device="cuda")
+    res = {}
+    for h, name in ((False, "arnoldi"), (True, "lanczos")):
+        ms = timed(lambda: eu.expv(1.0, sop.op, bl, m=30, ishermitian=h), 20)
+        res[name] = {"ms_per_expv": ms, "expv_per_s": 1e3 / ms}
+    log(json.dumps({"c2_row_sharded": res, "n_gpus": world}))
+    dist.barrier(); sop.close()
+
+if "c4" in which:
+    A = laplacian2d(2500, 4000); n = 10**7
+    sop, ranges, r0, nl = make(A, True)
+    ul = torch.randn(nl, 2, dtype=torch.float64, device="cuda")
+    res = {}
+    for h in (True, False):
+        P.kiops_sharded(1.0, sop, ul, ishermitian=h)
+        dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(3): w, st = P.kiops_sharded(1.0, sop, ul, ishermitian=h)
+        torch.cuda.synchronize(); dist.barrier(); dt = (time.perf_counter() - t0) / 3
+        res[f"herm{int(h)}"] = {"s_per_solve": dt, "stats": st}
+    log(json.dumps({"c4_kiops_row_sharded": res, "n_gpus": world}))
+    dist.barrier(); sop.close()
+dist.destroy_process_group()
