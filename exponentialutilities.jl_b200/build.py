@@ -1,10 +1,15 @@
 """In-tree build of libb200krylov.so (sm_100a only) with nvcc.
 
 The shared library is the product; it is built next to this file so that it travels with the
-repository snapshot to the GPU box (it is git-ignored, not gpurun-ignored).
+repository snapshot to the GPU box (it is git-ignored, not gpurun-ignored).  Staleness is decided by a
+content hash of the sources stored beside the library (file mtimes do not survive the snapshot copy),
+and concurrent builders (several ranks importing at once) are serialised with a file lock; the
+library is replaced atomically.
 """
 from __future__ import annotations
 
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -12,8 +17,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200krylov.so")
+HASHFILE = LIB + ".srchash"
 SOURCES = ["b200krylov.cu"]
-DEPS = ["b200krylov.cu", "krylov_kernel.cuh", "aux_kernels.cuh", "ptx.cuh", "smallmat.hpp",
+DEPS = ["b200krylov.cu", "krylov_kernel.cuh", "krylov_kernel_tma.cuh", "aux_kernels.cuh", "ptx.cuh", "smallmat.hpp",
         os.path.join("..", "..", "include", "b200krylov.h")]
 
 NVCC_FLAGS = [
@@ -29,25 +35,50 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libb200krylov.so")
 
 
+def source_hash() -> str:
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for d in DEPS:
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(d.encode())
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(HASHFILE):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    try:
+        return open(HASHFILE).read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the library if it is missing or older than its sources; returns its path."""
+    """Compile the library if it is missing or its sources changed; returns its path."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # another process built it while we waited
+                return LIB
+            tmp = LIB + f".tmp{os.getpid()}"
+            cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB)
+            with open(HASHFILE, "w") as f:
+                f.write(source_hash())
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -104,10 +104,14 @@ struct b200k_comm {
     void *local = nullptr;
     void *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool connected = false;
-    unsigned bar_base = 0;  // arrivals accumulated by all previous launches (identical on every rank)
-    // layout of each rank's buffer: [256 B barrier word][part 2*MAXCOL*cpad][partn 4*cpad][xbuf 2*xlen] doubles
+    unsigned bar_base = 0;  // local arrivals accumulated by all previous launches (identical on every rank)
+    unsigned seq_base = 0;  // team barriers passed by all previous launches
+    // layout of each rank's buffer: [1 KB header: counter @0, flags @128 + 64 s][part 2*MAXCOL*cpad][partn 4*cpad]
+    // [xbuf 2*xlen] doubles
+    static constexpr size_t HDR = 1024;
     unsigned *bar_of(int r) const { return reinterpret_cast<unsigned *>(peer[r]); }
-    double *part_of(int r) const { return reinterpret_cast<double *>(reinterpret_cast<char *>(peer[r]) + 256); }
+    unsigned *flag_of(int r) const { return reinterpret_cast<unsigned *>(reinterpret_cast<char *>(peer[r]) + 128); }
+    double *part_of(int r) const { return reinterpret_cast<double *>(reinterpret_cast<char *>(peer[r]) + HDR); }
     double *partn_of(int r) const { return part_of(r) + (size_t)2 * MAXCOL * cpad; }
     double *xbuf_of(int r) const { return partn_of(r) + (size_t)4 * cpad; }
 };
@@ -306,6 +310,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
             P.peer_part[r] = cm->part_of(r);
             P.peer_partn[r] = cm->partn_of(r);
             P.peer_bar[r] = cm->bar_of(r);
+            P.peer_flag[r] = cm->flag_of(r);
             P.peer_xbuf[r] = cm->xbuf_of(r);
         }
         // halo push ranges per CTA slice
@@ -324,6 +329,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
         P.send_pos = op->send_pos.as<int>();
         P.send_ofs = op->send_ofs.as<int>();
         bar_base = cm->bar_base;
+        P.seq_base = cm->seq_base;
     } else {
         CK(h, cudaMemsetAsync(P.bar, 0, (size_t)nt * 4, h->stream));
     }
@@ -529,7 +535,8 @@ int arnoldi_core(b200k_context *h, b200k_operator *op, const double *b, const b2
             const int js = c.j0 == 0 ? 1 : c.j0;
             nbar += 2u * (unsigned)(h->stath.as<int>()[0] - js + 1);
         }
-        op->comm->bar_base += nbar * (unsigned)(c.g.C * op->comm->nranks);
+        op->comm->bar_base += nbar * (unsigned)c.g.C;
+        op->comm->seq_base += nbar;
     }
     const double *Hh = h->Hh.as<double>();
     const int ldhd = m + 1;
@@ -1383,7 +1390,7 @@ int b200k_comm_create(b200k_handle_t h, int rank, int nranks, int64_t xlen, unsi
     cm->nranks = nranks;
     cm->xlen = round_up(xlen, 16);
     cm->cpad = (int)round_up((long long)h->max_ctas * nranks, 32);
-    cm->bytes = 256 + sizeof(double) * ((size_t)2 * MAXCOL * cm->cpad + (size_t)4 * cm->cpad + (size_t)2 * cm->xlen);
+    cm->bytes = b200k_comm::HDR + sizeof(double) * ((size_t)2 * MAXCOL * cm->cpad + (size_t)4 * cm->cpad + (size_t)2 * cm->xlen);
     cudaError_t e = cudaMalloc(&cm->local, cm->bytes);
     if (e == cudaSuccess) e = cudaMemset(cm->local, 0, cm->bytes);
     cudaIpcMemHandle_t hd;

@@ -98,7 +98,9 @@ struct KrylovParams {
     // arrives on every GPU's barrier word with a system-scope atomic: the all-reduce is the team barrier.
     int nranks;
     int myrank;
-    unsigned bar_base;      // barrier arrivals accumulated by earlier launches (multi-GPU counters are never reset)
+    unsigned bar_base;      // local barrier arrivals accumulated by earlier launches (multi-GPU counters are never reset)
+    unsigned seq_base;      // team barriers passed by earlier launches
+    unsigned *peer_flag[8]; // per GPU: 8 flags (64-byte stride), flag[s] = last barrier GPU s has reached
     int nhalo;              // remote x entries this GPU gathers (appended after the n local entries)
     int cpad;               // row length of the partial-sum tables: round_up(team_size * nranks, 32)
     double *peer_part[8];   // [2][MAXCOL][cpad] on each GPU
@@ -163,6 +165,7 @@ __device__ __forceinline__ double warp_reduce8(double (&a)[CB], int lane) {
 struct Team {
     unsigned *bar;
     unsigned target;
+    unsigned seq;  // number of team barriers passed (multi-GPU flags carry this)
     int C;
     int rank;
 };

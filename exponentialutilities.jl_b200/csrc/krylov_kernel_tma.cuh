@@ -50,6 +50,9 @@ struct __align__(128) SmemTma {
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -57,13 +60,13 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
 }
 
 // Team barrier.  Single GPU: the cooperative-groups grid-sync protocol on one counter.  Row-sharded over
-// several GPUs: every CTA arrives on the counter of EVERY GPU with a system-scope atomic over NVLink after a
-// system-scope fence, and waits on its own GPU's counter -- this is also what publishes the partial sums and
-// halo values that were pushed to the peers before the barrier (the fused all-reduce / halo exchange).
+// several GPUs: a two-level barrier over NVLink peer memory (local counter + one flag per peer GPU); it is
+// also what publishes the partial sums and halo values that the CTAs stored into the peers' buffers before
+// arriving (the fused all-reduce / halo exchange).
 __device__ __forceinline__ void team_barrier_c(Team &tm, const KrylovParams &P) {
     consumer_sync();
     if (threadIdx.x == 0) {
-        tm.target += (unsigned)(tm.C * P.nranks);
+        tm.target += (unsigned)tm.C;
         if (P.nranks == 1) {
             __threadfence();
             atomicAdd(tm.bar, 1u);
@@ -71,10 +74,22 @@ __device__ __forceinline__ void team_barrier_c(Team &tm, const KrylovParams &P) 
             }
             __threadfence();
         } else {
-            __threadfence_system();
-            for (int r = 0; r < P.nranks; ++r) atomicAdd_system(P.peer_bar[r], 1u);
-            while ((int)(ld_acquire_sys_u32(tm.bar) - tm.target) < 0) {
+            // hierarchical: CTAs arrive on their own GPU's counter; the last one to arrive tells every peer
+            // "GPU myrank reached barrier #seq" with ONE flag store per peer (instead of one remote atomic per CTA).
+            __threadfence_system();  // this CTA's stores into peer memory are performed before it arrives
+            const unsigned old = atomicAdd(tm.bar, 1u);
+            tm.seq += 1u;
+            if (old + 1u == tm.target) {
+                __threadfence_system();
+                for (int r = 0; r < P.nranks; ++r)
+                    if (r != P.myrank) st_release_sys_u32(P.peer_flag[r] + P.myrank * 16, tm.seq);
             }
+            while ((int)(ld_acquire_u32(tm.bar) - tm.target) < 0) {
+            }
+            for (int r = 0; r < P.nranks; ++r)
+                if (r != P.myrank)
+                    while ((int)(ld_acquire_sys_u32(P.peer_flag[P.myrank] + r * 16) - tm.seq) < 0) {
+                    }
             __threadfence_system();
         }
     }
@@ -607,6 +622,7 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
     tm.C = P.team_size;
     tm.bar = P.peer_bar[P.myrank] + team;
     tm.target = P.bar_base;
+    tm.seq = P.seq_base;
     TmaGeom G;
     G.r0 = min(P.n, tm.rank * P.slice);
     G.nrows = min(P.n, G.r0 + P.slice) - G.r0;
