@@ -77,6 +77,7 @@ struct b200k_context {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     int max_ctas = 0;  // co-resident CTAs of the persistent kernel
+    void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime (no libcuda link dependency)
     int force_ldg = 0; // B200K_KERNEL=ldg: use the LDG kernel even where the TMA-ring kernel applies
     int last_kernel = 0;  // 1 = LDG kernel, 2 = TMA-ring kernel
     std::string err;
@@ -87,6 +88,7 @@ struct b200k_context {
     HostBuf Hh, scalh, stath, Yh;
     // internal Krylov storage for the one-shot calls
     DevBuf V, bdev, wdev;
+    DevBuf kV, kB;  // kiops basis / flipped-u storage, kept across calls (cudaMalloc/cudaFree cost milliseconds)
     std::vector<double> H;
     smallmat::ExpWork expwork;
     // timing
@@ -341,6 +343,8 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
 
     // ---- kernel selection: TMA-ring kernel whenever the layout allows 16-byte-aligned bulk copies ----
     size_t smem = c.g.smem;
+    CUtensorMap tmapA;
+    std::memset(&tmapA, 0, sizeof(tmapA));
     const void *kern = (const void *)krylov_persistent_kernel;
     int threads = NT;
     if (vec2 && !h->force_ldg) {
@@ -371,6 +375,29 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
                 P.ch_rows = 32;
             }
         }
+        if (op->kind == 1 && c.g.slice <= 1024 && h->encode_tiled) {
+            // dense operator tiles through a 2-D tensor map: boxes of <= 256 rows x dense_cpt (<= 256) columns
+            int nrb = (c.g.slice + 255) / 256;
+            while (c.g.slice % nrb != 0 || (c.g.slice / nrb) % 2 != 0) ++nrb;
+            const int box_rows = c.g.slice / nrb;
+            int cpt = (int)std::min<size_t>(SLOT_BYTES / ((size_t)c.g.slice * 8), 256);
+            typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                          const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                          CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                          CUtensorMapFloatOOBfill);
+            const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)n};
+            const cuuint64_t gstr[1] = {(cuuint64_t)op->lda * 8};
+            const cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)cpt};
+            const cuuint32_t estr[2] = {1, 1};
+            if (cpt >= 1 && box_rows <= 256 &&
+                ((encode_fn)h->encode_tiled)(&tmapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)op->Ad, gdim, gstr, box,
+                                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                P.dense_cpt = cpt;
+                P.dense_box_rows = box_rows;
+            }
+        }
         P.dscratch_off = (int)(fixed + wsb + (size_t)nslot * SLOT_BYTES);
         smem = fixed + wsb + (size_t)nslot * SLOT_BYTES + extra;
         if (!P.w_in_smem) CK(h, h->wglob.ensure((size_t)nt * n * 8));
@@ -383,7 +410,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
     }
 
     if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
-    void *args[] = {(void *)&P};
+    void *args[] = {(void *)&P, (void *)&tmapA};
     CK(h, cudaLaunchCooperativeKernel(kern, dim3(c.g.C * c.g.nteams), dim3(threads), args, smem, h->stream));
     if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
     h->launches += 1;
@@ -682,6 +709,13 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
         delete h;
         return B200K_ECUDA;
     }
+    {
+        cudaDriverEntryPointQueryResult qres;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            h->encode_tiled = fn;
+    }
     if (const char *env = std::getenv("B200K_KERNEL")) h->force_ldg = std::strcmp(env, "ldg") == 0 ? 1 : 0;
     h->max_ctas = std::min(h->sm_count, CPAD);  // one CTA per SM
     for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
@@ -693,7 +727,7 @@ int b200k_destroy(b200k_handle_t h) {
     if (!h) return B200K_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
+    DevBuf *bufs[] = {&h->kV, &h->kB, &h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
                       &h->Y, &h->corr, &h->mvec, &h->betavec, &h->tmp, &h->V, &h->bdev, &h->wdev};
     for (DevBuf *b : bufs) b->release();
     HostBuf *hb[] = {&h->Hh, &h->scalh, &h->stath, &h->Yh};
@@ -1135,8 +1169,13 @@ int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out
     // Krylov storage: V (n+p) x (cap+1) grown like resize! (arnoldi.jl:80-93, contents preserved)
     const long long ldv = round_up(n + p, 16);
     int cap = m;
-    DevBuf Vbuf, Bbuf;
+    {   // start with room for the dimensions the controller usually grows to, unless that is a lot of memory
+        const int want = std::min(mmax, std::max(2 * m, 32));
+        if ((size_t)ldv * (want + 1) * 8 <= ((size_t)8 << 30)) cap = std::max(cap, want);
+    }
+    DevBuf &Vbuf = h->kV, &Bbuf = h->kB;
     CK(h, Vbuf.ensure((size_t)ldv * (cap + 1) * 8));
+    cap = std::max(cap, std::min(mmax, (int)(Vbuf.cap / ((size_t)ldv * 8)) - 1));  // use what is already there
     const int ldh = mmax + 2;
     std::vector<double> H((size_t)ldh * ldh, 0.0);
     int Ks_m = m;
@@ -1148,14 +1187,8 @@ int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out
     double nu = 1.0, mu = 1.0;
     const long long ldbm = round_up(n, 2);
     cudaError_t e = Bbuf.ensure((size_t)ldbm * p * 8);
-    if (e != cudaSuccess) {
-        Vbuf.release();
-        return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
-    }
-    auto cleanup = [&]() {
-        Vbuf.release();
-        Bbuf.release();
-    };
+    if (e != cudaSuccess) return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+    auto cleanup = [&]() {};  // the buffers belong to the handle
     if (pad_col) {
         cudaMemsetAsync(Bbuf.p, 0, (size_t)ldbm * p * 8, h->stream);
     } else if (ko->normU == ko->normU) {  // supplied by the caller (row-sharded: the global 1-norm)
@@ -1227,7 +1260,8 @@ int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out
                 return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
             }
             Vbuf.release();
-            Vbuf = nv;
+            Vbuf.p = nv.p;
+            Vbuf.cap = nv.cap;
             cap = m;
         }
         b200k_krylov_opts o;

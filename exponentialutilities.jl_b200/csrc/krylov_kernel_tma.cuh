@@ -20,6 +20,8 @@
 // A basis tile of column c may only be fetched once the consumers have written that column
 // (cols_ready > c, published after a generic->async proxy fence).
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "krylov_kernel.cuh"
 
 namespace b200k {
@@ -50,12 +52,14 @@ struct __align__(128) SmemTma {
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// relaxed system-scope accesses; ordering comes from ONE __threadfence_system() before the stores / after the
+// polling loop (a st.release.sys per peer would serialise one NVLink round trip per peer)
+__device__ __forceinline__ void st_relaxed_sys_u32(unsigned *p, unsigned v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
+__device__ __forceinline__ unsigned ld_relaxed_sys_u32(const unsigned *p) {
     unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -82,13 +86,13 @@ __device__ __forceinline__ void team_barrier_c(Team &tm, const KrylovParams &P) 
             if (old + 1u == tm.target) {
                 __threadfence_system();
                 for (int r = 0; r < P.nranks; ++r)
-                    if (r != P.myrank) st_release_sys_u32(P.peer_flag[r] + P.myrank * 16, tm.seq);
+                    if (r != P.myrank) st_relaxed_sys_u32(P.peer_flag[r] + P.myrank * 16, tm.seq);
             }
             while ((int)(ld_acquire_u32(tm.bar) - tm.target) < 0) {
             }
             for (int r = 0; r < P.nranks; ++r)
                 if (r != P.myrank)
-                    while ((int)(ld_acquire_sys_u32(P.peer_flag[P.myrank] + r * 16) - tm.seq) < 0) {
+                    while ((int)(ld_relaxed_sys_u32(P.peer_flag[P.myrank] + r * 16) - tm.seq) < 0) {
                     }
             __threadfence_system();
         }
@@ -120,15 +124,30 @@ struct TmaGeom {
 // ---------------------------------------------------------------------------------------------------
 // producer (one lane)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool prod_acquire(SmemTma *S, const Ring &rg, int seq) {
-    while (!mbar_try_wait(&S->empty[rg.slot], rg.phase ^ 1u)) {
-        if (S->stop_seq >= seq) return false;
+// All 32 lanes of the producer warp run this code; lane 0 waits / arms the barrier / issues the single-copy
+// tiles, and every lane issues its share of the column copies of a dense operator tile.
+__device__ __forceinline__ bool prod_acquire(SmemTma *S, const Ring &rg, int seq, int lane) {
+    int ok = 1;
+    if (lane == 0) {
+        while (!mbar_try_wait(&S->empty[rg.slot], rg.phase ^ 1u)) {
+            if (S->stop_seq >= seq) { ok = 0; break; }
+        }
     }
-    return true;
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
 }
 
-__device__ void producer_problem(const KrylovParams &P, SmemTma *S, Ring &rg, const TmaGeom &G, const double *V,
-                                 int seq, unsigned &issued) {
+__device__ __forceinline__ bool prod_wait_col(SmemTma *S, int col, int seq, int lane) {
+    int ok = 1;
+    if (lane == 0) {
+        while (S->cols_ready <= col) {
+            if (S->stop_seq >= seq) { ok = 0; break; }
+        }
+    }
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+
+__device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, SmemTma *S, Ring &rg,
+                                 const TmaGeom &G, const double *V, int seq, unsigned &issued, int lane) {
     const long long ldv = P.ldv;
     const int jstart = P.j0 == 0 ? 1 : P.j0;
     const int iopw = P.iop > 0 ? P.iop : P.m;
@@ -138,27 +157,47 @@ __device__ void producer_problem(const KrylovParams &P, SmemTma *S, Ring &rg, co
         const int jc = j - 1;
         if (P.op_kind == OP_CSR_STREAM) {
             for (int c = 0; c < G.nch; ++c) {
-                if (!prod_acquire(S, rg, seq)) { stopped = true; break; }
-                const int rs = G.r0 + c * P.ch_rows;
-                const int re = min(G.r0 + G.nrows, rs + P.ch_rows);
-                int a0, cnt;
-                if (G.nch <= MAXCH2) {
-                    a0 = S->chunk_a0[c];
-                    cnt = S->chunk_cnt[c];
-                } else {
-                    const int e0 = P.rowptr[rs], e1 = P.rowptr[re];
-                    a0 = e0 & ~3;
-                    cnt = ((e1 + 3) & ~3) - a0;
+                if (!prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
+                if (lane == 0) {
+                    const int rs = G.r0 + c * P.ch_rows;
+                    const int re = min(G.r0 + G.nrows, rs + P.ch_rows);
+                    int a0, cnt;
+                    if (G.nch <= MAXCH2) {
+                        a0 = S->chunk_a0[c];
+                        cnt = S->chunk_cnt[c];
+                    } else {
+                        const int e0 = P.rowptr[rs], e1 = P.rowptr[re];
+                        a0 = e0 & ~3;
+                        cnt = ((e1 + 3) & ~3) - a0;
+                    }
+                    const int rpc = (re - rs + 1 + 3) & ~3;
+                    S->slot_a0[rg.slot] = a0;
+                    unsigned char *dst = rg.ptr();
+                    mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)cnt * 12u + (uint32_t)rpc * 4u);
+                    if (cnt > 0) {
+                        bulk_g2s(dst, P.val + a0, (uint32_t)cnt * 8u, &S->full[rg.slot]);
+                        bulk_g2s(dst + (size_t)nnz_cap * 8, P.colind + a0, (uint32_t)cnt * 4u, &S->full[rg.slot]);
+                    }
+                    bulk_g2s(dst + (size_t)nnz_cap * 12, P.rowptr + rs, (uint32_t)rpc * 4u, &S->full[rg.slot]);
                 }
-                const int rpc = (re - rs + 1 + 3) & ~3;
-                S->slot_a0[rg.slot] = a0;
-                unsigned char *dst = rg.ptr();
-                mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)cnt * 12u + (uint32_t)rpc * 4u);
-                if (cnt > 0) {
-                    bulk_g2s(dst, P.val + a0, (uint32_t)cnt * 8u, &S->full[rg.slot]);
-                    bulk_g2s(dst + (size_t)nnz_cap * 8, P.colind + a0, (uint32_t)cnt * 4u, &S->full[rg.slot]);
+                rg.advance();
+                ++issued;
+            }
+            if (stopped) break;
+        } else if (P.op_kind == OP_DENSE && P.dense_cpt > 0 && G.nrows > 0) {
+            // dense operator: a tile = dense_cpt columns x the CTA's row slice, fetched as slice/box_rows
+            // tensor-map boxes (rows past n are zero-filled by the TMA unit and still count as bytes)
+            const int nrb = P.slice / P.dense_box_rows;
+            const uint32_t tbytes = (uint32_t)P.slice * (uint32_t)P.dense_cpt * 8u;
+            for (int c0 = 0; c0 < P.n; c0 += P.dense_cpt) {
+                if (!prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&S->full[rg.slot], tbytes);
+                    unsigned char *dst = rg.ptr();
+                    for (int rb = 0; rb < nrb; ++rb)
+                        tma_load_2d(dst + (size_t)rb * P.dense_box_rows * P.dense_cpt * 8, tmA,
+                                    G.r0 + rb * P.dense_box_rows, c0, &S->full[rg.slot]);
                 }
-                bulk_g2s(dst + (size_t)nnz_cap * 12, P.rowptr + rs, (uint32_t)rpc * 4u, &S->full[rg.slot]);
                 rg.advance();
                 ++issued;
             }
@@ -173,13 +212,12 @@ __device__ void producer_problem(const KrylovParams &P, SmemTma *S, Ring &rg, co
                 const int rows = min(G.TR, G.nrows - k * G.TR);
                 for (int u = 0; u < nb; ++u) {
                     const int col = cb + u;
-                    while (S->cols_ready <= col) {
-                        if (S->stop_seq >= seq) { stopped = true; break; }
+                    if (!prod_wait_col(S, col, seq, lane) || !prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 8u);
+                        bulk_g2s(rg.ptr(), V + (long long)col * ldv + G.r0 + (long long)k * G.TR, (uint32_t)rows * 8u,
+                                 &S->full[rg.slot]);
                     }
-                    if (stopped || !prod_acquire(S, rg, seq)) { stopped = true; break; }
-                    mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 8u);
-                    bulk_g2s(rg.ptr(), V + (long long)col * ldv + G.r0 + (long long)k * G.TR, (uint32_t)rows * 8u,
-                             &S->full[rg.slot]);
                     rg.advance();
                     ++issued;
                 }
@@ -188,22 +226,27 @@ __device__ void producer_problem(const KrylovParams &P, SmemTma *S, Ring &rg, co
         for (int k = 0; k < G.ntk && !stopped; ++k) {
             const int rows = min(G.TR, G.nrows - k * G.TR);
             for (int col = hi; col >= ulo; --col) {
-                if (!prod_acquire(S, rg, seq)) { stopped = true; break; }
-                mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 8u);
-                bulk_g2s(rg.ptr(), V + (long long)col * ldv + G.r0 + (long long)k * G.TR, (uint32_t)rows * 8u,
-                         &S->full[rg.slot]);
+                if (!prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 8u);
+                    bulk_g2s(rg.ptr(), V + (long long)col * ldv + G.r0 + (long long)k * G.TR, (uint32_t)rows * 8u,
+                             &S->full[rg.slot]);
+                }
                 rg.advance();
                 ++issued;
             }
         }
     }
-    // the consumers decide when the problem is over (m steps, happy breakdown, or beta == 0)
-    while (S->stop_seq < seq) {
+    if (lane == 0) {
+        // the consumers decide when the problem is over (m steps, happy breakdown, or beta == 0)
+        while (S->stop_seq < seq) {
+        }
+        // every copy that was issued must have landed before the ring is re-initialised / the CTA exits
+        const unsigned ns = (unsigned)rg.nslot;
+        const unsigned first = issued > ns ? issued - ns : 0u;
+        for (unsigned t = first; t < issued; ++t) mbar_wait(&S->full[t % ns], (t / ns) & 1u);
     }
-    // every copy that was issued must have landed before the ring is re-initialised / the CTA exits
-    const unsigned ns = (unsigned)rg.nslot;
-    const unsigned first = issued > ns ? issued - ns : 0u;
-    for (unsigned t = first; t < issued; ++t) mbar_wait(&S->full[t % ns], (t / ns) & 1u);
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -268,7 +311,19 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
                 const int a0 = S->slot_a0[cx.rg.slot];
                 const int e0 = rp[tid] - a0, e1 = rp[tid + 1] - a0;
                 double sum = 0.0;
-                for (int e = e0; e < e1; ++e) sum = fma(vs[e], xsrc[cs[e]], sum);
+                // gather in batches of 8: all x loads of a batch are in flight before the first FMA needs one
+                for (int eb = e0; eb < e1; eb += 8) {
+                    double av[8], xv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const bool ok = eb + u < e1;
+                        av[u] = ok ? vs[eb + u] : 0.0;
+                        xv[u] = 0.0;
+                        if (ok) xv[u] = xsrc[cs[eb + u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) sum = fma(av[u], xv[u], sum);
+                }
                 if (p > 0) {
                     const double *brow = P.Bm + (G.r0 + rl);
                     for (int k = 0; k < p; ++k) sum = fma(brow[(long long)k * P.ldb], S->xtail[k], sum);
@@ -290,7 +345,7 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
                 ws[rl] = sum * xscale;
             }
         }
-    } else {  // dense column-major (direct 16-byte loads; the ring is used for the basis only)
+    } else {  // dense column-major
         const int units = G.nrows / 2;
         int RL = 32;
         while (RL < units && RL < NTC) RL <<= 1;
@@ -298,30 +353,40 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
         const int ul = tid % RL, g = tid / RL;
         // NTC*2 doubles of reduction scratch behind the ring (the ring slots may have basis tiles in flight)
         double *dscratch = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(S) + P.dscratch_off);
-        for (int ubase = 0; ubase < units; ubase += RL) {
-            const int u = ubase + ul;
-            const bool valid = u < units;
+        if (P.dense_cpt > 0) {
+            // operator tiles arrive through the TMA ring: [dense_cpt columns][nrows] per slot
             double a0 = 0.0, a1 = 0.0;
-            if (valid) {
-                const double *ap = P.Ad + G.r0 + 2LL * u;
-#pragma unroll 8
-                for (int c = g; c < n; c += Gc) {
-                    const double xc = xsrc[c];
-                    const double2 a2 = ld_ro2(ap + (long long)c * P.lda);
-                    a0 = fma(a2.x, xc, a0);
-                    a1 = fma(a2.y, xc, a1);
+            if (G.nrows > 0) {
+                for (int c0 = 0; c0 < n; c0 += P.dense_cpt) {
+                    const int nc = min(P.dense_cpt, n - c0);
+                    cx.wait_full();
+                    if (ul < units) {
+                        // smem tile: [row box][column][box rows]; this thread's row pair sits in box rb
+                        const int bh = P.dense_box_rows >> 1;  // row pairs per box
+                        const int rb = ul / bh;
+                        const double2 *t2 = reinterpret_cast<const double2 *>(cx.rg.ptr()) +
+                                            (size_t)rb * bh * P.dense_cpt + (ul - rb * bh);
+#pragma unroll 4
+                        for (int cc = g; cc < nc; cc += Gc) {
+                            const double2 a2 = t2[(size_t)cc * bh];
+                            const double xc = xsrc[c0 + cc];
+                            a0 = fma(a2.x, xc, a0);
+                            a1 = fma(a2.y, xc, a1);
+                        }
+                    }
+                    cx.release();
                 }
             }
             dscratch[(g * RL + ul) * 2 + 0] = a0;
             dscratch[(g * RL + ul) * 2 + 1] = a1;
             consumer_sync();
-            if (g == 0 && valid) {
+            if (g == 0 && ul < units) {
                 double s0 = 0.0, s1 = 0.0;
                 for (int q = 0; q < Gc; ++q) {
                     s0 += dscratch[(q * RL + ul) * 2 + 0];
                     s1 += dscratch[(q * RL + ul) * 2 + 1];
                 }
-                const int rl = 2 * u;
+                const int rl = 2 * ul;
                 if (p > 0) {
                     for (int k = 0; k < p; ++k) {
                         s0 = fma(P.Bm[G.r0 + rl + (long long)k * P.ldb], S->xtail[k], s0);
@@ -331,7 +396,43 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
                 ws[rl] = s0 * xscale;
                 ws[rl + 1] = s1 * xscale;
             }
-            consumer_sync();
+        } else {
+            // direct 16-byte loads (slices with more than 1024 rows per CTA)
+            for (int ubase = 0; ubase < units; ubase += RL) {
+                const int u = ubase + ul;
+                const bool valid = u < units;
+                double a0 = 0.0, a1 = 0.0;
+                if (valid) {
+                    const double *ap = P.Ad + G.r0 + 2LL * u;
+#pragma unroll 8
+                    for (int c = g; c < n; c += Gc) {
+                        const double xc = xsrc[c];
+                        const double2 a2 = ld_ro2(ap + (long long)c * P.lda);
+                        a0 = fma(a2.x, xc, a0);
+                        a1 = fma(a2.y, xc, a1);
+                    }
+                }
+                dscratch[(g * RL + ul) * 2 + 0] = a0;
+                dscratch[(g * RL + ul) * 2 + 1] = a1;
+                consumer_sync();
+                if (g == 0 && valid) {
+                    double s0 = 0.0, s1 = 0.0;
+                    for (int q = 0; q < Gc; ++q) {
+                        s0 += dscratch[(q * RL + ul) * 2 + 0];
+                        s1 += dscratch[(q * RL + ul) * 2 + 1];
+                    }
+                    const int rl = 2 * u;
+                    if (p > 0) {
+                        for (int k = 0; k < p; ++k) {
+                            s0 = fma(P.Bm[G.r0 + rl + (long long)k * P.ldb], S->xtail[k], s0);
+                            s1 = fma(P.Bm[G.r0 + rl + 1 + (long long)k * P.ldb], S->xtail[k], s1);
+                        }
+                    }
+                    ws[rl] = s0 * xscale;
+                    ws[rl + 1] = s1 * xscale;
+                }
+                consumer_sync();
+            }
         }
     }
     consumer_sync();
@@ -608,7 +709,8 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
     }
 }
 
-__global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constant__ KrylovParams P) {
+__global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constant__ KrylovParams P,
+                                                            const __grid_constant__ CUtensorMap tmA) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemTma *S = reinterpret_cast<SmemTma *>(smem_raw);
     const size_t ws_bytes = P.w_in_smem ? (((size_t)P.slice * 8 + 127) & ~(size_t)127) : 0;
@@ -669,12 +771,9 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
     for (int prob = team; prob < P.nprob; prob += P.nteams) {
         ++nlocal;
         if (is_producer) {
-            if (tid == NTC) {
-                Ring rg{ring, P.nslot, 0, 0u};
-                unsigned issued = 0;
-                producer_problem(P, S, rg, G, P.V + (long long)prob * P.V_stride, nlocal + 1, issued);
-            }
-            __syncwarp();
+            Ring rg{ring, P.nslot, 0, 0u};
+            unsigned issued = 0;
+            producer_problem(P, &tmA, S, rg, G, P.V + (long long)prob * P.V_stride, nlocal + 1, issued, tid - NTC);
         } else {
             cx.rg = Ring{ring, P.nslot, 0, 0u};
             consumer_problem(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);

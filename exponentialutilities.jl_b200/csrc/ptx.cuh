@@ -69,6 +69,16 @@ __device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gm
         : "memory");
 }
 
+// 2-D tensor-map TMA load (SASS UTMALDG): box at element coordinates (c0 = row, c1 = column) of a column-major
+// fp64 matrix described by `tmap` (cuTensorMapEncodeTiled, no swizzle) -> dense [box cols][box rows] in smem.
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // ---- global loads ---------------------------------------------------------------------------------
 // Streaming 16-B load of basis data: coherent (the basis is written by this kernel), L1 no-allocate so
 // the L1 stays available for the x gather of the mat-vec.
