@@ -96,13 +96,17 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if _build.is_stale():
-        path = _build.build()
+    path = os.environ.get("B200K_LIB")  # A/B measurements against an older build of the library
+    if not path:
+        path = _build.LIB
+        if _build.is_stale():
+            path = _build.build()
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: run __graft_entry__.build() (nvcc, sm_100a)")
     lib = C.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
+        if os.environ.get("B200K_LIB") and not hasattr(lib, name):
+            continue  # older build used for an A/B measurement
         fn = getattr(lib, name)  # AttributeError if the ABI drifted
         fn.restype = res
         fn.argtypes = args

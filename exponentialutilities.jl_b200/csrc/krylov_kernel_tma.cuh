@@ -124,26 +124,20 @@ struct TmaGeom {
 // ---------------------------------------------------------------------------------------------------
 // producer (one lane)
 // ---------------------------------------------------------------------------------------------------
-// All 32 lanes of the producer warp run this code; lane 0 waits / arms the barrier / issues the single-copy
-// tiles, and every lane issues its share of the column copies of a dense operator tile.
-__device__ __forceinline__ bool prod_acquire(SmemTma *S, const Ring &rg, int seq, int lane) {
-    int ok = 1;
-    if (lane == 0) {
-        while (!mbar_try_wait(&S->empty[rg.slot], rg.phase ^ 1u)) {
-            if (S->stop_seq >= seq) { ok = 0; break; }
-        }
+// The producer is ONE lane of the producer warp (every copy, including the 2-D tensor-map boxes, is a single
+// instruction, so there is nothing for the other lanes to do).
+__device__ __forceinline__ bool prod_acquire(SmemTma *S, const Ring &rg, int seq, int) {
+    while (!mbar_try_wait(&S->empty[rg.slot], rg.phase ^ 1u)) {
+        if (S->stop_seq >= seq) return false;
     }
-    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+    return true;
 }
 
-__device__ __forceinline__ bool prod_wait_col(SmemTma *S, int col, int seq, int lane) {
-    int ok = 1;
-    if (lane == 0) {
-        while (S->cols_ready <= col) {
-            if (S->stop_seq >= seq) { ok = 0; break; }
-        }
+__device__ __forceinline__ bool prod_wait_col(SmemTma *S, int col, int seq, int) {
+    while (S->cols_ready <= col) {
+        if (S->stop_seq >= seq) return false;
     }
-    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+    return true;
 }
 
 __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, SmemTma *S, Ring &rg,
@@ -237,16 +231,13 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
             }
         }
     }
-    if (lane == 0) {
-        // the consumers decide when the problem is over (m steps, happy breakdown, or beta == 0)
-        while (S->stop_seq < seq) {
-        }
-        // every copy that was issued must have landed before the ring is re-initialised / the CTA exits
-        const unsigned ns = (unsigned)rg.nslot;
-        const unsigned first = issued > ns ? issued - ns : 0u;
-        for (unsigned t = first; t < issued; ++t) mbar_wait(&S->full[t % ns], (t / ns) & 1u);
+    // the consumers decide when the problem is over (m steps, happy breakdown, or beta == 0)
+    while (S->stop_seq < seq) {
     }
-    __syncwarp();
+    // every copy that was issued must have landed before the ring is re-initialised / the CTA exits
+    const unsigned ns = (unsigned)rg.nslot;
+    const unsigned first = issued > ns ? issued - ns : 0u;
+    for (unsigned t = first; t < issued; ++t) mbar_wait(&S->full[t % ns], (t / ns) & 1u);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -771,9 +762,12 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
     for (int prob = team; prob < P.nprob; prob += P.nteams) {
         ++nlocal;
         if (is_producer) {
-            Ring rg{ring, P.nslot, 0, 0u};
-            unsigned issued = 0;
-            producer_problem(P, &tmA, S, rg, G, P.V + (long long)prob * P.V_stride, nlocal + 1, issued, tid - NTC);
+            if (tid == NTC) {
+                Ring rg{ring, P.nslot, 0, 0u};
+                unsigned issued = 0;
+                producer_problem(P, &tmA, S, rg, G, P.V + (long long)prob * P.V_stride, nlocal + 1, issued, 0);
+            }
+            __syncwarp();
         } else {
             cx.rg = Ring{ring, P.nslot, 0, 0u};
             consumer_problem(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
