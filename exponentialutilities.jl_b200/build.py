@@ -19,8 +19,14 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200krylov.so")
 HASHFILE = LIB + ".srchash"
 SOURCES = ["b200krylov.cu"]
-DEPS = ["b200krylov.cu", "krylov_kernel.cuh", "krylov_kernel_tma.cuh", "aux_kernels.cuh", "ptx.cuh", "smallmat.hpp",
-        os.path.join("..", "..", "include", "b200krylov.h")]
+
+
+def _deps():
+    """Every source/header under csrc/ plus the public header (hashing all of them means a new header can
+    never be forgotten)."""
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h")))
+    return files + [os.path.join("..", "..", "include", "b200krylov.h")]
+
 
 NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17",
@@ -38,7 +44,7 @@ def _nvcc() -> str:
 def source_hash() -> str:
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
-    for d in DEPS:
+    for d in _deps():
         with open(os.path.join(CSRC, d), "rb") as f:
             h.update(d.encode())
             h.update(f.read())

@@ -10,11 +10,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <atomic>
 #include <vector>
 
 #include "aux_kernels.cuh"
 #include "krylov_kernel.cuh"
 #include "krylov_kernel_tma.cuh"
+#include "smallexp_kernel.cuh"
 #include "smallmat.hpp"
 
 using namespace b200k;
@@ -56,7 +59,10 @@ struct HostBuf {  // pinned
         p = nullptr;
         cap = 0;
         cudaError_t e = cudaMallocHost(&p, bytes + 256);
-        if (e == cudaSuccess) cap = bytes + 256;
+        if (e == cudaSuccess) {
+            cap = bytes + 256;
+            std::memset(p, 0, cap);
+        }
         return e;
     }
     void release() {
@@ -78,6 +84,9 @@ struct b200k_context {
     int sm_count = 0;
     int max_ctas = 0;  // co-resident CTAs of the persistent kernel
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime (no libcuda link dependency)
+    int host_smallexp = 0;  // B200K_SMALLEXP=host: one-shot / batched expv do the small exponential on the host
+    DevBuf tdev, errdev;
+    HostBuf errh;
     int force_ldg = 0; // B200K_KERNEL=ldg: use the LDG kernel even where the TMA-ring kernel applies
     int last_kernel = 0;  // 1 = LDG kernel, 2 = TMA-ring kernel
     std::string err;
@@ -432,18 +441,21 @@ int fetch_krylov(b200k_context *h, int nprob, int m) {
 }
 
 // Small dense phase of expv! on the host H (krylov_phiv.jl:223-244): y = exp(t H[1:m,1:m]) e1.
-int expv_small(b200k_context *h, double t, const double *H, int ldh, int m, double *y) {
-    if (smallmat::is_exactly_symmetric(m, H, ldh)) {
-        if (!smallmat::exp_symtridiag_e1(m, H, ldh, t, y))
-            return fail(h, B200K_ESINGULAR, "symmetric tridiagonal eigensolver did not converge");
-        return B200K_OK;
-    }
+// Thread-safe core (own workspace): 0 ok, 1 eigensolver failure, 2 singular Pade denominator.
+int expv_small_ws(double t, const double *H, int ldh, int m, double *y, smallmat::ExpWork &work) {
+    if (smallmat::is_exactly_symmetric(m, H, ldh)) return smallmat::exp_symtridiag_e1(m, H, ldh, t, y) ? 0 : 1;
     std::vector<double> Hc((size_t)m * m);
     for (int j = 0; j < m; ++j)
         for (int i = 0; i < m; ++i) Hc[(size_t)j * m + i] = t * H[(size_t)j * ldh + i];
-    const int st = smallmat::expm_higham2005base(m, Hc.data(), h->expwork);
-    if (st) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
+    if (smallmat::expm_higham2005base(m, Hc.data(), work)) return 2;
     for (int i = 0; i < m; ++i) y[i] = Hc[i];
+    return 0;
+}
+
+int expv_small(b200k_context *h, double t, const double *H, int ldh, int m, double *y) {
+    const int st = expv_small_ws(t, H, ldh, m, y, h->expwork);
+    if (st == 1) return fail(h, B200K_ESINGULAR, "symmetric tridiagonal eigensolver did not converge");
+    if (st == 2) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
     return B200K_OK;
 }
 
@@ -619,6 +631,82 @@ int phiv_ks_core(b200k_context *h, double t, const double *V, long long ldv, lon
     return launch_project(h, V, ldv, nrows, m, beta, C2.data(), m, k + 1, W, ldw, correct ? corr.data() : nullptr);
 }
 
+// Device-side small dense phase + projection for nprob problems whose factorisation (H, beta, m) is still in
+// h->Hd / h->scal / h->stat on the device: no host round trip.  t_host: nprob times.
+int launch_smallexp_project(b200k_context *h, int nprob, int m, int lanczos, const double *t_host, const double *V,
+                            long long ldv, long long vstride, long long n, double *W, long long ldw,
+                            long long wstride) {
+    CK(h, h->Y.ensure((size_t)nprob * m * 8));
+    CK(h, h->betavec.ensure((size_t)nprob * 8));
+    CK(h, h->mvec.ensure((size_t)nprob * 4));
+    CK(h, h->tdev.ensure((size_t)nprob * 8));
+    CK(h, h->errdev.ensure(64));
+    CK(h, h->errh.ensure(64));
+    // a single time goes by value; a batch of times is copied from the caller's (pageable) array, which the
+    // runtime stages before returning -- no pinned buffer of ours may be rewritten while a copy is still queued
+    if (nprob > 1)
+        CK(h, cudaMemcpyAsync(h->tdev.p, t_host, (size_t)nprob * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemsetAsync(h->errdev.p, 0, 4, h->stream));
+    SmallExpParams S;
+    std::memset(&S, 0, sizeof(S));
+    S.Hd = h->Hd.as<double>();
+    S.ldh = m + 1;
+    S.H_stride = (long long)(m + 1) * (m + 1);
+    S.scal = h->scal.as<double>();
+    S.stat = h->stat.as<int>();
+    S.tvec = nprob > 1 ? h->tdev.as<double>() : nullptr;
+    S.t = t_host[0];
+    S.m = m;
+    S.lanczos = lanczos;
+    S.Y = h->Y.as<double>();
+    S.ldy = m;
+    S.betavec = h->betavec.as<double>();
+    S.mvec = h->mvec.as<int>();
+    S.err = h->errdev.as<int>();
+    if (h->timing) CK(h, cudaEventRecord(h->ev[2], h->stream));
+    small_exp_kernel<<<nprob, SE_NT, (size_t)6 * m * m * 8, h->stream>>>(S);
+    CK(h, cudaGetLastError());
+    h->launches += 1;
+    ProjectParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.V = V;
+    P.ldv = ldv;
+    P.V_stride = vstride;
+    P.nrows = n;
+    P.Y = h->Y.as<double>();
+    P.ldy = m;
+    P.Y_stride = m;
+    P.mvec = h->mvec.as<int>();
+    P.betavec = h->betavec.as<double>();
+    P.m = m;
+    P.nc = 1;
+    P.W = W;
+    P.ldw = ldw;
+    P.W_stride = wstride;
+    P.vec2 = (n % 2 == 0) && (ldv % 2 == 0) && (vstride % 2 == 0) && (ldw % 2 == 0) && (wstride % 2 == 0) &&
+             aligned16(V) && aligned16(W);
+    const long long units = P.vec2 ? n / 2 : n;
+    const long long want = (units + PROJ_NT - 1) / PROJ_NT;
+    int gx = (int)std::min<long long>(want, nprob > 1 ? 64 : (long long)h->sm_count * 8);
+    if (gx < 1) gx = 1;
+    for (int base = 0; base < nprob; base += 32768) {  // gridDim.z limit
+        const int cnt = std::min(nprob - base, 32768);
+        ProjectParams Q = P;
+        Q.V += (long long)base * vstride;
+        Q.Y += (long long)base * m;
+        Q.mvec += base;
+        Q.betavec += base;
+        Q.W += (long long)base * wstride;
+        project_kernel<<<dim3(gx, 1, cnt), PROJ_NT, 0, h->stream>>>(Q);
+        h->launches += 1;
+    }
+    CK(h, cudaGetLastError());
+    if (h->timing) CK(h, cudaEventRecord(h->ev[3], h->stream));
+    // the (practically impossible) singular Pade denominator is reported by the next synchronising call
+    CK(h, cudaMemcpyAsync(h->errh.p, h->errdev.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    return B200K_OK;
+}
+
 int ensure_internal_ks(b200k_context *h, long long nrows, int m, long long *ldv) {
     *ldv = round_up(nrows, 16);
     CK(h, h->V.ensure((size_t)(*ldv) * (m + 1) * 8));
@@ -716,6 +804,9 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
             qres == cudaDriverEntryPointSuccess)
             h->encode_tiled = fn;
     }
+    if (const char *env = std::getenv("B200K_SMALLEXP")) h->host_smallexp = std::strcmp(env, "host") == 0 ? 1 : 0;
+    cudaFuncSetAttribute((const void *)small_exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         6 * SE_MAXM * SE_MAXM * 8);
     if (const char *env = std::getenv("B200K_KERNEL")) h->force_ldg = std::strcmp(env, "ldg") == 0 ? 1 : 0;
     h->max_ctas = std::min(h->sm_count, CPAD);  // one CTA per SM
     for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
@@ -727,10 +818,10 @@ int b200k_destroy(b200k_handle_t h) {
     if (!h) return B200K_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->kV, &h->kB, &h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
+    DevBuf *bufs[] = {&h->tdev, &h->errdev, &h->kV, &h->kB, &h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
                       &h->Y, &h->corr, &h->mvec, &h->betavec, &h->tmp, &h->V, &h->bdev, &h->wdev};
     for (DevBuf *b : bufs) b->release();
-    HostBuf *hb[] = {&h->Hh, &h->scalh, &h->stath, &h->Yh};
+    HostBuf *hb[] = {&h->errh, &h->Hh, &h->scalh, &h->stath, &h->Yh};
     for (HostBuf *b : hb) b->release();
     for (int i = 0; i < 4; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -747,6 +838,10 @@ int b200k_set_stream(b200k_handle_t h, void *stream) {
 int b200k_synchronize(b200k_handle_t h) {
     if (!h) return B200K_EARG;
     CK(h, cudaStreamSynchronize(h->stream));
+    if (h->errh.p && *h->errh.as<int>()) {  // deferred report of the device-side small exponential
+        *h->errh.as<int>() = 0;
+        return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
+    }
     return B200K_OK;
 }
 
@@ -990,6 +1085,54 @@ int b200k_expv(b200k_handle_t h, b200k_op_t op, double t, const double *b, const
     double beta = 0.0;
     int mo = 0, bd = 0;
     const int ldh = o.m + 2;
+    if (!h->host_smallexp && o.m <= SE_MAXM && o.m >= 1 && o.m < MAXCOL) {
+        // fully device-side: Krylov kernel -> small_exp_kernel -> project_kernel, no host round trip unless the
+        // caller asks for m / breakdown / beta
+        int herm = o.hermitian;
+        if (herm < 0) herm = op->is_herm;
+        KrylovCall c;
+        c.op = op;
+        c.b = b;
+        c.b_stride = 0;
+        c.nprob = 1;
+        c.V = h->V.as<double>();
+        c.ldv = ldv;
+        c.V_stride = 0;
+        c.m = o.m;
+        c.j0 = 0;
+        c.iop = o.iop;
+        c.lanczos = herm ? 1 : 0;
+        c.tol = o.tol;
+        c.p = 0;
+        c.B = nullptr;
+        c.ldb = 0;
+        c.btail_host = nullptr;
+        c.g = single_geom(h, op->n);
+        if (op->comm && c.g.C != h->max_ctas)
+            return fail(h, B200K_EUNSUPPORTED, "row-sharded operators need at least 16 rows per CTA on every rank");
+        st = launch_krylov(h, c);
+        if (st) return st;
+        st = launch_smallexp_project(h, 1, o.m, c.lanczos, &t, h->V.as<double>(), ldv, 0, op->n, w, op->n, 0);
+        if (st) return st;
+        if (op->comm || m_out || breakdown || beta_out) {
+            st = fetch_krylov(h, 1, o.m);
+            if (st) return st;
+            beta = h->scalh.as<double>()[0];
+            mo = beta == 0.0 ? o.m : h->stath.as<int>()[0];
+            bd = beta == 0.0 ? 0 : h->stath.as<int>()[1];
+            if (op->comm) {
+                unsigned nbar = 1;
+                if (beta != 0.0) nbar += 2u * (unsigned)mo;
+                op->comm->bar_base += nbar * (unsigned)c.g.C;
+                op->comm->seq_base += nbar;
+            }
+            if (*h->errh.as<int>()) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
+            if (m_out) *m_out = mo;
+            if (breakdown) *breakdown = bd;
+            if (beta_out) *beta_out = beta;
+        }
+        return B200K_OK;
+    }
     st = arnoldi_core(h, op, b, &o, h->V.as<double>(), ldv, o.m, h->H.data(), ldh, &beta, &mo, &bd);
     if (st) return st;
     if (m_out) *m_out = mo;
@@ -1010,6 +1153,7 @@ int b200k_expv_host(b200k_handle_t h, b200k_op_t op, double t, const double *b_h
     if (st) return st;
     CK(h, cudaMemcpyAsync(w_host, h->wdev.p, bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    if (h->errh.p && *h->errh.as<int>()) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
     return B200K_OK;
 }
 
@@ -1068,6 +1212,22 @@ int b200k_expv_batched(b200k_handle_t h, b200k_op_t op, int nb, const double *t,
     c.g = batch_geom(h, n, nb);
     int st = launch_krylov(h, c);
     if (st) return st;
+    if (!h->host_smallexp && m <= SE_MAXM) {
+        // nb exponentials on nb SMs + one batched projection, all on the device
+        st = launch_smallexp_project(h, nb, m, c.lanczos, t, h->V.as<double>(), ldv, vstride, n, W, ldw, ldw);
+        if (st) return st;
+        if (m_out || breakdown) {
+            st = fetch_krylov(h, nb, m);
+            if (st) return st;
+            for (int i = 0; i < nb; ++i) {
+                const double beta = h->scalh.as<double>()[i * 4];
+                if (m_out) m_out[i] = beta == 0.0 ? m : h->stath.as<int>()[i * 4];
+                if (breakdown) breakdown[i] = beta == 0.0 ? 0 : h->stath.as<int>()[i * 4 + 1];
+            }
+            if (*h->errh.as<int>()) return fail(h, B200K_ESINGULAR, "SingularException(0) in the batch");
+        }
+        return B200K_OK;
+    }
     st = fetch_krylov(h, nb, m);
     if (st) return st;
     // small dense phase per problem on the host, then one batched projection launch
@@ -1077,27 +1237,40 @@ int b200k_expv_batched(b200k_handle_t h, b200k_op_t op, int nb, const double *t,
     double *Yh = h->Yh.as<double>();
     double *betah = Yh + (size_t)nb * m;
     int *mh = reinterpret_cast<int *>(betah + nb);
-    std::vector<double> Hm((size_t)ldhd * (m + 1));
-    for (int i = 0; i < nb; ++i) {
-        const double beta = h->scalh.as<double>()[i * 4];
-        int mo = h->stath.as<int>()[i * 4 + 0];
-        const int bd = h->stath.as<int>()[i * 4 + 1];
-        if (beta == 0.0) {
-            mo = m;
+    // the nb independent m x m exponentials are spread over host threads (they are ~50 us each)
+    std::atomic<int> next(0), bad(0);
+    auto worker = [&]() {
+        smallmat::ExpWork work;
+        std::vector<double> Hm((size_t)ldhd * (m + 1));
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= nb) break;
+            const double beta = h->scalh.as<double>()[i * 4];
+            int mo = h->stath.as<int>()[i * 4 + 0];
+            const int bd = h->stath.as<int>()[i * 4 + 1];
+            if (beta == 0.0) mo = m;
+            if (m_out) m_out[i] = mo;
+            if (breakdown) breakdown[i] = beta == 0.0 ? 0 : bd;
+            betah[i] = beta;
+            mh[i] = mo;
+            double *y = Yh + (size_t)i * m;
+            std::fill(y, y + m, 0.0);
+            if (beta == 0.0) continue;
+            std::memcpy(Hm.data(), h->Hh.as<double>() + i * hstride, hstride * 8);
+            if (herm)
+                for (int q = 0; q + 1 < m; ++q) Hm[(size_t)(q + 1) * ldhd + q] = Hm[(size_t)q * ldhd + q + 1];
+            if (expv_small_ws(t[i], Hm.data(), ldhd, mo, y, work)) bad.store(1);
         }
-        if (m_out) m_out[i] = mo;
-        if (breakdown) breakdown[i] = beta == 0.0 ? 0 : bd;
-        betah[i] = beta;
-        mh[i] = mo;
-        double *y = Yh + (size_t)i * m;
-        std::fill(y, y + m, 0.0);
-        if (beta == 0.0) continue;
-        std::memcpy(Hm.data(), h->Hh.as<double>() + i * hstride, hstride * 8);
-        if (herm)
-            for (int q = 0; q + 1 < m; ++q) Hm[(size_t)(q + 1) * ldhd + q] = Hm[(size_t)q * ldhd + q + 1];
-        st = expv_small(h, t[i], Hm.data(), ldhd, mo, y);
-        if (st) return st;
+    };
+    {
+        int nthr = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        nthr = std::max(1, std::min(nthr, nb / 4));
+        std::vector<std::thread> pool;
+        for (int q = 1; q < nthr; ++q) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
     }
+    if (bad.load()) return fail(h, B200K_ESINGULAR, "small dense exponential failed for a problem of the batch");
     CK(h, h->Y.ensure((size_t)nb * m * 8));
     CK(h, h->betavec.ensure((size_t)nb * 8));
     CK(h, h->mvec.ensure((size_t)nb * 4));
