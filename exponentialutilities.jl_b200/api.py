@@ -468,7 +468,7 @@ def expv_batched(ts, A, B, *, m=30, tol=1.0e-7, ishermitian=None, iop=0):
 # kiops (src/kiops.jl:57-281)
 # ------------------------------------------------------------------------------------------
 def kiops(tau_out, A, u, *, mmin=10, mmax=128, m=None, tol=1.0e-7, opnorm=None, iop=2, ishermitian=None,
-          task1=False, _normU=None):
+          task1=False, _normU=None, return_device=False):
     """kiops(tau_out, A, u; mmin, mmax, m, tol, opnorm, iop, ishermitian, task1) -> (w, stats).
 
     ``w`` is n x numSteps (host NumPy array, as the reference returns a host ``zeros(n, numSteps)``,
@@ -503,7 +503,9 @@ def kiops(tau_out, A, u, *, mmin=10, mmax=128, m=None, tol=1.0e-7, opnorm=None, 
                              tau_is_row, C.c_void_p(Ut.data_ptr()), ld, ppo, C.byref(ko),
                              C.c_void_p(Wt.data_ptr()), ld, stats)
     eng.check(st)
-    w = Wt[:, :n].t().cpu().numpy()
+    w = Wt[:, :n].t()
+    if not return_device:  # the reference returns a host matrix (src/kiops.jl:89)
+        w = w.cpu().numpy()
     return w, tuple(int(s) for s in stats)
 
 

@@ -142,4 +142,4 @@ def kiops_sharded(tau_out, sop: ShardedOperator, u_local, **kw):
         t = ul[:, 1:].abs().sum().to(dtype=torch.float64, device=sop.engine.device).reshape(1)
         dist.all_reduce(t, group=sop.group)
         normU = float(t.item())
-    return kiops(tau_out, sop.op, u_local, _normU=normU, **kw)
+    return kiops(tau_out, sop.op, u_local, _normU=normU, **kw)  # pass return_device=True to keep w on the GPU

@@ -70,7 +70,7 @@ if "c4" in which:
     op = eu.operator(A)
     u = torch.stack([torch.randn(n, dtype=torch.float64, device="cuda"), torch.randn(n, dtype=torch.float64, device="cuda")], 1)
     for herm in (True, False):
-        t0 = time.time(); w, st = eu.kiops(1.0, op, u, ishermitian=herm); torch.cuda.synchronize(); dt = time.time() - t0
-        t0 = time.time(); w, st = eu.kiops(1.0, op, u, ishermitian=herm); torch.cuda.synchronize(); dt = time.time() - t0
+        t0 = time.time(); w, st = eu.kiops(1.0, op, u, ishermitian=herm, return_device=True); torch.cuda.synchronize(); dt = time.time() - t0
+        t0 = time.time(); w, st = eu.kiops(1.0, op, u, ishermitian=herm, return_device=True); torch.cuda.synchronize(); dt = time.time() - t0
         out[f"c4_kiops_1gpu_herm{int(herm)}"] = {"s": dt, "stats": st}
 print(json.dumps(out, indent=1))
