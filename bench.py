@@ -298,6 +298,24 @@ def main():
         "hbm_gbs_whole_expv": (fact_bytes + proj_bytes) / (ms_per_step * 1e-3) / 1e9,
         "clocks": clocks,
     }
+    # secondary figure: the other Krylov path on the same operator (a few steps, same timing protocol)
+    other = "lanczos" if args.path == "arnoldi" else "arnoldi"
+
+    def step_other():
+        return eu.expv(t_rank, op, b_dev, m=M, ishermitian=(other == "lanczos"))
+
+    for _ in range(3):
+        step_other()
+    torch.cuda.synchronize()
+    eo0, eo1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eo0.record()
+    for _ in range(10):
+        step_other()
+    eo1.record()
+    torch.cuda.synchronize()
+    line["also"] = {f"{other}_expv_per_s_one_gpu": 10.0 / (eo0.elapsed_time(eo1) * 1e-3),
+                    "note": "same operator through the other path; "
+                            "Lanczos is what the reference dispatches to by default for this symmetric operator"}
     if not args.no_cpu_baseline:
         reps = args.cpu_reps
         sec = cpu_oracle_run(A, b_host_np, args.path, reps)

@@ -32,6 +32,14 @@ class KiopsOpts(C.Structure):
     ]
 
 
+class TimestepOpts(C.Structure):
+    _fields_ = [
+        ("tau", C.c_double), ("m", C.c_int), ("tol", C.c_double), ("opnorm", C.c_double), ("iop", C.c_int),
+        ("correct", C.c_int), ("adaptive", C.c_int), ("delta", C.c_double), ("hermitian", C.c_int),
+        ("gamma", C.c_double), ("NA", C.c_int64),
+    ]
+
+
 # Every symbol include/b200krylov.h declares: (restype, argtypes)
 PROTOTYPES = {
     "b200k_version": (C.c_int, []),
@@ -69,6 +77,9 @@ PROTOTYPES = {
                                      C.POINTER(KrylovOpts), C.c_void_p, C.c_int64, c_int_p, c_int_p]),
     "b200k_kiops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_double_p, C.c_int, C.c_void_p, C.c_int64,
                               C.c_int, C.POINTER(KiopsOpts), C.c_void_p, C.c_int64, c_int64_p]),
+    "b200k_timestep_opts_default": (None, [C.POINTER(TimestepOpts)]),
+    "b200k_phiv_timestep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_double_p, C.c_void_p, C.c_int64, C.c_int,
+                                      C.POINTER(TimestepOpts), C.c_void_p, C.c_int64, c_int_p]),
     "b200k_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
     "b200k_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200k_comm_destroy": (C.c_int, [C.c_void_p]),
@@ -81,6 +92,7 @@ PROTOTYPES = {
     "b200k_last_timing": (C.c_int, [C.c_void_p, c_float_p, c_float_p]),
     "b200k_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "b200k_last_kernel": (C.c_int, [C.c_void_p, c_int_p]),
+    "b200k_set_flag": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
 }
 
 _lib = None

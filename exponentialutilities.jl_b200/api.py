@@ -22,7 +22,7 @@ import weakref
 import numpy as np
 
 from . import _lib
-from ._lib import ArgumentError, DimensionMismatch, KiopsOpts, KrylovOpts
+from ._lib import ArgumentError, DimensionMismatch, KiopsOpts, KrylovOpts, TimestepOpts
 
 try:  # torch is the device-memory / stream plumbing
     import torch
@@ -80,6 +80,11 @@ class Engine:
 
     def set_timing(self, enabled: bool):
         self.check(self.lib.b200k_set_timing(self.handle, 1 if enabled else 0))
+
+    def set_flag(self, name: str, value: bool):
+        """'force_ldg' or 'host_smallexp' (include/b200krylov.h: B200K_FLAG_*)."""
+        flag = {"force_ldg": 1, "host_smallexp": 2}[name]
+        self.check(self.lib.b200k_set_flag(self.handle, flag, 1 if value else 0))
 
     def last_kernel(self):
         """'ldg' (krylov_persistent_kernel) or 'tma' (krylov_tma_kernel) for the last factorisation."""
@@ -507,6 +512,55 @@ def kiops(tau_out, A, u, *, mmin=10, mmax=128, m=None, tol=1.0e-7, opnorm=None, 
     if not return_device:  # the reference returns a host matrix (src/kiops.jl:89)
         w = w.cpu().numpy()
     return w, tuple(int(s) for s in stats)
+
+
+# ------------------------------------------------------------------------------------------
+# phiv_timestep / expv_timestep (src/krylov_phiv_adaptive.jl)
+# ------------------------------------------------------------------------------------------
+def phiv_timestep(ts, A, B, *, tau=0.0, m=None, tol=1.0e-7, opnorm=None, iop=0, correct=False, adaptive=False,
+                  delta=1.2, ishermitian=None, gamma=0.8, NA=0, return_steps=False):
+    """phiv_timestep(ts, A, B; tau, m, tol, opnorm, iop, correct, adaptive, delta, ishermitian, gamma, NA)
+    -- src/krylov_phiv_adaptive.jl:116-453.  B is n x (p+1) (a vector gives expv_timestep); ``ts`` a scalar or a
+    list of output times; ``opnorm`` None (Arnoldi estimate), a scalar, or a callable (A, inf) -> bound."""
+    op = operator(A)
+    eng = op.engine
+    scalar_t = np.isscalar(ts)
+    tsa = np.ascontiguousarray(np.atleast_1d(np.asarray(ts, dtype=np.float64)))
+    Bd, was_np = _to_device(B, eng)
+    if Bd.dim() == 1:
+        Bd = Bd.reshape(-1, 1)
+    n, ncoef = Bd.shape
+    if n != op.n:
+        raise DimensionMismatch("Dimension mismatch")
+    ld = _round_up(n, 2)
+    Bt = torch.zeros((ncoef, ld), dtype=torch.float64, device=eng.device)
+    Bt[:, :n] = Bd.t()
+    Ut = torch.zeros((tsa.size, ld), dtype=torch.float64, device=eng.device)
+    to = TimestepOpts()
+    eng.lib.b200k_timestep_opts_default(C.byref(to))
+    to.tau, to.tol, to.iop = float(tau), float(tol), int(iop)
+    to.m = int(min(10, op.n) if m is None else m)
+    if opnorm is not None:
+        to.opnorm = float(opnorm(A, np.inf)) if callable(opnorm) else float(opnorm)
+    to.correct, to.adaptive = int(bool(correct)), int(bool(adaptive))
+    to.delta, to.gamma, to.NA = float(delta), float(gamma), int(NA)
+    to.hermitian = -1 if ishermitian is None else int(bool(ishermitian))
+    nsteps = C.c_int()
+    eng.bind_stream()
+    st = eng.lib.b200k_phiv_timestep(eng.handle, op.ptr, tsa.size, tsa.ctypes.data_as(_lib.c_double_p),
+                                     C.c_void_p(Bt.data_ptr()), ld, ncoef, C.byref(to), C.c_void_p(Ut.data_ptr()), ld,
+                                     C.byref(nsteps))
+    eng.check(st)
+    eng.synchronize()
+    Uo = Ut[:, :n].t()
+    out = Uo[:, 0] if scalar_t else Uo
+    out = out.cpu().numpy() if was_np else out
+    return (out, nsteps.value) if return_steps else out
+
+
+def expv_timestep(ts, A, b, **kw):
+    """expv_timestep(ts, A, b; ...) -- src/krylov_phiv_adaptive.jl:57-114 (phiv_timestep with p = 0)."""
+    return phiv_timestep(ts, A, b, **kw)
 
 
 # ------------------------------------------------------------------------------------------

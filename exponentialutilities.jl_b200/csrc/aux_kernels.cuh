@@ -230,6 +230,34 @@ __global__ void abs_sum_kernel(long long n, int ncol, const double *X, long long
     }
 }
 
+// y += a * x  (axpy!), y = a * x (lmul!(a, copyto!(y, x))), per-block max |x| (norm(x, Inf))
+__global__ void axpy_kernel(long long n, double a, const double *x, double *y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        y[i] = fma(a, x[i], y[i]);
+}
+__global__ void scalecopy_kernel(long long n, double a, const double *x, double *y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        y[i] = a * x[i];
+}
+__global__ void abs_max_kernel(long long n, const double *x, double *partial) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        s = fmax(s, fabs(x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = fmax(t, red[w]);
+        partial[blockIdx.x] = t;
+    }
+}
+
 __global__ void scale_kernel(long long n, double *x, double a) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x)

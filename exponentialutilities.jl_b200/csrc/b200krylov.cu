@@ -97,6 +97,7 @@ struct b200k_context {
     HostBuf Hh, scalh, stath, Yh;
     // internal Krylov storage for the one-shot calls
     DevBuf V, bdev, wdev;
+    DevBuf tsV, tsW, tsP, tsu;  // phiv_timestep workspace (basis, W, P, u)
     DevBuf kV, kB;  // kiops basis / flipped-u storage, kept across calls (cudaMalloc/cudaFree cost milliseconds)
     std::vector<double> H;
     smallmat::ExpWork expwork;
@@ -818,7 +819,7 @@ int b200k_destroy(b200k_handle_t h) {
     if (!h) return B200K_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->tdev, &h->errdev, &h->kV, &h->kB, &h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
+    DevBuf *bufs[] = {&h->tsV, &h->tsW, &h->tsP, &h->tsu, &h->tdev, &h->errdev, &h->kV, &h->kB, &h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
                       &h->Y, &h->corr, &h->mvec, &h->betavec, &h->tmp, &h->V, &h->bdev, &h->wdev};
     for (DevBuf *b : bufs) b->release();
     HostBuf *hb[] = {&h->errh, &h->Hh, &h->scalh, &h->stath, &h->Yh};
@@ -858,6 +859,14 @@ int b200k_device_info(b200k_handle_t h, int *sm_count, int *max_team, int64_t *l
 int b200k_set_timing(b200k_handle_t h, int enabled) {
     if (!h) return B200K_EARG;
     h->timing = enabled ? 1 : 0;
+    return B200K_OK;
+}
+
+int b200k_set_flag(b200k_handle_t h, int flag, int value) {
+    if (!h) return B200K_EARG;
+    if (flag == B200K_FLAG_FORCE_LDG) h->force_ldg = value ? 1 : 0;
+    else if (flag == B200K_FLAG_HOST_SMALLEXP) h->host_smallexp = value ? 1 : 0;
+    else return fail(h, B200K_EARG, "unknown flag");
     return B200K_OK;
 }
 
@@ -1580,6 +1589,230 @@ int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out
         stats[3] = exps;
         stats[4] = m;
     }
+    return B200K_OK;
+}
+
+// ---- phiv_timestep! (src/krylov_phiv_adaptive.jl:260-501) --------------------------------------------------
+namespace {
+long long ts_flops(int m, double tau, long long n, int p, long long NA, int iop, double Hnorm, double maxtau) {
+    const long long flops_W = 2LL * (p - 1) * (NA + n);
+    const long long flops_u = (2LL * p + 1) * n;
+    if (iop == 0) iop = m;
+    const long long flops_matvec = 2LL * m * NA;
+    long long flops_vecvec = 0;
+    for (int i = 1; i <= m; ++i) flops_vecvec += 3 * std::min(i, iop);
+    const double MH = 44.0 / 3.0 + 2.0 * std::ceil(std::max(0.0, std::log2(Hnorm / 5.37)));
+    const long long flops_phiv = (long long)std::llround(MH * std::pow((double)(m + p), 3));
+    return (flops_W + flops_u + flops_matvec + flops_vecvec + flops_phiv) * (long long)std::ceil(maxtau / tau);
+}
+double hnorm1(const double *H, int ldh, int rows, int cols) {
+    double best = 0.0;
+    for (int j = 0; j < cols; ++j) {
+        double s = 0.0;
+        for (int i = 0; i < rows; ++i) s += std::fabs(H[(size_t)j * ldh + i]);
+        best = std::max(best, s);
+    }
+    return best;
+}
+}  // namespace
+
+void b200k_timestep_opts_default(b200k_timestep_opts *o) {
+    o->tau = 0.0;
+    o->m = 10;
+    o->tol = 1.0e-7;
+    o->opnorm = NAN;
+    o->iop = 0;
+    o->correct = 0;
+    o->adaptive = 0;
+    o->delta = 1.2;
+    o->hermitian = -1;
+    o->gamma = 0.8;
+    o->NA = 0;
+}
+
+int b200k_phiv_timestep(b200k_handle_t h, b200k_op_t op, int nts, double *ts, const double *B, int64_t ldb,
+                        int ncoef, const b200k_timestep_opts *to, double *U, int64_t ldu, int *num_timesteps) {
+    if (!h || !op || !ts || !B || !to || !U || nts < 1 || ncoef < 1) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    const long long n = op->n;
+    if (ldb < n || ldu < n) return fail(h, B200K_EDIM, "Dimension mismatch");
+    if (op->comm) return fail(h, B200K_EUNSUPPORTED, "phiv_timestep on a row-sharded operator is not implemented");
+    const int p = ncoef - 1;
+    int m = (int)std::min<long long>(to->m, n);
+    if (m < 1) return fail(h, B200K_EARG, "m must be >= 1");
+    const double tol = to->tol, gamma = to->gamma, delta = to->delta;
+    int iop = to->iop;
+    double tau = to->tau;
+    const bool arnoldi_scale = !(to->opnorm == to->opnorm);
+    bool have_abstol = false;
+    double abstol = 0.0, opn = 0.0;
+    auto launch1d = [&](long long len) { return (int)std::min<long long>((len + 255) / 256, (long long)h->sm_count * 8); };
+    auto absmax = [&](const double *x, double *out) -> int {
+        const int nblk = 256;
+        CK(h, h->tmp.ensure((size_t)nblk * 8));
+        abs_max_kernel<<<nblk, 256, 0, h->stream>>>(n, x, h->tmp.as<double>());
+        std::vector<double> part(nblk);
+        CK(h, cudaMemcpyAsync(part.data(), h->tmp.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        h->launches += 1;
+        *out = *std::max_element(part.begin(), part.end());
+        return B200K_OK;
+    };
+    auto tau_formula = [&](double opn_, double abstol_, double b0norm) {
+        return 10.0 / opn_ * std::pow(abstol_ * std::pow((m + 1) / M_E, m + 1) * std::sqrt(2 * M_PI * (m + 1)) /
+                                          (4 * opn_ * b0norm),
+                                      1.0 / m);
+    };
+    double b0norm = -1.0;
+    if (!arnoldi_scale) {
+        opn = to->opnorm;
+        abstol = tol * opn;
+        have_abstol = true;
+        if (tau == 0.0) {
+            int st = absmax(B, &b0norm);
+            if (st) return st;
+            tau = tau_formula(opn, abstol, b0norm);
+        }
+    }
+    std::sort(ts, ts + nts);
+    const double tend = ts[nts - 1];
+    const bool seed_arnoldi_tau = arnoldi_scale && tau == 0.0;
+    if (seed_arnoldi_tau) tau = tend;
+    int herm = to->hermitian;
+    if (herm < 0) herm = op->is_herm;
+    long long NA = to->NA;
+    if (to->adaptive) {
+        if (herm) iop = 2;  // "does not have an effect on arnoldi!, just for flops estimation" (:332-334)
+        if (NA == 0) NA = op->nnz;
+    }
+    // workspace: u, W (n x (p+1)), P (n x (p+2)), V (n x (cap+1))
+    const long long ld = round_up(n, 16);
+    int cap = m;
+    CK(h, h->tsu.ensure((size_t)ld * 8));
+    CK(h, h->tsW.ensure((size_t)ld * (p + 1) * 8));
+    CK(h, h->tsP.ensure((size_t)ld * (p + 2) * 8));
+    CK(h, h->tsV.ensure((size_t)ld * (cap + 1) * 8));
+    double *u = h->tsu.as<double>(), *W = h->tsW.as<double>(), *P = h->tsP.as<double>();
+    std::vector<double> H;
+    int ldh = 0;
+    auto ensure_cap = [&](int mm) -> int {
+        if (mm > cap || H.empty()) {
+            cap = std::max(cap, mm);
+            CK(h, h->tsV.ensure((size_t)ld * (cap + 1) * 8));
+            ldh = cap + 2;
+            H.assign((size_t)ldh * (cap + 1), 0.0);
+        }
+        return B200K_OK;
+    };
+    int st = ensure_cap(m);
+    if (st) return st;
+    CK(h, cudaMemcpyAsync(u, B, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));  // u(0) = b0
+    std::vector<double> coeffs(std::max(p, 1), 1.0);
+    double beta = 0.0;
+    int mo = 0, bd = 0;
+    auto do_arnoldi = [&]() -> int {  // arnoldi!(Ks, A, W[:, end]; tol, m, iop): dispatches on ishermitian(A)
+        int s2 = ensure_cap(m);
+        if (s2) return s2;
+        b200k_krylov_opts o;
+        b200k_krylov_opts_default(&o);
+        o.m = m;
+        o.tol = tol;
+        o.iop = iop;  // as the reference: the (possibly overridden) iop; Lanczos ignores it
+        o.hermitian = op->is_herm;
+        beta = 0.0;
+        return arnoldi_core(h, op, W + (size_t)p * ld, &o, h->tsV.as<double>(), ld, cap, H.data(), ldh, &beta, &mo, &bd);
+    };
+    auto do_phiv = [&](double tt, double *eps) -> int {
+        return phiv_ks_core(h, tt, h->tsV.as<double>(), ld, n, H.data(), ldh, mo, beta, p + 1, to->correct, P, ld, eps);
+    };
+    auto combine = [&](double tt, double *dst) -> int {  // dst = tt^p * P[:, end-1] + sum_j coeffs_j(tt) W[:, j]
+        scalecopy_kernel<<<launch1d(n), 256, 0, h->stream>>>(n, std::pow(tt, p), P + (size_t)p * ld, dst);
+        for (int l = 1; l <= p - 1; ++l) coeffs[l] = coeffs[l - 1] * tt / l;
+        for (int j = 0; j <= p - 1; ++j) axpy_kernel<<<launch1d(n), 256, 0, h->stream>>>(n, coeffs[j], W + (size_t)j * ld, dst);
+        CK(h, cudaGetLastError());
+        h->launches += 1 + p;
+        return B200K_OK;
+    };
+    double t = 0.0;
+    int snapshot = 1, nsteps = 0;
+    while (t < tend) {
+        if (t + tau > tend) tau = tend - t;
+        CK(h, cudaMemcpyAsync(W, u, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));  // w0 = u(t)
+        for (int l = 1; l <= p - 1; ++l) coeffs[l] = coeffs[l - 1] * t / l;
+        for (int j = 1; j <= p; ++j) {
+            st = b200k_op_apply(h, op, W + (size_t)(j - 1) * ld, W + (size_t)j * ld);
+            if (st) return st;
+            for (int l = 0; l <= p - j; ++l)
+                axpy_kernel<<<launch1d(n), 256, 0, h->stream>>>(n, coeffs[l], B + (size_t)(j + l) * ldb, W + (size_t)j * ld);
+            h->launches += p - j + 1;
+        }
+        st = do_arnoldi();
+        if (st) return st;
+        if (!have_abstol) {
+            opn = hnorm1(H.data(), ldh, mo + 1, mo);
+            abstol = tol * opn;
+            have_abstol = true;
+            if (seed_arnoldi_tau) {
+                if (b0norm < 0) {
+                    st = absmax(B, &b0norm);
+                    if (st) return st;
+                }
+                tau = std::min(tend - t, gamma * tau_formula(opn, abstol, b0norm));
+            }
+        }
+        if (bd) tau = tend - t;
+        double epsilon = 0.0;
+        st = do_phiv(tau, &epsilon);
+        if (st) return st;
+        if (to->adaptive) {
+            double omega = (tend / tau) * (epsilon / abstol);
+            double epsilon_old = epsilon, tau_old = tau, q = m / 4.0, kappa = 2.0;
+            int m_old = m;
+            const double maxtau = tend - t;
+            int guard = 0;
+            while (omega > delta && guard++ < 200) {  // inner loop of Algorithm 3
+                const double Hn = hnorm1(H.data(), ldh, mo + 1, mo);
+                if (tau_old > tau) q = std::log(tau / tau_old) / std::log(epsilon / epsilon_old) - 1;
+                double tau_new = tau * std::pow(gamma / omega, 1.0 / (q + 1));
+                tau_new = std::min(std::min(std::max(tau_new, tau / 5), 2 * tau), maxtau);
+                if (m_old < m) kappa = std::pow(epsilon / epsilon_old, 1.0 / (m_old - m));
+                double mn = m + std::ceil(std::log(omega / gamma) / std::log(kappa));
+                if (!(mn == mn)) mn = m;
+                mn = std::max(-1.0e9, std::min(1.0e9, mn));
+                int m_new = std::min(std::max(std::max((int)mn, (3 * m) / 4), 1), (int)std::ceil(4.0 * m / 3.0));
+                m_new = (int)std::min<long long>(m_new, std::min<long long>(n, MAXCOL - 1));
+                const long long cost_tau = ts_flops(m, tau_new, n, p, NA, iop, Hn, maxtau);
+                const long long cost_m = ts_flops(m_new, tau, n, p, NA, iop, Hn, maxtau);
+                if (cost_tau < cost_m) m_new = m;
+                else tau_new = tau;
+                m_old = m;
+                m = m_new;
+                tau_old = tau;
+                tau = tau_new;
+                st = do_arnoldi();
+                if (st) return st;
+                double eps_new = 0.0;
+                st = do_phiv(tau, &eps_new);
+                if (st) return st;
+                epsilon_old = epsilon;
+                epsilon = eps_new;
+                omega = (tend / tau) * (epsilon / abstol);
+            }
+        }
+        st = combine(tau, u);
+        if (st) return st;
+        while (snapshot <= nts && t + tau >= ts[snapshot - 1]) {
+            const double tau_s = ts[snapshot - 1] - t;
+            st = do_phiv(tau_s, nullptr);
+            if (st) return st;
+            st = combine(tau_s, U + (size_t)(snapshot - 1) * ldu);
+            if (st) return st;
+            snapshot += 1;
+        }
+        t += tau;
+        nsteps += 1;
+    }
+    if (num_timesteps) *num_timesteps = nsteps;
     return B200K_OK;
 }
 

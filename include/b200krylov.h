@@ -160,6 +160,29 @@ int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out
                 const double *U, int64_t ldu, int ppo, const b200k_kiops_opts *opts, double *W,
                 int64_t ldw, int64_t *stats);
 
+/* ---- phiv_timestep! / expv_timestep! (src/krylov_phiv_adaptive.jl:57-114, 260-501) ------------------------
+ * u(t) = phi_0(tA) b_0 + t phi_1(tA) b_1 + ... + t^p phi_p(tA) b_p at the times ts, by internal time stepping
+ * with the Niesen-Wright adaptation of (tau, m) when `adaptive`.  Keyword arguments of the reference, same
+ * defaults; opnorm = NaN means `nothing` (scale estimated from the Arnoldi Hessenberg, :371-385). */
+typedef struct {
+    double tau;     /* 0.0: estimate */
+    int m;          /* min(10, n) */
+    double tol;     /* 1e-7 */
+    double opnorm;  /* NaN = nothing */
+    int iop;        /* 0 */
+    int correct;    /* false */
+    int adaptive;   /* false */
+    double delta;   /* 1.2 */
+    int hermitian;  /* -1: ishermitian(A); only used for the flops model, as in the reference */
+    double gamma;   /* 0.8 */
+    int64_t NA;     /* 0: nnz(A) */
+} b200k_timestep_opts;
+void b200k_timestep_opts_default(b200k_timestep_opts *o);
+/* ts: HOST, nts times (sorted in place, as the reference does).  B: device n x ncoef (ncoef = p + 1; ncoef = 1 is
+ * expv_timestep).  U: device n x nts.  num_timesteps (may be NULL) receives the number of internal steps. */
+int b200k_phiv_timestep(b200k_handle_t h, b200k_op_t op, int nts, double *ts, const double *B, int64_t ldb,
+                        int ncoef, const b200k_timestep_opts *opts, double *U, int64_t ldu, int *num_timesteps);
+
 /* ---- row sharding of ONE vector across the GPUs of a node (one process per GPU) --------------------------
  * No reference equivalent (the reference has no distributed code); this is how
  * arnoldi!/expv/phiv/kiops scale past one GPU.  Rank r owns a contiguous block of rows of every vector and of
@@ -208,6 +231,12 @@ int b200k_set_timing(b200k_handle_t h, int enabled);
  * 2 = TMA-ring kernel (krylov_tma_kernel; needs even n / ldv and 16-byte aligned bases).  The environment
  * variable B200K_KERNEL=ldg, read at b200k_create, forces 1 (A/B measurements). */
 int b200k_last_kernel(b200k_handle_t h, int *which);
+/* Runtime switches (A/B measurements and tests): B200K_FLAG_FORCE_LDG = 1 uses krylov_persistent_kernel even
+ * where the TMA-ring kernel applies; B200K_FLAG_HOST_SMALLEXP = 1 makes the fused one-shot / batched expv do the
+ * small exponential on the host (both branches of krylov_phiv.jl:225-244) instead of small_exp_kernel. */
+#define B200K_FLAG_FORCE_LDG 1
+#define B200K_FLAG_HOST_SMALLEXP 2
+int b200k_set_flag(b200k_handle_t h, int flag, int value);
 
 #ifdef __cplusplus
 }

@@ -590,3 +590,144 @@ def kiops(tau_out, A, u, *, mmin=10, mmax=128, m=None, tol=1e-7, opnorm=None, io
             w[:, l - 1] = w[:, l - 1] * (1 / tau_flat[l - 1]) ** p
         # the multi-output branch is marked FIXME in the reference (src/kiops.jl:255-274); not restated
     return w, (step, reject, krystep, exps, m)
+
+
+# --------------------------------------------------------------------------------------
+# phiv_timestep / expv_timestep  (src/krylov_phiv_adaptive.jl:260-501)
+# --------------------------------------------------------------------------------------
+def _timestep_flops(m, tau, n, p, NA, iop, Hnorm, maxtau):
+    """_phiv_timestep_estimate_flops -- src/krylov_phiv_adaptive.jl:482-501."""
+    flops_W = 2 * (p - 1) * (NA + n)
+    flops_u = (2 * p + 1) * n
+    if iop == 0:
+        iop = m
+    flops_matvec = 2 * m * NA
+    flops_vecvec = sum(3 * min(i, iop) for i in range(1, m + 1))
+    MH = 44 / 3 + 2 * math.ceil(max(0.0, math.log2(Hnorm / 5.37)))
+    flops_phiv = round(MH * (m + p) ** 3)
+    return (flops_W + flops_u + flops_matvec + flops_vecvec + flops_phiv) * int(math.ceil(maxtau / tau))
+
+
+def _timestep_adapt(m, tau, epsilon, m_old, tau_old, epsilon_old, q, kappa, gamma, omega, maxtau, n, p, NA, iop,
+                    Hnorm):
+    """_phiv_timestep_adapt -- src/krylov_phiv_adaptive.jl:455-481."""
+    if tau_old > tau:
+        q = math.log(tau / tau_old) / math.log(epsilon / epsilon_old) - 1
+    tau_new = tau * (gamma / omega) ** (1 / (q + 1))
+    tau_new = min(max(tau_new, tau / 5), 2 * tau, maxtau)
+    if m_old < m:
+        kappa = (epsilon / epsilon_old) ** (1 / (m_old - m))
+    m_new = m + math.ceil(math.log(omega / gamma) / math.log(kappa))
+    m_new = min(max(m_new, (3 * m) // 4, 1), int(math.ceil(4 * m / 3)))
+    cost_tau = _timestep_flops(m, tau_new, n, p, NA, iop, Hnorm, maxtau)
+    cost_m = _timestep_flops(m_new, tau, n, p, NA, iop, Hnorm, maxtau)
+    if cost_tau < cost_m:
+        m_new = m
+    else:
+        tau_new = tau
+    return m_new, tau_new, q, kappa
+
+
+def phiv_timestep(ts, A, B, *, tau=0.0, m=None, tol=1e-7, opnorm=None, iop=0, correct=False, adaptive=False,
+                  delta=1.2, ishermitian_=None, gamma=0.8, NA=0, return_steps=False):
+    """phiv_timestep!(U, ts, A, B; ...) -- src/krylov_phiv_adaptive.jl:260-453.
+
+    u(t) = phi_0(tA) b_0 + t phi_1(tA) b_1 + ... + t^p phi_p(tA) b_p at the times ``ts``; B is n x (p+1)
+    (or a vector for p = 0, which is expv_timestep).  Returns U (n x len(ts)), or a vector for a scalar ``ts``."""
+    scalar_t = np.isscalar(ts)
+    ts = np.sort(np.atleast_1d(np.asarray(ts, dtype=float)))
+    B = np.asarray(B, dtype=float)
+    Bm = B.reshape(B.shape[0], -1)
+    n = A.shape[0]
+    if m is None:
+        m = min(10, n)
+    if ishermitian_ is None:
+        ishermitian_ = ishermitian(A)
+    arnoldi_scale = opnorm is None
+    abstol = None
+    opn = None
+    if not arnoldi_scale:
+        opn = opnorm if np.isscalar(opnorm) else opnorm(A, np.inf)
+        abstol = tol * opn
+        if tau == 0:
+            b0norm = np.abs(Bm[:, 0]).max()
+            tau = 10 / opn * (abstol * ((m + 1) / math.e) ** (m + 1) * math.sqrt(2 * math.pi * (m + 1)) /
+                              (4 * opn * b0norm)) ** (1 / m)
+    tend = ts[-1]
+    seed_arnoldi_tau = arnoldi_scale and tau == 0
+    if seed_arnoldi_tau:
+        tau = tend
+    p = Bm.shape[1] - 1
+    U = np.zeros((n, ts.size), order="F")
+    u = Bm[:, 0].copy()
+    W = np.zeros((n, p + 1), order="F")
+    Ks = KrylovSubspace(n, m)
+    coeffs = np.ones(max(p, 0))
+    if adaptive:
+        if ishermitian_:
+            iop = 2
+        if NA == 0:
+            NA = A.nnz if sp.issparse(A) else int(np.count_nonzero(A))
+    t = 0.0
+    snapshot = 1
+    nsteps = 0
+    while t < tend:
+        if t + tau > tend:
+            tau = tend - t
+        W[:, 0] = u
+        for l in range(1, p):
+            coeffs[l] = coeffs[l - 1] * t / l
+        for j in range(1, p + 1):
+            W[:, j] = _mul(A, W[:, j - 1])
+            for l in range(0, p - j + 1):
+                W[:, j] += coeffs[l] * Bm[:, j + l]
+        arnoldi_(Ks, A, W[:, p].copy(), tol=tol, m=m, iop=iop)
+        if abstol is None:
+            opn = np.linalg.norm(Ks.getH(), 1)
+            abstol = tol * opn
+            if seed_arnoldi_tau:
+                b0norm = np.abs(Bm[:, 0]).max()
+                tau = min(tend - t, gamma * 10 / opn * (abstol * ((m + 1) / math.e) ** (m + 1) *
+                                                      math.sqrt(2 * math.pi * (m + 1)) / (4 * opn * b0norm)) ** (1 / m))
+        if Ks.wasbreakdown:
+            tau = tend - t
+        P, epsilon = phiv_ks(tau, Ks, p + 1, correct=correct, errest=True)
+        if adaptive:
+            omega = (tend / tau) * (epsilon / abstol)
+            epsilon_old, m_old, tau_old = epsilon, m, tau
+            q, kappa = m / 4, 2.0
+            maxtau = tend - t
+            while omega > delta:
+                m_new, tau_new, q, kappa = _timestep_adapt(m, tau, epsilon, m_old, tau_old, epsilon_old, q, kappa,
+                                                           gamma, omega, maxtau, n, p, NA, iop,
+                                                           np.linalg.norm(Ks.getH(), 1))
+                m, m_old = m_new, m
+                tau, tau_old = tau_new, tau
+                arnoldi_(Ks, A, W[:, p].copy(), tol=tol, m=m, iop=iop)
+                P, epsilon_new = phiv_ks(tau, Ks, p + 1, correct=correct, errest=True)
+                epsilon, epsilon_old = epsilon_new, epsilon
+                omega = (tend / tau) * (epsilon / abstol)
+        u = tau ** p * P[:, -2]
+        for l in range(1, p):
+            coeffs[l] = coeffs[l - 1] * tau / l
+        for j in range(0, p):
+            u = u + coeffs[j] * W[:, j]
+        while snapshot <= ts.size and t + tau >= ts[snapshot - 1]:
+            tau_s = ts[snapshot - 1] - t
+            Ps = phiv_ks(tau_s, Ks, p + 1, correct=correct)
+            us = tau_s ** p * Ps[:, -2]
+            for l in range(1, p):
+                coeffs[l] = coeffs[l - 1] * tau_s / l
+            for j in range(0, p):
+                us = us + coeffs[j] * W[:, j]
+            U[:, snapshot - 1] = us
+            snapshot += 1
+        t += tau
+        nsteps += 1
+    out = U[:, 0] if scalar_t else U
+    return (out, nsteps) if return_steps else out
+
+
+def expv_timestep(ts, A, b, **kw):
+    """expv_timestep(ts, A, b; ...) -- src/krylov_phiv_adaptive.jl:57-114 (phiv_timestep with p = 0)."""
+    return phiv_timestep(ts, A, np.asarray(b, dtype=float).reshape(-1), **kw)

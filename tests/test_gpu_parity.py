@@ -242,3 +242,78 @@ def test_full_size_properties_C2(gpu):
         assert float(torch.linalg.norm(w12 - (2.0 * w1 - 3.0 * w2)) / torch.linalg.norm(w12)) < 1e-9
         ww = gpu.expv(0.25, op, gpu.expv(0.25, op, b1, m=30, ishermitian=herm), m=30, ishermitian=herm)
         assert float(torch.linalg.norm(ww - w1) / torch.linalg.norm(w1)) < 1e-9
+
+
+def test_kernel_variants_agree(gpu, oracle):
+    """LDG kernel vs TMA-ring kernel, and host vs device small exponential, on the same problems."""
+    eng = gpu.get_engine()
+    A = convdiff2d(120, 100)
+    L = laplacian2d(120, 100)
+    b = np.random.default_rng(0).standard_normal(12000)
+    ref_a = oracle.expv(0.8, A, b, m=30)
+    ref_l = oracle.expv(0.8, L, b, m=30)
+    results = {}
+    try:
+        for ldg in (False, True):
+            for hostexp in (False, True):
+                eng.set_flag("force_ldg", ldg)
+                eng.set_flag("host_smallexp", hostexp)
+                wa = gpu.expv(0.8, A, b, m=30)
+                assert eng.last_kernel() == ("ldg" if ldg else "tma")
+                wl = gpu.expv(0.8, L, b, m=30)
+                assert relerr(wa, ref_a) < RTOL and relerr(wl, ref_l) < RTOL
+                results[(ldg, hostexp)] = (wa, wl)
+    finally:
+        eng.set_flag("force_ldg", False)
+        eng.set_flag("host_smallexp", False)
+    base = results[(False, False)]
+    for k, v in results.items():
+        assert relerr(v[0], base[0]) < 1e-12 and relerr(v[1], base[1]) < 1e-12, k
+    # the two Krylov kernels use the same reduction order: identical factorisations
+    eng.set_flag("force_ldg", True)
+    K1 = gpu.arnoldi(A, b, m=20)
+    eng.set_flag("force_ldg", False)
+    K2 = gpu.arnoldi(A, b, m=20)
+    assert np.abs(K1.getH() - K2.getH()).max() < 1e-12
+
+
+def test_device_small_exp_branches(gpu, oracle):
+    """Fused expv (device Pade) across the Pade orders: scale t so that ||tH|| hits C3..C13 and several squarings."""
+    A = convdiff2d(60, 50)
+    b = np.random.default_rng(2).standard_normal(3000)
+    op = gpu.operator(A)
+    for t in (1e-4, 2e-3, 2e-2, 0.1, 0.25, 1.0, 6.0):
+        assert relerr(gpu.expv(t, op, b, m=20), oracle.expv(t, A, b, m=20)) < RTOL, t
+    # m above the device limit (48) takes the host path transparently
+    assert relerr(gpu.expv(0.5, op, b, m=60), oracle.expv(0.5, A, b, m=60)) < RTOL
+    # badly scaled operator: D A D^-1 exercises the balancing sweeps of the device kernel
+    import scipy.sparse as sp
+    d = 2.0 ** np.random.default_rng(3).integers(-6, 7, 3000)
+    As = (sp.diags(d) @ A @ sp.diags(1.0 / d)).tocsr()
+    assert relerr(gpu.expv(0.3, As, b, m=20), oracle.expv(0.3, As, b, m=20)) < 1e-8
+
+
+def test_phiv_timestep_and_expv_timestep(gpu, oracle):
+    """phiv_timestep! / expv_timestep! (src/krylov_phiv_adaptive.jl): the reference's own assertions
+    (test/basictests.jl:666-691) and step-for-step parity with the oracle's controller."""
+    n, K, t, tol = 100, 4, 5.0, 1e-7
+    A = sp.diags([np.ones(n - 1), -2 * np.ones(n), np.ones(n - 1)], [-1, 0, 1]).tocsr()
+    B = np.random.default_rng(14).standard_normal((n, K + 1))
+    U, ns = gpu.phiv_timestep([t / 2, t], A, B, adaptive=True, tol=tol, return_steps=True)
+    Uo, nso = oracle.phiv_timestep([t / 2, t], A, B, adaptive=True, tol=tol, return_steps=True)
+    assert ns == nso and relerr(U, Uo) < 1e-8
+    ue = sla.expm(t * A.toarray()) @ B[:, 0]
+    opn = abs(A).sum(axis=1).max()
+    for on in (None, opn, lambda A_, p_: abs(A_).sum(axis=1).max()):
+        u, ns = gpu.expv_timestep(t, A, B[:, 0], adaptive=True, tol=tol, opnorm=on, return_steps=True)
+        uo, nso = oracle.expv_timestep(t, A, B[:, 0], adaptive=True, tol=tol, opnorm=on, return_steps=True)
+        assert ns == nso and relerr(u, uo) < 1e-8
+        assert relerr(u, ue) < (1e-5 if on is None else tol)
+    # larger non-symmetric operator, non-adaptive and adaptive, several snapshots, correct=True
+    A2 = convdiff2d(60, 50)
+    B2 = np.random.default_rng(15).standard_normal((3000, 3))
+    for kw in ({}, {"adaptive": True}, {"adaptive": True, "correct": True, "m": 15}):
+        U, ns = gpu.phiv_timestep([0.3, 0.7, 1.0], A2, B2, tol=1e-8, return_steps=True, **kw)
+        Uo, nso = oracle.phiv_timestep([0.3, 0.7, 1.0], A2, B2, tol=1e-8, return_steps=True, **kw)
+        assert ns == nso, (kw, ns, nso)
+        assert relerr(U, Uo) < 1e-8, kw

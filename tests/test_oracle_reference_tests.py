@@ -114,3 +114,22 @@ def test_kiops_quirks_and_stats(oracle):
     W = phis_dense(1.0 * A.toarray(), u[:, 0], 1)  # exp(A) u0 + phi_1(A) u1
     M = phis_dense(1.0 * A.toarray(), u[:, 1], 2)
     assert relerr(w2[:, 0], W[:, 0] + M[:, 1]) < 1e-6
+
+
+def test_adaptive_krylov_timestepping(oracle):
+    """test/basictests.jl:666-691 "Adaptive Krylov" and :693-729 (Arnoldi-estimated tolerance scale)."""
+    n, K, t, tol = 100, 4, 5.0, 1e-7
+    A = sp.diags([np.ones(n - 1), -2 * np.ones(n), np.ones(n - 1)], [-1, 0, 1]).tocsr()
+    B = np.random.default_rng(14).standard_normal((n, K + 1))
+    Ad = A.toarray()
+
+    def exact(tt):
+        return sum(tt ** i * phis_dense(tt * Ad, B[:, i], max(i, 1))[:, i] for i in range(K + 1))
+
+    U = oracle.phiv_timestep([t / 2, t], A, B, adaptive=True, tol=tol)
+    assert relerr(U[:, 0], exact(t / 2)) < tol and relerr(U[:, 1], exact(t)) < tol          # :680-682
+    ue = sla.expm(t * Ad) @ B[:, 0]
+    opn = abs(A).sum(axis=1).max()
+    for on in (lambda A_, p_: abs(A_).sum(axis=1).max(), opn):                                # :685-690
+        assert relerr(oracle.expv_timestep(t, A, B[:, 0], adaptive=True, tol=tol, opnorm=on), ue) < tol
+    assert relerr(oracle.expv_timestep(t, A, B[:, 0], adaptive=True, tol=tol), ue) < 1e-5    # :716-717
