@@ -68,6 +68,8 @@ PROTOTYPES = {
                                 c_double_p]),
     "b200k_expv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.POINTER(KrylovOpts),
                              C.c_void_p, c_int_p, c_int_p, c_double_p]),
+    "b200k_expv_ee": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                C.c_void_p, c_int_p]),
     "b200k_expv_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.POINTER(KrylovOpts),
                                   C.c_void_p, c_int_p, c_int_p]),
     "b200k_phiv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,

@@ -363,15 +363,13 @@ def expv_(w, t, Ks: KrylovSubspace, *, cache=None):
 
 
 def expv(t, A, b=None, *, mode="happy_breakdown", m=None, tol=1.0e-7, ishermitian=None, iop=0, opnorm=None,
-         cache=None, expmethod=None):
+         cache=None, expmethod=None, rtol=None, return_m=False):
     """expv(t, A, b; m, tol, ishermitian, iop, ...) or expv(t, Ks) -- src/krylov_phiv.jl:125-168."""
     if isinstance(A, KrylovSubspace):
         Ks = A
         w = torch.empty(Ks.nrows, dtype=torch.float64, device=Ks.engine.device)
         return expv_(w, t, Ks)
-    if mode != "happy_breakdown":
-        if mode == "error_estimate":
-            raise _lib.UnsupportedError("mode=:error_estimate is not implemented by the B200 engine yet")
+    if mode not in ("happy_breakdown", "error_estimate"):
         raise ArgumentError(f"Unknown Krylov iteration termination mode, {mode}")
     op = operator(A)
     eng = op.engine
@@ -381,6 +379,19 @@ def expv(t, A, b=None, *, mode="happy_breakdown", m=None, tol=1.0e-7, ishermitia
         raise DimensionMismatch("length(b) != size(A, 1)")
     if m is None:
         m = min(30, op.n)
+    if mode == "error_estimate":  # _expv_ee (src/krylov_phiv.jl:145-160): atol = tol, rtol = sqrt(tol)
+        herm = op.ishermitian if ishermitian is None else bool(ishermitian)
+        if not herm:
+            raise _lib.UnsupportedError("Error estimation not yet available for non-Hermitian matrices.")
+        w = torch.empty_like(bd)
+        mo = C.c_int()
+        eng.bind_stream()
+        st = eng.lib.b200k_expv_ee(eng.handle, op.ptr, float(t), C.c_void_p(bd.data_ptr()), int(m), float(tol),
+                                   float(math.sqrt(tol) if rtol is None else rtol), C.c_void_p(w.data_ptr()),
+                                   C.byref(mo))
+        eng.check(st)
+        out = _from_device(w, was_np)
+        return (out, mo.value) if return_m else out
     opts = KrylovOpts()
     eng.lib.b200k_krylov_opts_default(C.byref(opts))
     opts.m, opts.tol, opts.iop = int(m), float(tol), int(iop)

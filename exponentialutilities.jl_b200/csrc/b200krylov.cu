@@ -1150,6 +1150,58 @@ int b200k_expv(b200k_handle_t h, b200k_op_t op, double t, const double *b, const
     return expv_ks_core(h, t, h->V.as<double>(), ldv, op->n, h->H.data(), ldh, mo, beta, w);
 }
 
+int b200k_expv_ee(b200k_handle_t h, b200k_op_t op, double t, const double *b, int m, double atol, double rtol,
+                  double *w, int *m_out) {
+    if (!h || !op || !b || !w) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    if (!op->is_herm)
+        return fail(h, B200K_EUNSUPPORTED, "Error estimation not yet available for non-Hermitian matrices.");
+    m = (int)std::min<long long>(m, op->n);
+    if (m < 1) return fail(h, B200K_EARG, "m must be >= 1");
+    long long ldv;
+    int st = ensure_internal_ks(h, op->n, m, &ldv);
+    if (st) return st;
+    b200k_krylov_opts o;
+    b200k_krylov_opts_default(&o);
+    o.m = m;
+    o.tol = 0.0;  // lanczos_step! is called directly: no happy-breakdown test in this mode
+    o.hermitian = 1;
+    double beta = 0.0;
+    int mo = 0, bd = 0;
+    const int ldh = m + 2;
+    st = arnoldi_core(h, op, b, &o, h->V.as<double>(), ldv, m, h->H.data(), ldh, &beta, &mo, &bd);
+    if (st) return st;
+    if (beta == 0.0) {  // Ks.m = 0; w .= 0
+        if (m_out) *m_out = 0;
+        CK(h, cudaMemsetAsync(w, 0, (size_t)op->n * 8, h->stream));
+        return B200K_OK;
+    }
+    const double eps = atol + rtol * beta;
+    const double *H = h->H.data();
+    int jstop = m;
+    std::vector<double> d, e, zf, zl;
+    for (int j = 1; j <= m; ++j) {
+        d.resize(j);
+        e.resize(std::max(j - 1, 0));
+        for (int i = 0; i < j; ++i) d[i] = H[(size_t)i * ldh + i];
+        for (int i = 0; i + 1 < j; ++i) e[i] = H[(size_t)i * ldh + i + 1];
+        if (!smallmat::symtridiag_eig_firstlast(j, d, e, zf, zl))
+            return fail(h, B200K_ESINGULAR, "symmetric tridiagonal eigensolver did not converge");
+        double vj = 0.0;
+        for (int k = 0; k < j; ++k) vj += std::exp(t * d[k]) * zf[k] * zl[k];
+        const double sigma = H[(size_t)(j - 1) * ldh + j] * beta * std::fabs(vj);
+        if (sigma < eps) {
+            jstop = j;
+            break;
+        }
+    }
+    if (m_out) *m_out = jstop;
+    std::vector<double> y(jstop);
+    if (!smallmat::exp_symtridiag_e1(jstop, H, ldh, t, y.data()))
+        return fail(h, B200K_ESINGULAR, "symmetric tridiagonal eigensolver did not converge");
+    return launch_project(h, h->V.as<double>(), ldv, op->n, jstop, beta, y.data(), jstop, 1, w, op->n, nullptr);
+}
+
 int b200k_expv_host(b200k_handle_t h, b200k_op_t op, double t, const double *b_host,
                     const b200k_krylov_opts *opts, double *w_host, int *m_out, int *breakdown) {
     if (!h || !op || !b_host || !opts || !w_host) return B200K_EARG;

@@ -360,6 +360,67 @@ inline bool symtridiag_eig(int n, std::vector<double> &d, std::vector<double> e_
     return true;
 }
 
+// Same QL iteration, but only rows 0 and n-1 of the eigenvector matrix are accumulated (O(n) per rotation):
+// enough for e_n' exp(tT) e_1 = sum_k exp(t lambda_k) Z[0,k] Z[n-1,k], the error estimate of
+// krylov_phiv_error_estimate.jl:189-191.
+inline bool symtridiag_eig_firstlast(int n, std::vector<double> &d, std::vector<double> e_in,
+                                     std::vector<double> &zfirst, std::vector<double> &zlast) {
+    zfirst.assign(n, 0.0);
+    zlast.assign(n, 0.0);
+    if (n == 0) return true;
+    // row 0 of Z starts as e_0', row n-1 as e_{n-1}'
+    zfirst[0] = 1.0;
+    zlast[n - 1] = 1.0;
+    if (n == 1) return true;
+    std::vector<double> e(n, 0.0);
+    for (int i = 0; i + 1 < n; ++i) e[i] = e_in[i];
+    const double eps = std::numeric_limits<double>::epsilon();
+    for (int l = 0; l < n; ++l) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < n - 1; ++m) {
+                const double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+                if (std::fabs(e[m]) <= eps * dd) break;
+            }
+            if (m != l) {
+                if (iter++ == 60) return false;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = std::hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + (g >= 0 ? std::fabs(r) : -std::fabs(r)));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                for (i = m - 1; i >= l; --i) {
+                    double f = s * e[i];
+                    const double b = c * e[i];
+                    e[i + 1] = (r = std::hypot(f, g));
+                    if (r == 0.0) {
+                        d[i + 1] -= p;
+                        e[m] = 0.0;
+                        break;
+                    }
+                    s = f / r;
+                    c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    d[i + 1] = g + (p = s * r);
+                    g = c * r - b;
+                    f = zfirst[i + 1];
+                    zfirst[i + 1] = s * zfirst[i] + c * f;
+                    zfirst[i] = c * zfirst[i] - s * f;
+                    f = zlast[i + 1];
+                    zlast[i + 1] = s * zlast[i] + c * f;
+                    zlast[i] = c * zlast[i] - s * f;
+                }
+                if (r == 0.0 && i >= l) continue;
+                d[l] -= p;
+                e[l] = g;
+                e[m] = 0.0;
+            }
+        } while (m != l);
+    }
+    return true;
+}
+
 // expHe = exp(t T) e1 for the symmetric tridiagonal T = tridiag(e, d, e)  (krylov_phiv.jl:227-229):
 //   expHe = Z * (exp.(t * lambda) .* Z[1, :]).
 inline bool exp_symtridiag_e1(int m, const double *H, int ldh, double t, double *out) {

@@ -124,6 +124,14 @@ int b200k_phiv_ks(b200k_handle_t h, double t, const double *V, int64_t ldv, int6
 int b200k_expv(b200k_handle_t h, b200k_op_t op, double t, const double *b,
                const b200k_krylov_opts *opts, double *w, int *m_out, int *breakdown,
                double *beta_out);
+/* expv(t, A, b; mode = :error_estimate) (src/krylov_phiv.jl:145-160, src/krylov_phiv_error_estimate.jl:149-207):
+ * Lanczos with Saad's a-posteriori estimate sigma_j = beta_j * beta * |e_j' exp(t T_j) e_1| and the stop
+ * sigma_j < atol + rtol * beta.  Hermitian operators only (the reference raises otherwise -> B200K_EUNSUPPORTED).
+ * The m-step Lanczos factorisation runs in one launch (its coefficients do not depend on the stopping index);
+ * the estimates are then evaluated for j = 1, 2, ... on the host and the subspace is truncated at the first hit,
+ * so w and m_out equal the reference's. */
+int b200k_expv_ee(b200k_handle_t h, b200k_op_t op, double t, const double *b, int m, double atol, double rtol,
+                  double *w, int *m_out);
 /* Same call with HOST vectors: copies b in and w out on the handle's stream (end-to-end path). */
 int b200k_expv_host(b200k_handle_t h, b200k_op_t op, double t, const double *b_host,
                     const b200k_krylov_opts *opts, double *w_host, int *m_out, int *breakdown);

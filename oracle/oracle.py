@@ -731,3 +731,38 @@ def phiv_timestep(ts, A, B, *, tau=0.0, m=None, tol=1e-7, opnorm=None, iop=0, co
 def expv_timestep(ts, A, b, **kw):
     """expv_timestep(ts, A, b; ...) -- src/krylov_phiv_adaptive.jl:57-114 (phiv_timestep with p = 0)."""
     return phiv_timestep(ts, A, np.asarray(b, dtype=float).reshape(-1), **kw)
+
+
+# --------------------------------------------------------------------------------------
+# expv(...; mode = :error_estimate)  (src/krylov_phiv_error_estimate.jl:149-207, src/krylov_phiv.jl:145-160)
+# --------------------------------------------------------------------------------------
+def expv_ee(t, A, b, *, m=None, tol=1e-7, rtol=None, return_m=False):
+    """_expv_ee + expv!(w, t, A, b, Ks, cache; atol = tol, rtol = sqrt(tol)): Lanczos stopped by Saad's estimate
+    sigma_j = beta_j * beta * |(exp(t T_j) e_1)_j| < atol + rtol * beta.  Hermitian A only."""
+    if not ishermitian(A):
+        raise ValueError("Error estimation not yet available for non-Hermitian matrices.")
+    n = A.shape[0]
+    if m is None:
+        m = min(30, n)
+    if rtol is None:
+        rtol = math.sqrt(tol)
+    Ks = KrylovSubspace(n, m)
+    V, H = Ks.getV(), Ks.getH()
+    Ks.beta = _nrm2(np.ascontiguousarray(b))
+    if Ks.beta == 0:
+        return (np.zeros(n), 0) if return_m else np.zeros(n)
+    V[:, 0] = b / Ks.beta
+    eps = tol + rtol * Ks.beta
+    v = None
+    for j in range(1, m + 1):
+        _lanczos_step(j, A, V, H, -1, -1)
+        alpha = np.diag(H)[:j].copy()
+        beta = np.diag(H, -1)[:j].copy()
+        lam, Z = sla.eigh_tridiagonal(alpha, beta[: j - 1], lapack_driver="stemr") if j > 1 else (alpha, np.ones((1, 1)))
+        v = Z @ (np.exp(t * lam) * Z[0, :])
+        sigma = beta[j - 1] * Ks.beta * abs(v[j - 1])
+        if sigma < eps:
+            Ks.m = j
+            break
+    w = Ks.beta * (V[:, : Ks.m] @ v[: Ks.m])
+    return (w, Ks.m) if return_m else w

@@ -73,4 +73,22 @@ if "c4" in which:
         t0 = time.time(); w, st = eu.kiops(1.0, op, u, ishermitian=herm, return_device=True); torch.cuda.synchronize(); dt = time.time() - t0
         t0 = time.time(); w, st = eu.kiops(1.0, op, u, ishermitian=herm, return_device=True); torch.cuda.synchronize(); dt = time.time() - t0
         out[f"c4_kiops_1gpu_herm{int(herm)}"] = {"s": dt, "stats": st}
+if "ts" in which:
+    # phiv_timestep on the C2 operator, p = 2, adaptive, next to the CPU oracle on the same input
+    from oracle import oracle as O
+    A = laplacian2d(1000, 1000); n = 10**6
+    op = eu.operator(A)
+    Bh = np.random.default_rng(11).standard_normal((n, 3))
+    Bd = torch.from_numpy(Bh).cuda()
+    f = lambda: eu.phiv_timestep([0.5, 1.0], op, Bd, adaptive=True, tol=1e-7, return_steps=True)
+    U, ns = f(); ms = timeit(lambda: f(), reps=5, warm=1)
+    t0 = time.time(); Uo, nso = O.phiv_timestep([0.5, 1.0], A, Bh, adaptive=True, tol=1e-7, return_steps=True); cpu_s = time.time() - t0
+    out["ts_phiv_timestep_p2_adaptive"] = {"ms": ms, "internal_steps": ns, "cpu_oracle_s": cpu_s, "cpu_steps": nso,
+                                          "relerr_vs_oracle": float(np.linalg.norm(U.cpu().numpy() - Uo) / np.linalg.norm(Uo))}
+    b = torch.from_numpy(Bh[:, 0].copy()).cuda()
+    g = lambda: eu.expv(1.0, op, b, mode="error_estimate", m=30, tol=1e-7, return_m=True)
+    w, mm = g(); ms = timeit(lambda: g(), reps=10)
+    wo, mo = O.expv_ee(1.0, A, Bh[:, 0], m=30, tol=1e-7, return_m=True)
+    out["ee_expv_error_estimate"] = {"ms": ms, "m_stop": mm, "m_stop_oracle": mo,
+                                    "relerr_vs_oracle": float(np.linalg.norm(w.cpu().numpy() - wo) / np.linalg.norm(wo))}
 print(json.dumps(out, indent=1))

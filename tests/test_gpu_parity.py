@@ -317,3 +317,17 @@ def test_phiv_timestep_and_expv_timestep(gpu, oracle):
         Uo, nso = oracle.phiv_timestep([0.3, 0.7, 1.0], A2, B2, tol=1e-8, return_steps=True, **kw)
         assert ns == nso, (kw, ns, nso)
         assert relerr(U, Uo) < 1e-8, kw
+
+
+def test_error_estimate_mode(gpu, oracle):
+    """expv(...; mode = :error_estimate): same stopping index and result as the restated reference."""
+    A = laplacian2d(60, 50)
+    b = np.random.default_rng(9).standard_normal(3000)
+    for t, tol in ((0.05, 1e-7), (0.5, 1e-7), (1.0, 1e-10)):
+        w, mm = gpu.expv(t, A, b, mode="error_estimate", m=30, tol=tol, return_m=True)
+        wo, mo = oracle.expv_ee(t, A, b, m=30, tol=tol, return_m=True)
+        assert mm == mo and relerr(w, wo) < RTOL, (t, tol, mm, mo)
+    assert gpu.expv(0.05, A, b, mode="error_estimate", return_m=True)[1] < 30      # it does stop early
+    assert np.linalg.norm(gpu.expv(0.5, A, np.zeros(3000), mode="error_estimate")) == 0.0
+    with pytest.raises(gpu.UnsupportedError):
+        gpu.expv(0.5, convdiff2d(60, 50), b, mode="error_estimate")

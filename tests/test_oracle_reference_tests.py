@@ -133,3 +133,17 @@ def test_adaptive_krylov_timestepping(oracle):
     for on in (lambda A_, p_: abs(A_).sum(axis=1).max(), opn):                                # :685-690
         assert relerr(oracle.expv_timestep(t, A, B[:, 0], adaptive=True, tol=tol, opnorm=on), ue) < tol
     assert relerr(oracle.expv_timestep(t, A, B[:, 0], adaptive=True, tol=tol), ue) < 1e-5    # :716-717
+
+
+def test_error_estimate_lanczos_mode(oracle):
+    """test/basictests.jl:756-784 "Alternative Lanczos expv Interface": n = 300, m = 30, atol = rtol = 1e-10."""
+    n, m = 300, 30
+    rng = np.random.default_rng(8)
+    d = rng.standard_normal(n)
+    e = rng.standard_normal(n - 1)
+    A = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    b = rng.standard_normal(n)
+    t = 0.1
+    w, mm = oracle.expv_ee(t, A, b, m=m, tol=1e-10, rtol=1e-10, return_m=True)
+    assert relerr(w, sla.expm(t * A) @ b) < 1e-9 and 1 <= mm <= m
+    assert np.linalg.norm(oracle.expv_ee(t, A, np.zeros(n), m=m)) == 0.0          # :783
