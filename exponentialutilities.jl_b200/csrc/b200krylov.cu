@@ -118,11 +118,12 @@ struct b200k_comm {
     bool connected = false;
     unsigned bar_base = 0;  // local arrivals accumulated by all previous launches (identical on every rank)
     unsigned seq_base = 0;  // team barriers passed by all previous launches
-    // layout of each rank's buffer: [1 KB header: counter @0, flags @128 + 64 s][part 2*MAXCOL*cpad][partn 4*cpad]
-    // [xbuf 2*xlen] doubles
-    static constexpr size_t HDR = 1024;
+    // layout of each rank's buffer: [header: barrier counter @0, LL packet inbox @1024: 2 x (MAXCOL+1) x 8 x 16 B]
+    // [part 2*MAXCOL*cpad][partn 4*cpad][xbuf 2*xlen] doubles
+    static constexpr size_t PKT_BYTES = (size_t)2 * (MAXCOL + 1) * 8 * 16;
+    static constexpr size_t HDR = 1024 + PKT_BYTES;
     unsigned *bar_of(int r) const { return reinterpret_cast<unsigned *>(peer[r]); }
-    unsigned *flag_of(int r) const { return reinterpret_cast<unsigned *>(reinterpret_cast<char *>(peer[r]) + 128); }
+    uint4 *pkt_of(int r) const { return reinterpret_cast<uint4 *>(reinterpret_cast<char *>(peer[r]) + 1024); }
     double *part_of(int r) const { return reinterpret_cast<double *>(reinterpret_cast<char *>(peer[r]) + HDR); }
     double *partn_of(int r) const { return part_of(r) + (size_t)2 * MAXCOL * cpad; }
     double *xbuf_of(int r) const { return partn_of(r) + (size_t)4 * cpad; }
@@ -322,7 +323,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
             P.peer_part[r] = cm->part_of(r);
             P.peer_partn[r] = cm->partn_of(r);
             P.peer_bar[r] = cm->bar_of(r);
-            P.peer_flag[r] = cm->flag_of(r);
+            P.peer_pkt[r] = cm->pkt_of(r);
             P.peer_xbuf[r] = cm->xbuf_of(r);
         }
         // halo push ranges per CTA slice

@@ -102,7 +102,7 @@ struct KrylovParams {
     int myrank;
     unsigned bar_base;      // local barrier arrivals accumulated by earlier launches (multi-GPU counters are never reset)
     unsigned seq_base;      // team barriers passed by earlier launches
-    unsigned *peer_flag[8]; // per GPU: 8 flags (64-byte stride), flag[s] = last barrier GPU s has reached
+    uint4 *peer_pkt[8];     // per GPU: LL inbox [2 parities][MAXCOL + 1 quantities][8 source ranks] of {lo, seq, hi, seq}
     int nhalo;              // remote x entries this GPU gathers (appended after the n local entries)
     int cpad;               // row length of the partial-sum tables: round_up(team_size * nranks, 32)
     double *peer_part[8];   // [2][MAXCOL][cpad] on each GPU

@@ -45,6 +45,7 @@ struct __align__(128) SmemTma {
     int chunk_a0[MAXCH2];
     int chunk_cnt[MAXCH2];
     int slot_a0[MAXSLOT];
+    double bc[2];             // reduced scalars (squared norm) broadcast to the CTA
     volatile int cols_ready;  // number of complete basis columns of the current problem
     volatile int stop_seq;    // consumers finished local problem #stop_seq (1-based)
 };
@@ -52,50 +53,42 @@ struct __align__(128) SmemTma {
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// relaxed system-scope accesses; ordering comes from ONE __threadfence_system() before the stores / after the
-// polling loop (a st.release.sys per peer would serialise one NVLink round trip per peer)
-__device__ __forceinline__ void st_relaxed_sys_u32(unsigned *p, unsigned v) {
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// ---- team barrier and team-wide reduction -----------------------------------------------------------------------
+// Single GPU: the cooperative-groups grid-sync protocol on one counter, then every CTA sums the per-CTA partials in
+// a fixed order.  Row-sharded over R GPUs (NVLink peer memory, no NCCL): two levels --
+//   1. the CTAs of a GPU synchronise on their OWN counter (they stored their partials locally; CTAs that pushed
+//      halo values into a peer's gather buffer first make them visible with a system-scope fence);
+//   2. for each reduced quantity one CTA sums the GPU-local partials and stores {value, seq} packets straight into
+//      every GPU's inbox: one self-validating 16-byte store {lo32, seq, hi32, seq} per peer, the NCCL "LL" idea, so
+//      no fence / flag round trip sits between data and notification;
+//   3. every CTA polls the R packets of each quantity and adds them in rank order (bitwise identical everywhere).
+__device__ __forceinline__ void ll_push(uint4 *p, double v, unsigned seq) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(seq),
+                 "r"((unsigned)(b >> 32)), "r"(seq)
+                 : "memory");
 }
-__device__ __forceinline__ unsigned ld_relaxed_sys_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ double ll_poll(const uint4 *p, unsigned seq) {
+    unsigned lo, f1, hi, f2;
+    do {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2)
+                     : "l"(p)
+                     : "memory");
+    } while (f1 != seq || f2 != seq);
+    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
-// Team barrier.  Single GPU: the cooperative-groups grid-sync protocol on one counter.  Row-sharded over
-// several GPUs: a two-level barrier over NVLink peer memory (local counter + one flag per peer GPU); it is
-// also what publishes the partial sums and halo values that the CTAs stored into the peers' buffers before
-// arriving (the fused all-reduce / halo exchange).
-__device__ __forceinline__ void team_barrier_c(Team &tm, const KrylovParams &P) {
+__device__ __forceinline__ void team_barrier_c(Team &tm, const KrylovParams &P, bool pushed_to_peers) {
     consumer_sync();
     if (threadIdx.x == 0) {
         tm.target += (unsigned)tm.C;
-        if (P.nranks == 1) {
-            __threadfence();
-            atomicAdd(tm.bar, 1u);
-            while ((int)(ld_acquire_u32(tm.bar) - tm.target) < 0) {
-            }
-            __threadfence();
-        } else {
-            // hierarchical: CTAs arrive on their own GPU's counter; the last one to arrive tells every peer
-            // "GPU myrank reached barrier #seq" with ONE flag store per peer (instead of one remote atomic per CTA).
-            __threadfence_system();  // this CTA's stores into peer memory are performed before it arrives
-            const unsigned old = atomicAdd(tm.bar, 1u);
-            tm.seq += 1u;
-            if (old + 1u == tm.target) {
-                __threadfence_system();
-                for (int r = 0; r < P.nranks; ++r)
-                    if (r != P.myrank) st_relaxed_sys_u32(P.peer_flag[r] + P.myrank * 16, tm.seq);
-            }
-            while ((int)(ld_acquire_u32(tm.bar) - tm.target) < 0) {
-            }
-            for (int r = 0; r < P.nranks; ++r)
-                if (r != P.myrank)
-                    while ((int)(ld_relaxed_sys_u32(P.peer_flag[P.myrank] + r * 16) - tm.seq) < 0) {
-                    }
-            __threadfence_system();
+        if (pushed_to_peers) __threadfence_system();  // halo stores into peer memory are performed first
+        else __threadfence();
+        atomicAdd(tm.bar, 1u);
+        while ((int)(ld_acquire_u32(tm.bar) - tm.target) < 0) {
         }
+        __threadfence();
     }
     consumer_sync();
 }
@@ -247,6 +240,7 @@ struct Cons {
     SmemTma *S;
     double *ws;
     int tid, lane, warp;
+    unsigned seq;  // team barriers passed so far (the LL packets of barrier #seq carry it)
     Ring rg;
     __device__ __forceinline__ void wait_full() { mbar_wait(&S->full[rg.slot], rg.phase); }
     __device__ __forceinline__ void release() {
@@ -256,7 +250,7 @@ struct Cons {
     }
 };
 
-// CTA-wide deterministic sum; thread 0 stores it at offset `off` of the norm table of every GPU.
+// CTA-wide deterministic sum; thread 0 stores it at offset `off` of this GPU's norm table.
 __device__ __forceinline__ void block_sum_to_c(const KrylovParams &P, Cons &cx, double v, long long off) {
     v = warp_sum(v);
     if (cx.lane == 0) cx.S->redn[cx.warp] = v;
@@ -265,8 +259,41 @@ __device__ __forceinline__ void block_sum_to_c(const KrylovParams &P, Cons &cx, 
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) s += cx.S->redn[w];
-        for (int r = 0; r < P.nranks; ++r) P.peer_partn[r][off] = s;
+        P.peer_partn[P.myrank][off] = s;
     }
+}
+
+// Team barrier + reduction of `ncols` quantities whose per-CTA partials sit in this GPU's table `ltab`
+// (row ci at ltab + ci*cpad, entry = CTA rank).  out[ci] (shared memory) = sum over the whole team.
+__device__ void team_reduce_c(const KrylovParams &P, Cons &cx, Team &tm, const double *ltab, int ncols, double *out,
+                              bool pushed_to_peers) {
+    team_barrier_c(tm, P, pushed_to_peers);
+    cx.seq += 1u;
+    if (P.nranks == 1) {
+        for (int ci = cx.warp; ci < ncols; ci += NW) {
+            const double s = team_sum(ltab + (long long)ci * P.cpad, tm.C, cx.lane);
+            if (cx.lane == 0) out[ci] = s;
+        }
+    } else {
+        const unsigned seq = cx.seq;
+        const long long pbase = (long long)(seq & 1u) * (MAXCOL + 1) * 8;
+        if (cx.warp == 0) {  // this GPU's sum of quantity ci goes to every GPU's inbox
+            for (int ci = tm.rank; ci < ncols; ci += tm.C) {
+                const double s = team_sum(ltab + (long long)ci * P.cpad, tm.C, cx.lane);
+                if (cx.lane < P.nranks) ll_push(P.peer_pkt[cx.lane] + pbase + (long long)ci * 8 + P.myrank, s, seq);
+            }
+        }
+        for (int ci = cx.warp; ci < ncols; ci += NW) {
+            double v = 0.0;
+            if (cx.lane < P.nranks) v = ll_poll(P.peer_pkt[P.myrank] + pbase + (long long)ci * 8 + cx.lane, seq);
+            double s = 0.0;
+            for (int r = 0; r < P.nranks; ++r) s += __shfl_sync(0xffffffffu, v, r);
+            if (cx.lane == 0) out[ci] = s;
+        }
+        consumer_sync();
+        if (cx.tid == 0) __threadfence_system();  // L1 is invalidated before anyone gathers pushed halo values
+    }
+    consumer_sync();
 }
 
 // Push this CTA's rows that other GPUs gather (halo) into their gather buffers (peer stores over NVLink).
@@ -481,8 +508,7 @@ __device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) s += S->red[buf][w][tid];
-            const long long off = part_off + (long long)(cb - lo + tid) * P.cpad + P.myrank * tm.C + tm.rank;
-            for (int r = 0; r < P.nranks; ++r) P.peer_part[r][off] = s;
+            P.peer_part[P.myrank][part_off + (long long)(cb - lo + tid) * P.cpad + tm.rank] = s;
         }
     }
 }
@@ -558,8 +584,6 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
     double xscale;
     int jstart;
     int m_out = P.m, breakdown = 0;
-    const int ctot = tm.C * P.nranks;                 // CTAs of the (possibly multi-GPU) team
-    const int gcta = P.myrank * tm.C + tm.rank;       // this CTA's index in it
     const bool sharded = P.nranks > 1;
     const bool via_xb0 = p > 0 || sharded;            // first gather source must carry tail / halo entries
     const double *lpart = P.peer_part[P.myrank];      // this GPU's inboxes
@@ -580,10 +604,10 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
             if (P.myrank == 0) nrm = fma(bt, bt, nrm);
         }
         const long long pslot = partn0 + (long long)(2 + (nlocal & 1)) * P.cpad;
-        block_sum_to_c(P, cx, nrm, pslot + gcta);
+        block_sum_to_c(P, cx, nrm, pslot + tm.rank);
         push_halo(P, cx, G, tm, xoff0);
-        team_barrier_c(tm, P);
-        const double beta = sqrt(team_sum(lpartn + pslot, ctot, cx.lane));
+        team_reduce_c(P, cx, tm, lpartn + pslot, 1, S->bc, sharded);
+        const double beta = sqrt(S->bc[0]);
         if (tm.rank == 0 && tid == 0) P.scal[prob * 4] = beta;
         if (beta == 0.0) {
             if (tm.rank == 0 && tid == 0) {
@@ -625,9 +649,9 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
                 reinterpret_cast<double2 *>(xb0 + G.r0)[i] = v2;
             }
             if (p > 0 && tm.rank == 0 && tid < p) xb0[xt + tid] = vj[n + tid];
-            consumer_sync();
+            block_sum_to_c(P, cx, 0.0, partn0 + 2LL * P.cpad + tm.rank);  // (has the CTA barrier the push needs)
             push_halo(P, cx, G, tm, xoff0);
-            team_barrier_c(tm, P);
+            team_reduce_c(P, cx, tm, lpartn + partn0 + 2LL * P.cpad, 1, S->bc, true);  // every GPU's halo is in place
             xsrc = xb0;
         } else {
             xsrc = vj;
@@ -651,26 +675,20 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
         const int hi = jc;
         dots_phase_c(P, cx, G, tm, V, lo, hi, part);
-        team_barrier_c(tm, P);
-
         const int nc = hi - lo + 1;
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
-        for (int ci = cx.warp; ci < nc; ci += NW) {
-            const double s = team_sum(lpart + part + (long long)ci * P.cpad, ctot, cx.lane);
-            if (cx.lane == 0) {
-                S->hs[lo + ci - ulo] = s;
-                if (tm.rank == 0) Hd[(long long)jc * ldh + lo + ci] = s;
-            }
-        }
+        team_reduce_c(P, cx, tm, lpart + part, nc, S->hs + (lo - ulo), false);
+        if (tm.rank == 0)
+            for (int ci = tid; ci < nc; ci += NTC) Hd[(long long)jc * ldh + lo + ci] = S->hs[lo + ci - ulo];
         if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = beta_prev;
         consumer_sync();
 
         const double nrm = update_phase_c(P, cx, G, tm, V, ulo, hi, xout);
-        block_sum_to_c(P, cx, nrm, partn + gcta);
+        block_sum_to_c(P, cx, nrm, partn + tm.rank);
         push_halo(P, cx, G, tm, xoff);  // after block_sum's CTA barrier: the whole w slice is in place
-        team_barrier_c(tm, P);
+        team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, sharded);
 
-        const double beta = sqrt(team_sum(lpartn + partn, ctot, cx.lane));
+        const double beta = sqrt(S->bc[0]);
         if (tm.rank == 0 && tid == 0) Hd[(long long)jc * ldh + jc + 1] = beta;
         {
             double *vn = V + (long long)(jc + 1) * ldv;
@@ -757,6 +775,7 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
     cx.tid = tid;
     cx.lane = tid & 31;
     cx.warp = tid >> 5;
+    cx.seq = P.seq_base;
 
     int nlocal = -1;
     for (int prob = team; prob < P.nprob; prob += P.nteams) {

@@ -95,9 +95,9 @@ if "c4" in which:
     ul = torch.randn(nl, 2, dtype=torch.float64, device="cuda")
     res = {}
     for h in (True, False):
-        P.kiops_sharded(1.0, sop, ul, ishermitian=h)
+        P.kiops_sharded(1.0, sop, ul, ishermitian=h, return_device=True)
         dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
-        for _ in range(3): w, st = P.kiops_sharded(1.0, sop, ul, ishermitian=h)
+        for _ in range(3): w, st = P.kiops_sharded(1.0, sop, ul, ishermitian=h, return_device=True)
         torch.cuda.synchronize(); dist.barrier(); dt = (time.perf_counter() - t0) / 3
         res[f"herm{int(h)}"] = {"s_per_solve": dt, "stats": st}
     log(json.dumps({"c4_kiops_row_sharded": res, "n_gpus": world}))
