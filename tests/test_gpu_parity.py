@@ -331,3 +331,50 @@ def test_error_estimate_mode(gpu, oracle):
     assert np.linalg.norm(gpu.expv(0.5, A, np.zeros(3000), mode="error_estimate")) == 0.0
     with pytest.raises(gpu.UnsupportedError):
         gpu.expv(0.5, convdiff2d(60, 50), b, mode="error_estimate")
+
+
+def test_edge_layouts_and_breakdown_in_stream_mode(gpu, oracle):
+    """Odd sizes (LDG kernel), tiny CSR operators, empty rows, and a happy breakdown while the TMA producer is
+    running ahead (CSR stream mode)."""
+    rng = np.random.default_rng(31)
+    eng = gpu.get_engine()
+    # dense with odd n -> unaligned columns -> LDG kernel
+    D = rng.standard_normal((301, 301)) / 10
+    b = rng.standard_normal(301)
+    assert relerr(gpu.expv(1.0, D, b, m=30), oracle.expv(1.0, D, b, m=30)) < RTOL
+    assert eng.last_kernel() == "ldg"
+    # CSR with n smaller than one CTA slice, and one with empty rows
+    T = sp.diags([np.ones(9), -2 * np.ones(10), np.ones(9)], [-1, 0, 1]).tocsr()
+    b10 = rng.standard_normal(10)
+    assert relerr(gpu.expv(0.5, T, b10, m=10), oracle.expv(0.5, T, b10, m=10)) < RTOL
+    E = sp.random(400, 400, density=0.01, random_state=5, format="lil")
+    E[7, :] = 0
+    E[123, :] = 0
+    E = (E.tocsr() - 2 * sp.identity(400)).tolil()
+    E[7, :] = 0      # truly empty rows (no diagonal either)
+    E[123, :] = 0
+    E = E.tocsr()
+    E.eliminate_zeros()
+    b400 = rng.standard_normal(400)
+    assert relerr(gpu.expv(0.7, E, b400, m=25), oracle.expv(0.7, E, b400, m=25)) < RTOL
+    # breakdown in CSR stream mode: a diagonal operator with 3 distinct eigenvalues has a 3-dimensional Krylov space
+    n = 6000
+    d = np.array([1.0, 2.0, 3.0])[np.arange(n) % 3]
+    Dg = sp.diags(d).tocsr()
+    bn = rng.standard_normal(n)
+    for herm in (True, False):
+        Ks = gpu.arnoldi(Dg, bn, m=30, ishermitian=herm)
+        Ko = oracle.arnoldi(Dg, bn, m=30, ishermitian_=herm)
+        assert eng.last_kernel() == "tma"
+        assert Ks.m == Ko.m == 3 and Ks.wasbreakdown
+        w = gpu.expv(0.9, Dg, bn, m=30, ishermitian=herm)
+        assert relerr(w, np.exp(0.9 * d) * bn) < 1e-9
+    # a batch in which some problems break down and some do not
+    B = rng.standard_normal((n, 5))
+    W = gpu.expv_batched([0.1, 0.2, 0.3, 0.4, 0.5], Dg, B, m=30)
+    for i, t in enumerate([0.1, 0.2, 0.3, 0.4, 0.5]):
+        assert relerr(W[:, i], np.exp(t * d) * B[:, i]) < 1e-9
+    # large Krylov dimension (m = 100), full Arnoldi
+    A = convdiff2d(50, 40)
+    b2 = rng.standard_normal(2000)
+    assert relerr(gpu.expv(2.0, A, b2, m=100), oracle.expv(2.0, A, b2, m=100)) < 1e-9
