@@ -83,8 +83,8 @@ class Engine:
 
     def set_flag(self, name: str, value: bool):
         """'force_ldg' or 'host_smallexp' (include/b200krylov.h: B200K_FLAG_*)."""
-        flag = {"force_ldg": 1, "host_smallexp": 2}[name]
-        self.check(self.lib.b200k_set_flag(self.handle, flag, 1 if value else 0))
+        flag = {"force_ldg": 1, "host_smallexp": 2, "l2hint": 3}[name]
+        self.check(self.lib.b200k_set_flag(self.handle, flag, int(value)))
 
     def last_kernel(self):
         """'ldg' (krylov_persistent_kernel) or 'tma' (krylov_tma_kernel) for the last factorisation."""

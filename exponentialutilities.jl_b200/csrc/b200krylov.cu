@@ -84,6 +84,8 @@ struct b200k_context {
     int sm_count = 0;
     int max_ctas = 0;  // co-resident CTAs of the persistent kernel
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime (no libcuda link dependency)
+    int l2hint = -1;        // B200K_FLAG_L2HINT: -1 automatic, 0 never, 1 always evict_first for operator chunks
+    long long l2_bytes = 0;
     int host_smallexp = 0;  // B200K_SMALLEXP=host: one-shot / batched expv do the small exponential on the host
     DevBuf tdev, errdev;
     HostBuf errh;
@@ -407,6 +409,19 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
                 P.dense_cpt = cpt;
                 P.dense_box_rows = box_rows;
+            }
+        }
+        // L2 policy for the operator stream (see producer_problem)
+        P.l2hint = 0;
+        P.hintA_cols = 1 << 30;
+        if (op->kind == 0) {
+            if (h->l2hint == 1) P.hintA_cols = 0;
+            else if (h->l2hint < 0) {
+                const double budget = 0.75 * (double)h->l2_bytes;
+                const double S_A = 12.0 * (double)op->nnz + 4.0 * (double)(n + 1);
+                const double per_col = 2.0 * 8.0 * (double)n * (c.nprob > 1 ? c.g.nteams : 1);
+                const double cols = (budget - S_A) / per_col;
+                P.hintA_cols = cols <= 0 ? 0 : (cols > 1e6 ? (1 << 30) : (int)std::ceil(cols));
             }
         }
         P.dscratch_off = (int)(fixed + wsb + (size_t)nslot * SLOT_BYTES);
@@ -779,6 +794,7 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
         return B200K_ECUDA;
     }
     h->sm_count = prop.multiProcessorCount;
+    h->l2_bytes = prop.l2CacheSize;
     if (!prop.cooperativeLaunch ||
         cudaFuncSetAttribute((const void *)krylov_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)SMEM_LIMIT) != cudaSuccess) {
@@ -867,6 +883,7 @@ int b200k_set_flag(b200k_handle_t h, int flag, int value) {
     if (!h) return B200K_EARG;
     if (flag == B200K_FLAG_FORCE_LDG) h->force_ldg = value ? 1 : 0;
     else if (flag == B200K_FLAG_HOST_SMALLEXP) h->host_smallexp = value ? 1 : 0;
+    else if (flag == B200K_FLAG_L2HINT) h->l2hint = value < 0 ? -1 : (value ? 1 : 0);
     else return fail(h, B200K_EARG, "unknown flag");
     return B200K_OK;
 }

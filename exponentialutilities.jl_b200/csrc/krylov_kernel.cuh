@@ -92,6 +92,8 @@ struct KrylovParams {
     int nnz_cap;       // nnz capacity of one ring slot holding a CSR chunk (val | colind | rowptr segment)
     int nslot;         // ring depth
     int tile_rows;     // rows per basis tile (multiple of 16, <= 4096)
+    int l2hint;        // bit 1: basis tiles L2::evict_last (experiment; off)
+    int hintA_cols;    // operator chunks get L2::evict_first in steps whose window has >= this many columns
     int dense_cpt;     // dense operator: columns per ring slot (0: direct loads)
     int dense_box_rows;  // rows per tensor-map box (<= 256); a tile = slice/dense_box_rows boxes of dense_cpt columns
     int dscratch_off;  // byte offset of the dense mat-vec reduction scratch in dynamic shared memory

@@ -139,9 +139,18 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
     const int jstart = P.j0 == 0 ? 1 : P.j0;
     const int iopw = P.iop > 0 ? P.iop : P.m;
     const int nnz_cap = P.nnz_cap;
+    // L2 eviction priorities (P.l2hint): the operator is streamed once per step and would otherwise push the
+    // basis out of the 126 MB L2 between the two Gram-Schmidt passes.
+    const uint64_t polA = policy_evict_first();
+    const uint64_t polV = policy_evict_last();
+    const bool hintV = (P.l2hint & 2) != 0;
     bool stopped = false;
     for (int j = jstart; j <= P.m && !stopped; ++j) {
         const int jc = j - 1;
+        // operator chunks are marked evict_first in the steps whose orthogonalisation window is so wide that the
+        // operator could not survive in L2 until the next step anyway (hintA_cols from the host: L2 size vs
+        // operator + two basis passes); in narrow-window steps (Lanczos, IOP, early Arnoldi) it stays resident.
+        const bool hintA = (jc - (P.lanczos ? jc : max(0, jc - iopw + 1)) + 1) >= P.hintA_cols;
         if (P.op_kind == OP_CSR_STREAM) {
             for (int c = 0; c < G.nch; ++c) {
                 if (!prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
@@ -161,11 +170,21 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
                     S->slot_a0[rg.slot] = a0;
                     unsigned char *dst = rg.ptr();
                     mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)cnt * 12u + (uint32_t)rpc * 4u);
-                    if (cnt > 0) {
-                        bulk_g2s(dst, P.val + a0, (uint32_t)cnt * 8u, &S->full[rg.slot]);
-                        bulk_g2s(dst + (size_t)nnz_cap * 8, P.colind + a0, (uint32_t)cnt * 4u, &S->full[rg.slot]);
+                    if (hintA) {
+                        if (cnt > 0) {
+                            bulk_g2s_hint(dst, P.val + a0, (uint32_t)cnt * 8u, &S->full[rg.slot], polA);
+                            bulk_g2s_hint(dst + (size_t)nnz_cap * 8, P.colind + a0, (uint32_t)cnt * 4u,
+                                          &S->full[rg.slot], polA);
+                        }
+                        bulk_g2s_hint(dst + (size_t)nnz_cap * 12, P.rowptr + rs, (uint32_t)rpc * 4u, &S->full[rg.slot],
+                                      polA);
+                    } else {
+                        if (cnt > 0) {
+                            bulk_g2s(dst, P.val + a0, (uint32_t)cnt * 8u, &S->full[rg.slot]);
+                            bulk_g2s(dst + (size_t)nnz_cap * 8, P.colind + a0, (uint32_t)cnt * 4u, &S->full[rg.slot]);
+                        }
+                        bulk_g2s(dst + (size_t)nnz_cap * 12, P.rowptr + rs, (uint32_t)rpc * 4u, &S->full[rg.slot]);
                     }
-                    bulk_g2s(dst + (size_t)nnz_cap * 12, P.rowptr + rs, (uint32_t)rpc * 4u, &S->full[rg.slot]);
                 }
                 rg.advance();
                 ++issued;
@@ -202,8 +221,11 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
                     if (!prod_wait_col(S, col, seq, lane) || !prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
                     if (lane == 0) {
                         mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 8u);
-                        bulk_g2s(rg.ptr(), V + (long long)col * ldv + G.r0 + (long long)k * G.TR, (uint32_t)rows * 8u,
-                                 &S->full[rg.slot]);
+                        {
+                        const double *src = V + (long long)col * ldv + G.r0 + (long long)k * G.TR;
+                        if (hintV) bulk_g2s_hint(rg.ptr(), src, (uint32_t)rows * 8u, &S->full[rg.slot], polV);
+                        else bulk_g2s(rg.ptr(), src, (uint32_t)rows * 8u, &S->full[rg.slot]);
+                    }
                     }
                     rg.advance();
                     ++issued;
@@ -216,8 +238,11 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
                 if (!prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
                 if (lane == 0) {
                     mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 8u);
-                    bulk_g2s(rg.ptr(), V + (long long)col * ldv + G.r0 + (long long)k * G.TR, (uint32_t)rows * 8u,
-                             &S->full[rg.slot]);
+                    {
+                        const double *src = V + (long long)col * ldv + G.r0 + (long long)k * G.TR;
+                        if (hintV) bulk_g2s_hint(rg.ptr(), src, (uint32_t)rows * 8u, &S->full[rg.slot], polV);
+                        else bulk_g2s(rg.ptr(), src, (uint32_t)rows * 8u, &S->full[rg.slot]);
+                    }
                 }
                 rg.advance();
                 ++issued;

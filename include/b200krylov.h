@@ -244,6 +244,8 @@ int b200k_last_kernel(b200k_handle_t h, int *which);
  * small exponential on the host (both branches of krylov_phiv.jl:225-244) instead of small_exp_kernel. */
 #define B200K_FLAG_FORCE_LDG 1
 #define B200K_FLAG_HOST_SMALLEXP 2
+#define B200K_FLAG_L2HINT 3 /* L2::evict_first on the CSR operator stream: -1 automatic (default: only in steps
+                               whose working set exceeds the L2), 0 never, 1 always */
 int b200k_set_flag(b200k_handle_t h, int flag, int value);
 
 #ifdef __cplusplus
