@@ -33,22 +33,23 @@ struct ProjectParams {
 };
 
 // grid = (row tiles, ceil(nc / PROJ_NC), nprob)
-__global__ void __launch_bounds__(PROJ_NT) project_kernel(const ProjectParams P) {
-    __shared__ double Ys[PROJ_NC][PROJ_MAXM];
-    __shared__ double cs[PROJ_NC];
+template <int NCT>
+__global__ void __launch_bounds__(PROJ_NT) project_kernel_t(const ProjectParams P) {
+    __shared__ double Ys[NCT][PROJ_MAXM];
+    __shared__ double cs[NCT];
     const int prob = blockIdx.z;
-    const int c0 = blockIdx.y * PROJ_NC;
-    const int ncl = min(PROJ_NC, P.nc - c0);
+    const int c0 = blockIdx.y * NCT;
+    const int ncl = min(NCT, P.nc - c0);
     const int m = P.mvec ? P.mvec[prob] : P.m;
     const double beta = P.betavec ? P.betavec[prob] : P.beta;
     const double *V = P.V + (long long)prob * P.V_stride;
     double *W = P.W + (long long)prob * P.W_stride;
     const double *Y = P.Y + (long long)prob * P.Y_stride;
-    for (int idx = threadIdx.x; idx < PROJ_NC * m; idx += PROJ_NT) {
+    for (int idx = threadIdx.x; idx < NCT * m; idx += PROJ_NT) {
         const int c = idx / m, i = idx % m;
         Ys[c][i] = (c < ncl) ? Y[(long long)(c0 + c) * P.ldy + i] : 0.0;
     }
-    if (threadIdx.x < PROJ_NC)
+    if (threadIdx.x < NCT)
         cs[threadIdx.x] = (P.corr && threadIdx.x < ncl) ? P.corr[c0 + threadIdx.x] : 0.0;
     __syncthreads();
     const bool has_corr = P.corr != nullptr;
@@ -63,23 +64,30 @@ __global__ void __launch_bounds__(PROJ_NT) project_kernel(const ProjectParams P)
         const long long units = P.nrows >> 1;
         for (long long u = (long long)blockIdx.x * PROJ_NT + threadIdx.x; u < units;
              u += (long long)gridDim.x * PROJ_NT) {
-            double2 acc[PROJ_NC];
+            double2 acc[NCT];
 #pragma unroll
-            for (int c = 0; c < PROJ_NC; ++c) acc[c] = make_double2(0.0, 0.0);
+            for (int c = 0; c < NCT; ++c) acc[c] = make_double2(0.0, 0.0);
             const double *vp = V + 2 * u;
-#pragma unroll 4
-            for (int i = 0; i < m; ++i) {
-                const double2 v2 = ld_stream2(vp + (long long)i * P.ldv);
+            constexpr int LB = NCT == 1 ? 10 : 4;  // loads in flight per thread
+            for (int ib = 0; ib < m; ib += LB) {
+                double2 v2[LB];
 #pragma unroll
-                for (int c = 0; c < PROJ_NC; ++c) {
-                    acc[c].x = fma(v2.x, Ys[c][i], acc[c].x);
-                    acc[c].y = fma(v2.y, Ys[c][i], acc[c].y);
-                }
+                for (int u = 0; u < LB; ++u)
+                    if (ib + u < m) v2[u] = ld_stream2(vp + (long long)(ib + u) * P.ldv);
+#pragma unroll
+                for (int u = 0; u < LB; ++u)
+                    if (ib + u < m) {
+#pragma unroll
+                        for (int c = 0; c < NCT; ++c) {
+                            acc[c].x = fma(v2[u].x, Ys[c][ib + u], acc[c].x);
+                            acc[c].y = fma(v2[u].y, Ys[c][ib + u], acc[c].y);
+                        }
+                    }
             }
             double2 vl = make_double2(0.0, 0.0);
             if (has_corr) vl = ld_stream2(vlast + 2 * u);
 #pragma unroll
-            for (int c = 0; c < PROJ_NC; ++c)
+            for (int c = 0; c < NCT; ++c)
                 if (c < ncl) {
                     double2 o;
                     o.x = beta * acc[c].x;
@@ -94,19 +102,19 @@ __global__ void __launch_bounds__(PROJ_NT) project_kernel(const ProjectParams P)
     } else {
         for (long long r = (long long)blockIdx.x * PROJ_NT + threadIdx.x; r < P.nrows;
              r += (long long)gridDim.x * PROJ_NT) {
-            double acc[PROJ_NC];
+            double acc[NCT];
 #pragma unroll
-            for (int c = 0; c < PROJ_NC; ++c) acc[c] = 0.0;
+            for (int c = 0; c < NCT; ++c) acc[c] = 0.0;
             const double *vp = V + r;
 #pragma unroll 4
             for (int i = 0; i < m; ++i) {
                 const double v1 = ld_stream1(vp + (long long)i * P.ldv);
 #pragma unroll
-                for (int c = 0; c < PROJ_NC; ++c) acc[c] = fma(v1, Ys[c][i], acc[c]);
+                for (int c = 0; c < NCT; ++c) acc[c] = fma(v1, Ys[c][i], acc[c]);
             }
             const double vl = has_corr ? vlast[r] : 0.0;
 #pragma unroll
-            for (int c = 0; c < PROJ_NC; ++c)
+            for (int c = 0; c < NCT; ++c)
                 if (c < ncl) {
                     double o = beta * acc[c];
                     if (has_corr) o = fma(cs[c], vl, o);
@@ -114,6 +122,12 @@ __global__ void __launch_bounds__(PROJ_NT) project_kernel(const ProjectParams P)
                 }
         }
     }
+}
+
+// Launch helper: one output column (expv, kiops) uses the specialised instance.
+inline void launch_project_kernel(const ProjectParams &P, dim3 grid, cudaStream_t stream) {
+    if (P.nc == 1) project_kernel_t<1><<<grid, PROJ_NT, 0, stream>>>(P);
+    else project_kernel_t<PROJ_NC><<<grid, PROJ_NT, 0, stream>>>(P);
 }
 
 // ---- operator ingestion ---------------------------------------------------------------------------

@@ -507,11 +507,11 @@ int launch_project(b200k_context *h, const double *V, long long ldv, long long n
     P.ldw = ldw;
     P.vec2 = (nrows % 2 == 0) && (ldv % 2 == 0) && (ldw % 2 == 0) && aligned16(V) && aligned16(W);
     const long long units = P.vec2 ? nrows / 2 : nrows;
-    int gx = (int)std::min<long long>((units + PROJ_NT - 1) / PROJ_NT, (long long)h->sm_count * 8);
+    int gx = (int)std::min<long long>((units + PROJ_NT - 1) / PROJ_NT, (long long)h->sm_count * 16);
     if (gx < 1) gx = 1;
-    dim3 grid(gx, (nc + PROJ_NC - 1) / PROJ_NC, 1);
+    dim3 grid(gx, nc == 1 ? 1 : (nc + PROJ_NC - 1) / PROJ_NC, 1);
     if (h->timing) CK(h, cudaEventRecord(h->ev[2], h->stream));
-    project_kernel<<<grid, PROJ_NT, 0, h->stream>>>(P);
+    launch_project_kernel(P, grid, h->stream);
     CK(h, cudaGetLastError());
     if (h->timing) CK(h, cudaEventRecord(h->ev[3], h->stream));
     h->launches += 1;
@@ -704,7 +704,7 @@ int launch_smallexp_project(b200k_context *h, int nprob, int m, int lanczos, con
              aligned16(V) && aligned16(W);
     const long long units = P.vec2 ? n / 2 : n;
     const long long want = (units + PROJ_NT - 1) / PROJ_NT;
-    int gx = (int)std::min<long long>(want, nprob > 1 ? 64 : (long long)h->sm_count * 8);
+    int gx = (int)std::min<long long>(want, nprob > 1 ? 64 : (long long)h->sm_count * 16);
     if (gx < 1) gx = 1;
     for (int base = 0; base < nprob; base += 32768) {  // gridDim.z limit
         const int cnt = std::min(nprob - base, 32768);
@@ -714,7 +714,7 @@ int launch_smallexp_project(b200k_context *h, int nprob, int m, int lanczos, con
         Q.mvec += base;
         Q.betavec += base;
         Q.W += (long long)base * wstride;
-        project_kernel<<<dim3(gx, 1, cnt), PROJ_NT, 0, h->stream>>>(Q);
+        launch_project_kernel(Q, dim3(gx, 1, cnt), h->stream);
         h->launches += 1;
     }
     CK(h, cudaGetLastError());
@@ -1385,7 +1385,7 @@ int b200k_expv_batched(b200k_handle_t h, b200k_op_t op, int nb, const double *t,
         Q.mvec += base;
         Q.betavec += base;
         Q.W += (long long)base * ldw;
-        project_kernel<<<dim3(gx, 1, cnt), PROJ_NT, 0, h->stream>>>(Q);
+        launch_project_kernel(Q, dim3(gx, 1, cnt), h->stream);
         h->launches += 1;
     }
     CK(h, cudaGetLastError());
