@@ -111,6 +111,7 @@ struct b200k_context {
 
 struct b200k_comm {
     b200k_context *ctx = nullptr;
+    int device = 0;
     int rank = 0, nranks = 1;
     long long xlen = 0;
     int cpad = 0;
@@ -136,7 +137,8 @@ struct b200k_operator {
     long long nhalo = 0;
     DevBuf send_row, send_peer, send_pos, send_ofs;
     std::vector<int> send_row_host;
-    b200k_context *ctx = nullptr;
+    b200k_context *ctx = nullptr;  // creating handle (NOT dereferenced on destroy: it may already be gone)
+    int device = 0;
     int kind = 0;  // 0 CSR, 1 dense
     long long n = 0, nnz = 0;
     DevBuf rowptr, colind, val;  // owned, 0-based, padded
@@ -918,6 +920,7 @@ int b200k_op_csr_create(b200k_handle_t h, int64_t n, int64_t nnz, const int32_t 
     CK(h, cudaSetDevice(h->device));
     b200k_operator *op = new b200k_operator();
     op->ctx = h;
+    op->device = h->device;
     op->kind = 0;
     op->n = n;
     op->nnz = nnz;
@@ -986,6 +989,7 @@ int b200k_op_dense_create(b200k_handle_t h, int64_t n, const double *A, int64_t 
     CK(h, cudaSetDevice(h->device));
     b200k_operator *op = new b200k_operator();
     op->ctx = h;
+    op->device = h->device;
     op->kind = 1;
     op->n = n;
     op->nnz = n * n;
@@ -1039,7 +1043,7 @@ int b200k_op_dense_create(b200k_handle_t h, int64_t n, const double *A, int64_t 
 
 int b200k_op_destroy(b200k_op_t op) {
     if (!op) return B200K_OK;
-    if (op->ctx) cudaSetDevice(op->ctx->device);
+    cudaSetDevice(op->device);
     op->send_row.release();
     op->send_peer.release();
     op->send_pos.release();
@@ -1896,6 +1900,7 @@ int b200k_comm_create(b200k_handle_t h, int rank, int nranks, int64_t xlen, unsi
     CK(h, cudaSetDevice(h->device));
     b200k_comm *cm = new b200k_comm();
     cm->ctx = h;
+    cm->device = h->device;
     cm->rank = rank;
     cm->nranks = nranks;
     cm->xlen = round_up(xlen, 16);
@@ -1936,10 +1941,8 @@ int b200k_comm_connect(b200k_comm_t cm, const unsigned char *all_handles) {
 
 int b200k_comm_destroy(b200k_comm_t cm) {
     if (!cm) return B200K_OK;
-    if (cm->ctx) {
-        cudaSetDevice(cm->ctx->device);
-        cudaStreamSynchronize(cm->ctx->stream);
-    }
+    cudaSetDevice(cm->device);
+    cudaDeviceSynchronize();  // the handle (and its stream) may already have been destroyed
     for (int r = 0; r < cm->nranks; ++r)
         if (r != cm->rank && cm->peer[r]) cudaIpcCloseMemHandle(cm->peer[r]);
     if (cm->local) cudaFree(cm->local);
