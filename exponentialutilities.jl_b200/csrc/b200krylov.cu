@@ -430,7 +430,14 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
         smem = fixed + wsb + (size_t)nslot * SLOT_BYTES + extra;
         if (!P.w_in_smem) CK(h, h->wglob.ensure((size_t)nt * n * 8));
         P.wglob = h->wglob.as<double>();
-        kern = (const void *)krylov_tma_kernel;
+        {
+            const bool aug = c.p > 0;
+            switch (P.op_kind) {
+                case OP_CSR_STREAM: kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false>; break;
+                case OP_CSR_WARP: kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_WARP, true> : (const void *)krylov_tma_kernel<OP_CSR_WARP, false>; break;
+                default: kern = aug ? (const void *)krylov_tma_kernel<OP_DENSE, true> : (const void *)krylov_tma_kernel<OP_DENSE, false>; break;
+            }
+        }
         threads = NT2;
         h->last_kernel = 2;
     } else {
@@ -810,9 +817,14 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
         delete h;
         return B200K_ECUDA;
     }
-    if (cudaFuncSetAttribute((const void *)krylov_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)SMEM_LIMIT) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, krylov_tma_kernel, NT2, SMEM_LIMIT) != cudaSuccess ||
+    const void *tma_kernels[] = {(const void *)krylov_tma_kernel<OP_CSR_STREAM, false>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true>,
+                                 (const void *)krylov_tma_kernel<OP_CSR_WARP, false>, (const void *)krylov_tma_kernel<OP_CSR_WARP, true>,
+                                 (const void *)krylov_tma_kernel<OP_DENSE, false>, (const void *)krylov_tma_kernel<OP_DENSE, true>};
+    bool attr_ok = true;
+    for (const void *k : tma_kernels)
+        attr_ok = attr_ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) == cudaSuccess;
+    if (!attr_ok ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, krylov_tma_kernel<OP_CSR_STREAM, false>, NT2, SMEM_LIMIT) != cudaSuccess ||
         per_sm < 1) {
         delete h;
         return B200K_ECUDA;

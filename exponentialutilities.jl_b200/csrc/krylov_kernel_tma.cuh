@@ -133,6 +133,7 @@ __device__ __forceinline__ bool prod_wait_col(SmemTma *S, int col, int seq, int)
     return true;
 }
 
+template <int OPK, bool AUG>
 __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, SmemTma *S, Ring &rg,
                                  const TmaGeom &G, const double *V, int seq, unsigned &issued, int lane) {
     const long long ldv = P.ldv;
@@ -151,7 +152,7 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
         // operator could not survive in L2 until the next step anyway (hintA_cols from the host: L2 size vs
         // operator + two basis passes); in narrow-window steps (Lanczos, IOP, early Arnoldi) it stays resident.
         const bool hintA = (jc - (P.lanczos ? jc : max(0, jc - iopw + 1)) + 1) >= P.hintA_cols;
-        if (P.op_kind == OP_CSR_STREAM) {
+        if (OPK == OP_CSR_STREAM) {
             for (int c = 0; c < G.nch; ++c) {
                 if (!prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
                 if (lane == 0) {
@@ -190,7 +191,7 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
                 ++issued;
             }
             if (stopped) break;
-        } else if (P.op_kind == OP_DENSE && P.dense_cpt > 0 && G.nrows > 0) {
+        } else if (OPK == OP_DENSE && P.dense_cpt > 0 && G.nrows > 0) {
             // dense operator: a tile = dense_cpt columns x the CTA's row slice, fetched as slice/box_rows
             // tensor-map boxes (rows past n are zero-filled by the TMA unit and still count as bytes)
             const int nrb = P.slice / P.dense_box_rows;
@@ -330,17 +331,18 @@ __device__ __forceinline__ void push_halo(const KrylovParams &P, Cons &cx, const
         P.peer_xbuf[P.send_peer[e]][xoff + P.send_pos[e]] = cx.ws[P.send_row[e] - G.r0];
 }
 
+template <int OPK, bool AUG>
 __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *xsrc, double xscale) {
     SmemTma *S = cx.S;
     const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
-    const int n = P.n, p = P.p;
+    const int n = P.n, p = AUG ? P.p : 0;
     double *ws = cx.ws;
     if (p > 0) {
         if (tid < p) S->xtail[tid] = xsrc[n + P.nhalo + tid];
         consumer_sync();
         if (tid < p) S->wtail[tid] = (tid < p - 1) ? S->xtail[tid + 1] * xscale : 0.0;
     }
-    if (P.op_kind == OP_CSR_STREAM) {
+    if (OPK == OP_CSR_STREAM) {
         const int nnz_cap = P.nnz_cap;
         for (int c = 0; c < G.nch; ++c) {
             const int rl = c * P.ch_rows + tid;
@@ -378,7 +380,7 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
             }
             cx.release();
         }
-    } else if (P.op_kind == OP_CSR_WARP) {
+    } else if (OPK == OP_CSR_WARP) {
         for (int rl = warp; rl < G.nrows; rl += NW) {
             const int row = G.r0 + rl;
             const int e0 = P.rowptr[row], e1 = P.rowptr[row + 1];
@@ -484,6 +486,7 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
     consumer_sync();
 }
 
+template <int OPK, bool AUG>
 __device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
                              int lo, int hi, long long part_off) {
     SmemTma *S = cx.S;
@@ -521,7 +524,7 @@ __device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
                 }
             }
         }
-        if (P.p > 0 && tm.rank == 0 && P.myrank == 0 && tid == 0) {  // augmented tail rows (direct loads)
+        if (AUG && P.p > 0 && tm.rank == 0 && P.myrank == 0 && tid == 0) {  // augmented tail rows (direct loads)
 #pragma unroll
             for (int u = 0; u < CB; ++u)
                 if (u < nb)
@@ -541,6 +544,7 @@ __device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
     }
 }
 
+template <int OPK, bool AUG>
 __device__ double update_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
                                  int ulo, int uhi, double *xout) {
     SmemTma *S = cx.S;
@@ -583,7 +587,7 @@ __device__ double update_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom 
             }
         }
     }
-    if (P.p > 0 && tid < P.p) {
+    if (AUG && P.p > 0 && tid < P.p) {
         double wt = S->wtail[tid];
         for (int c = uhi; c >= ulo; --c) wt = fma(-hs[c - ulo], V[(long long)c * P.ldv + P.n + tid], wt);
         S->wtail[tid] = wt;
@@ -596,11 +600,12 @@ __device__ double update_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom 
 }
 
 // One problem on the consumer side.  Mirrors krylov_body<2> of krylov_kernel.cuh.
+template <int OPK, bool AUG>
 __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom &G, Team &tm, int prob, int nlocal,
                                  double *xb0, double *xb1, long long xoff0, long long part0, long long partn0) {
     SmemTma *S = cx.S;
     const int tid = cx.tid;
-    const int n = P.n, p = P.p;
+    const int n = P.n, p = AUG ? P.p : 0;
     double *V = P.V + (long long)prob * P.V_stride;
     double *Hd = P.Hd + (long long)prob * P.H_stride;
     const double *b = P.b + (long long)prob * P.b_stride;
@@ -698,11 +703,11 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         const long long part = part0 + (long long)par * MAXCOL * P.cpad;
         const long long partn = partn0 + (long long)par * P.cpad;
 
-        matvec_phase_c(P, cx, G, xsrc, xscale);
+        matvec_phase_c<OPK, AUG>(P, cx, G, xsrc, xscale);
 
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
         const int hi = jc;
-        dots_phase_c(P, cx, G, tm, V, lo, hi, part);
+        dots_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, hi, part);
         const int nc = hi - lo + 1;
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
         team_reduce_c(P, cx, tm, lpart + part, nc, S->hs + (lo - ulo), false);
@@ -711,7 +716,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = beta_prev;
         consumer_sync();
 
-        const double nrm = update_phase_c(P, cx, G, tm, V, ulo, hi, xout);
+        const double nrm = update_phase_c<OPK, AUG>(P, cx, G, tm, V, ulo, hi, xout);
         block_sum_to_c(P, cx, nrm, partn + tm.rank);
         push_halo(P, cx, G, tm, xoff);  // after block_sum's CTA barrier: the whole w slice is in place
         team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, sharded);
@@ -746,6 +751,9 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
     }
 }
 
+// One instance per (operator kind, augmented or not): the persistent kernel is sensitive to code size (an unused
+// extra mat-vec loop cost 3-5 % everywhere), so each instance carries only the paths it can take.
+template <int OPK, bool AUG>
 __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constant__ KrylovParams P,
                                                             const __grid_constant__ CUtensorMap tmA) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -767,7 +775,7 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
     G.nrows = min(P.n, G.r0 + P.slice) - G.r0;
     G.TR = P.tile_rows;
     G.ntk = (G.nrows + G.TR - 1) / G.TR;
-    G.nch = P.op_kind == OP_CSR_STREAM ? (G.nrows + P.ch_rows - 1) / P.ch_rows : 0;
+    G.nch = OPK == OP_CSR_STREAM ? (G.nrows + P.ch_rows - 1) / P.ch_rows : 0;
 
     if (G.nch > 0 && G.nch <= MAXCH2) {
         for (int c = tid; c < G.nch; c += NT2) {
@@ -812,12 +820,12 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
             if (tid == NTC) {
                 Ring rg{ring, P.nslot, 0, 0u};
                 unsigned issued = 0;
-                producer_problem(P, &tmA, S, rg, G, P.V + (long long)prob * P.V_stride, nlocal + 1, issued, 0);
+                producer_problem<OPK, AUG>(P, &tmA, S, rg, G, P.V + (long long)prob * P.V_stride, nlocal + 1, issued, 0);
             }
             __syncwarp();
         } else {
             cx.rg = Ring{ring, P.nslot, 0, 0u};
-            consumer_problem(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
+            consumer_problem<OPK, AUG>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
             consumer_sync();
             if (tid == 0) S->stop_seq = nlocal + 1;
         }
