@@ -587,6 +587,29 @@ def exponential_(A):
     return Af
 
 
+def exponential_batched_(A, engine: Engine | None = None):
+    """exponential! of a batch of small matrices on the device, in place.  ``A``: float64 CUDA tensor of
+    shape (nbatch, n, n) holding each matrix in COLUMN-major order (i.e. A[b] is the transpose of the matrix as
+    torch prints it), n <= 48; NumPy input of shape (nbatch, n, n) (ordinary row-major matrices) is converted,
+    processed on the device and returned as NumPy."""
+    eng = engine or get_engine()
+    was_np = not (torch is not None and isinstance(A, torch.Tensor))
+    if was_np:
+        An = np.asarray(A, dtype=np.float64)
+        if An.ndim != 3 or An.shape[1] != An.shape[2]:
+            raise DimensionMismatch("expected (nbatch, n, n)")
+        At = torch.from_numpy(np.ascontiguousarray(An.transpose(0, 2, 1))).to(eng.device)
+    else:
+        At = A
+        if At.dim() != 3 or At.shape[1] != At.shape[2] or At.dtype != torch.float64 or not At.is_contiguous():
+            raise DimensionMismatch("expected a contiguous float64 (nbatch, n, n) tensor")
+    nb, n, _ = At.shape
+    eng.bind_stream()
+    eng.check(eng.lib.b200k_exponential_batched(eng.handle, int(nb), int(n), C.c_void_p(At.data_ptr()), int(n),
+                                                int(n) * int(n)))
+    return At.cpu().numpy().transpose(0, 2, 1).copy() if was_np else At
+
+
 def phiv_dense(A, v, k):
     """phiv_dense(A, v, k) -- src/phi.jl:63-66, 84-115 (host)."""
     lib = _lib.load()

@@ -839,6 +839,8 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
     if (const char *env = std::getenv("B200K_SMALLEXP")) h->host_smallexp = std::strcmp(env, "host") == 0 ? 1 : 0;
     cudaFuncSetAttribute((const void *)small_exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          6 * SE_MAXM * SE_MAXM * 8);
+    cudaFuncSetAttribute((const void *)small_exp_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         6 * SE_MAXM * SE_MAXM * 8);
     if (const char *env = std::getenv("B200K_KERNEL")) h->force_ldg = std::strcmp(env, "ldg") == 0 ? 1 : 0;
     h->max_ctas = std::min(h->sm_count, CPAD);  // one CTA per SM
     for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
@@ -2013,6 +2015,26 @@ int b200k_exponential(int n, double *A, int lda) {
     if (st) return B200K_ESINGULAR;
     for (int j = 0; j < n; ++j)
         for (int i = 0; i < n; ++i) A[(size_t)j * lda + i] = C[(size_t)j * n + i];
+    return B200K_OK;
+}
+
+int b200k_exponential_batched(b200k_handle_t h, int nbatch, int n, double *A, int lda, int64_t stride) {
+    if (!h || !A || nbatch < 1 || n < 1 || lda < n || stride < (int64_t)lda * (n - 1) + n) return B200K_EARG;
+    if (n > SE_MAXM) return fail(h, B200K_EUNSUPPORTED, "device-side exponential supports n <= 48");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, h->errdev.ensure(64));
+    CK(h, cudaMemsetAsync(h->errdev.p, 0, 4, h->stream));
+    for (int base = 0; base < nbatch; base += 65535) {
+        const int cnt = std::min(nbatch - base, 65535);
+        small_exp_batched_kernel<<<cnt, SE_NT, (size_t)6 * n * n * 8, h->stream>>>(n, A + (long long)base * stride, lda,
+                                                                                  stride, h->errdev.as<int>());
+        h->launches += 1;
+    }
+    CK(h, cudaGetLastError());
+    int err = 0;
+    CK(h, cudaMemcpyAsync(&err, h->errdev.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (err) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
     return B200K_OK;
 }
 

@@ -47,37 +47,15 @@ __device__ __forceinline__ void se_matmul(int n, const double *A, const double *
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SE_NT) small_exp_kernel(const SmallExpParams P) {
-    extern __shared__ double sm[];
-    __shared__ double sc[SE_MAXM];   // balancing scale factors
-    __shared__ double colsum[SE_MAXM];
+// exp of the n x n column-major matrix in sm[0 .. n*n) (shared memory, 6 n^2 doubles of workspace behind it).
+// Returns a pointer (into sm) to the exponential of the BALANCED matrix: exp(A)[i, j] = sc[i] * X[i, j] / sc[j];
+// nullptr if the Pade denominator is singular.  `full` = all columns are needed (otherwise only column 0).
+__device__ double *se_expm_core(int n, double *sm, double *sc, double *colsum, bool full) {
     __shared__ double s_nA;
     __shared__ int s_piv, s_flag;
-    const int prob = blockIdx.x;
     const int tid = threadIdx.x;
-    const double beta = P.scal[prob * 4];
-    int n = P.stat[prob * 4 + 0];
-    if (beta == 0.0) n = P.m;
-    if (tid == 0) {
-        P.betavec[prob] = beta;
-        P.mvec[prob] = n;
-    }
-    double *yout = P.Y + (long long)prob * P.ldy;
-    if (beta == 0.0 || n < 1 || n > SE_MAXM) {
-        for (int i = tid; i < P.ldy; i += SE_NT) yout[i] = 0.0;
-        return;
-    }
-    const double t = P.tvec ? P.tvec[prob] : P.t;
-    const double *H = P.Hd + (long long)prob * P.H_stride;
     const int nn = n * n;
     double *A = sm, *A2 = sm + nn, *Pm = sm + 2 * nn, *U = sm + 3 * nn, *V = sm + 4 * nn, *T = sm + 5 * nn;
-
-    for (int idx = tid; idx < nn; idx += SE_NT) {
-        const int i = idx % n, j = idx / n;
-        double v = H[(long long)j * P.ldh + i];
-        if (P.lanczos && j == i + 1) v = H[(long long)i * P.ldh + j];  // mirror the sub-diagonal
-        A[idx] = t * v;
-    }
     if (tid < n) sc[tid] = 1.0;
     __syncthreads();
 
@@ -234,11 +212,7 @@ __global__ void __launch_bounds__(SE_NT) small_exp_kernel(const SmallExpParams P
             }
         }
         __syncthreads();
-        if (s_flag) {
-            if (tid == 0) *P.err = 1;
-            for (int i = tid; i < P.ldy; i += SE_NT) yout[i] = 0.0;
-            return;
-        }
+        if (s_flag) return nullptr;  // singular Pade denominator (uniform for the CTA)
         const int pv = s_piv;
         if (pv != k) {  // swap rows k and pv of D and X
             for (int j = tid; j < 2 * n; j += SE_NT) {
@@ -270,7 +244,7 @@ __global__ void __launch_bounds__(SE_NT) small_exp_kernel(const SmallExpParams P
     }
     // back substitution U x = y: sequential in k, parallel over (row, right-hand side).  Only column 0 is
     // needed when no squaring follows.
-    const int nrhs = si > 0 ? n : 1;
+    const int nrhs = (si > 0 || full) ? n : 1;
     for (int k = n - 1; k >= 0; --k) {
         const double dkk = D[k * n + k];
         for (int j = tid; j < nrhs; j += SE_NT) X[j * n + k] /= dkk;
@@ -287,8 +261,68 @@ __global__ void __launch_bounds__(SE_NT) small_exp_kernel(const SmallExpParams P
         se_matmul(n, Xc, Xc, Xn);
         double *tmp = Xc; Xc = Xn; Xn = tmp;
     }
-    // ---- unbalance and take the first column: exp(tH)[i, 0] = sc[i] * X[i, 0] / sc[0] ----
+    return Xc;
+}
+
+__global__ void __launch_bounds__(SE_NT) small_exp_kernel(const SmallExpParams P) {
+    extern __shared__ double sm[];
+    __shared__ double sc[SE_MAXM];   // balancing scale factors
+    __shared__ double colsum[SE_MAXM];
+    const int prob = blockIdx.x;
+    const int tid = threadIdx.x;
+    const double beta = P.scal[prob * 4];
+    int n = P.stat[prob * 4 + 0];
+    if (beta == 0.0) n = P.m;
+    if (tid == 0) {
+        P.betavec[prob] = beta;
+        P.mvec[prob] = n;
+    }
+    double *yout = P.Y + (long long)prob * P.ldy;
+    if (beta == 0.0 || n < 1 || n > SE_MAXM) {
+        for (int i = tid; i < P.ldy; i += SE_NT) yout[i] = 0.0;
+        return;
+    }
+    const double t = P.tvec ? P.tvec[prob] : P.t;
+    const double *H = P.Hd + (long long)prob * P.H_stride;
+    const int nn = n * n;
+    for (int idx = tid; idx < nn; idx += SE_NT) {
+        const int i = idx % n, j = idx / n;
+        double v = H[(long long)j * P.ldh + i];
+        if (P.lanczos && j == i + 1) v = H[(long long)i * P.ldh + j];  // mirror the sub-diagonal
+        sm[idx] = t * v;
+    }
+    __syncthreads();
+    const double *Xc = se_expm_core(n, sm, sc, colsum, false);
+    if (!Xc) {
+        if (tid == 0) *P.err = 1;
+        for (int i = tid; i < P.ldy; i += SE_NT) yout[i] = 0.0;
+        return;
+    }
+    // unbalance and take the first column: exp(tH)[i, 0] = sc[i] * X[i, 0] / sc[0]
     for (int i = tid; i < P.ldy; i += SE_NT) yout[i] = i < n ? Xc[i] * sc[i] / sc[0] : 0.0;
+}
+
+// Batched exponential!(A_b, ExpMethodHigham2005Base()) for many small matrices resident on the device
+// (SURVEY 8f-4): one CTA per matrix, in place.  A: [nbatch] matrices, n x n column-major with leading
+// dimension lda and `stride` doubles between matrices.
+__global__ void __launch_bounds__(SE_NT) small_exp_batched_kernel(int n, double *A, int lda, long long stride, int *err) {
+    extern __shared__ double sm[];
+    __shared__ double sc[SE_MAXM];
+    __shared__ double colsum[SE_MAXM];
+    const int tid = threadIdx.x;
+    double *Ab = A + (long long)blockIdx.x * stride;
+    const int nn = n * n;
+    for (int idx = tid; idx < nn; idx += SE_NT) sm[idx] = Ab[(long long)(idx / n) * lda + idx % n];
+    __syncthreads();
+    const double *Xc = se_expm_core(n, sm, sc, colsum, true);
+    if (!Xc) {
+        if (tid == 0) atomicExch(err, 1);
+        return;
+    }
+    for (int idx = tid; idx < nn; idx += SE_NT) {
+        const int i = idx % n, j = idx / n;
+        Ab[(long long)j * lda + i] = Xc[idx] * sc[i] / sc[j];
+    }
 }
 
 }  // namespace b200k

@@ -222,6 +222,10 @@ int b200k_op_csr_create_sharded(b200k_handle_t h, b200k_comm_t comm, int64_t nlo
 /* ---- small dense matrix functions (host, m <= ~130) ----------------------------------------- */
 /* exponential!(A, ExpMethodHigham2005Base()) in place (src/exp_baseexp.jl:112-161). */
 int b200k_exponential(int n, double *A, int lda);
+/* Batched exponential!(A_b, ExpMethodHigham2005Base()) of nbatch n x n matrices RESIDENT ON THE DEVICE, in place, one CTA
+ * per matrix (n <= 48).  A: device, matrix b at A + b*stride, column-major with leading dimension lda.
+ * Synchronous with respect to the status: returns B200K_ESINGULAR if any Pade denominator was singular. */
+int b200k_exponential_batched(b200k_handle_t h, int nbatch, int n, double *A, int lda, int64_t stride);
 /* The small dense phase of expv! on its own (src/krylov_phiv.jl:223-244): y = exp(t*H[1:m,1:m]) e1,
  * taking the SymTridiagonal eigen branch when H[1:m,1:m] is exactly symmetric, else the Pade branch.
  * branch (may be NULL) receives 1 for the symmetric branch, 0 for Pade. */

@@ -378,3 +378,30 @@ def test_edge_layouts_and_breakdown_in_stream_mode(gpu, oracle):
     A = convdiff2d(50, 40)
     b2 = rng.standard_normal(2000)
     assert relerr(gpu.expv(2.0, A, b2, m=100), oracle.expv(2.0, A, b2, m=100)) < 1e-9
+
+
+def test_batched_device_exponential(gpu, oracle):
+    """b200k_exponential_batched: many small matrices on the device, every Pade branch, against
+    the oracle's exponential! and scipy.linalg.expm (test/basictests.jl:952-974 style)."""
+    rng = np.random.default_rng(41)
+    mats = []
+    for scale in (3.0, 1.5, 0.5, 0.1, 0.005, 40.0, 0.0):
+        for n in (1, 2, 7, 34, 48):
+            A = rng.standard_normal((n, n))
+            nrm = np.linalg.norm(A, 1)
+            mats.append((n, A * (scale / nrm if nrm > 0 else 0.0)))
+    for n in (1, 2, 7, 34, 48):
+        batch = np.stack([A for (k, A) in mats if k == n])
+        E = gpu.exponential_batched_(batch)
+        for b in range(batch.shape[0]):
+            ref = oracle.exponential_higham2005base(batch[b])
+            assert relerr(E[b], ref) < 1e-11, (n, b)
+            assert relerr(E[b], sla.expm(batch[b])) < 1e-10, (n, b)
+    # badly scaled matrices exercise the balancing sweeps
+    A = rng.standard_normal((12, 12))
+    D = np.diag(2.0 ** rng.integers(-15, 15, 12))
+    Bs = np.stack([D @ A @ np.linalg.inv(D), A])
+    E = gpu.exponential_batched_(Bs)
+    assert relerr(E[0], oracle.exponential_higham2005base(Bs[0])) < 1e-9
+    with pytest.raises(gpu.UnsupportedError):
+        gpu.exponential_batched_(np.zeros((2, 49, 49)))
