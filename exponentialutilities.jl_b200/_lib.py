@@ -79,6 +79,19 @@ PROTOTYPES = {
                                      C.POINTER(KrylovOpts), C.c_void_p, C.c_int64, c_int_p, c_int_p]),
     "b200k_kiops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_double_p, C.c_int, C.c_void_p, C.c_int64,
                               C.c_int, C.POINTER(KiopsOpts), C.c_void_p, C.c_int64, c_int64_p]),
+    "b200k_op_csr_create_z": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200k_op_dense_create_z": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
+                                          C.POINTER(C.c_void_p)]),
+    "b200k_arnoldi_z": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(KrylovOpts), C.c_void_p,
+                                  C.c_int64, C.c_int, C.c_void_p, C.c_int, c_double_p, c_int_p, c_int_p]),
+    "b200k_expv_ks_z": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                  C.c_int, C.c_int, C.c_double, C.c_void_p]),
+    "b200k_expv_z": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.POINTER(KrylovOpts),
+                               C.c_void_p, c_int_p, c_int_p]),
+    "b200k_expv_small_z": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, c_int_p]),
+    "b200k_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_double, c_double_p, C.c_int,
+                                C.c_int, C.c_void_p, C.c_int64]),
     "b200k_timestep_opts_default": (None, [C.POINTER(TimestepOpts)]),
     "b200k_phiv_timestep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_double_p, C.c_void_p, C.c_int64, C.c_int,
                                       C.POINTER(TimestepOpts), C.c_void_p, C.c_int64, c_int_p]),

@@ -90,7 +90,7 @@ class Engine:
         """'ldg' (krylov_persistent_kernel) or 'tma' (krylov_tma_kernel) for the last factorisation."""
         w = C.c_int()
         self.check(self.lib.b200k_last_kernel(self.handle, C.byref(w)))
-        return {1: "ldg", 2: "tma"}.get(w.value, "none")
+        return {1: "ldg", 2: "tma", 3: "z"}.get(w.value, "none")
 
     def last_timing(self):
         a, b = C.c_float(), C.c_float()
@@ -116,21 +116,37 @@ def get_engine(device=None) -> Engine:
 # operators (docs/src/interfaces.md: size / eltype / mul! / ishermitian / opnorm)
 # ------------------------------------------------------------------------------------------
 class Operator:
-    def __init__(self, engine: Engine, ptr, keep):
+    def __init__(self, engine: Engine, ptr, keep, is_complex=False, src=None):
         self.engine = engine
         self.ptr = ptr
         self._keep = keep
+        self.is_complex = bool(is_complex)
+        self._src = src          # host matrix the operator was ingested from (needed to promote it to complex)
+        self._as_complex = None
         n, nnz, kind, herm, nrm = C.c_int64(), C.c_int64(), C.c_int(), C.c_int(), C.c_double()
         _lib.check(engine.lib.b200k_op_info(ptr, C.byref(n), C.byref(nnz), C.byref(kind), C.byref(herm),
                                             C.byref(nrm)))
         self.n, self.nnz, self.kind = n.value, nnz.value, kind.value
         self.ishermitian, self.opnorm_inf = bool(herm.value), nrm.value
         self.shape = (self.n, self.n)
-        self.dtype = np.float64
+        self.dtype = np.complex128 if self.is_complex else np.float64
         self._finalizer = weakref.finalize(self, engine.lib.b200k_op_destroy, ptr)
+
+    def as_complex(self):
+        """The same operator with ComplexF64 entries (promote_type(eltype(A), eltype(b)) when b is complex)."""
+        if self.is_complex:
+            return self
+        if self._as_complex is None:
+            if self._src is None:
+                raise _lib.UnsupportedError("cannot promote a device-ingested operator to complex: pass a complex matrix")
+            src = self._src
+            self._as_complex = operator(src.astype(np.complex128), self.engine)
+        return self._as_complex
 
     def mul(self, x):
         """mul!(y, A, x)"""
+        if self.is_complex:
+            raise _lib.UnsupportedError("mul! is not exposed for complex operators")
         xd, was_np = _to_device(x, self.engine)
         if xd.numel() != self.n:
             raise DimensionMismatch("length(x) != size(A, 2)")
@@ -163,10 +179,15 @@ def operator(A, engine: Engine | None = None) -> Operator:
             A.sum_duplicates()
         rp = np.ascontiguousarray(A.indptr, dtype=np.int32)
         ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+        if np.iscomplexobj(A.data):
+            va = np.ascontiguousarray(A.data, dtype=np.complex128)
+            eng.check(lib.b200k_op_csr_create_z(eng.handle, A.shape[0], va.size, rp.ctypes.data, ci.ctypes.data,
+                                                va.ctypes.data, 0, 1, C.byref(ptr)))
+            return Operator(eng, ptr, None, is_complex=True, src=A)
         va = np.ascontiguousarray(A.data, dtype=np.float64)
         eng.check(lib.b200k_op_csr_create(eng.handle, A.shape[0], va.size, rp.ctypes.data, ci.ctypes.data,
                                           va.ctypes.data, 0, 1, C.byref(ptr)))
-        return Operator(eng, ptr, None)
+        return Operator(eng, ptr, None, src=A)
     if isinstance(A, tuple) and len(A) == 3:
         rp, ci, va = A
         if torch is not None and isinstance(va, torch.Tensor):
@@ -184,6 +205,13 @@ def operator(A, engine: Engine | None = None) -> Operator:
         eng.check(lib.b200k_op_csr_create(eng.handle, rp.size - 1, va.size, rp.ctypes.data, ci.ctypes.data,
                                           va.ctypes.data, 0, 1, C.byref(ptr)))
         return Operator(eng, ptr, None)
+    if torch is not None and isinstance(A, torch.Tensor) and A.is_complex():
+        if A.dim() != 2 or A.shape[0] != A.shape[1]:
+            raise DimensionMismatch("operator must be square")
+        n = A.shape[0]
+        At = A.to(device=eng.device, dtype=torch.complex128).t().contiguous()  # row i = column i of A
+        eng.check(lib.b200k_op_dense_create_z(eng.handle, n, C.c_void_p(At.data_ptr()), n, 0, C.byref(ptr)))
+        return Operator(eng, ptr, At, is_complex=True)
     if torch is not None and isinstance(A, torch.Tensor):
         if A.dim() != 2 or A.shape[0] != A.shape[1]:
             raise DimensionMismatch("operator must be square")
@@ -193,22 +221,35 @@ def operator(A, engine: Engine | None = None) -> Operator:
         At[:, :n] = A.to(device=eng.device, dtype=torch.float64).t()
         eng.check(lib.b200k_op_dense_create(eng.handle, n, C.c_void_p(At.data_ptr()), ld, 0, C.byref(ptr)))
         return Operator(eng, ptr, At)
+    if np.iscomplexobj(A):
+        A = np.asarray(A, dtype=np.complex128)
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise DimensionMismatch("operator must be square")
+        Af = np.asfortranarray(A)
+        eng.check(lib.b200k_op_dense_create_z(eng.handle, A.shape[0], Af.ctypes.data, A.shape[0], 1, C.byref(ptr)))
+        return Operator(eng, ptr, None, is_complex=True, src=A)
     A = np.asarray(A, dtype=np.float64)
     if A.ndim != 2 or A.shape[0] != A.shape[1]:
         raise DimensionMismatch("operator must be square")
     Af = np.asfortranarray(A)
     eng.check(lib.b200k_op_dense_create(eng.handle, A.shape[0], Af.ctypes.data, A.shape[0], 1, C.byref(ptr)))
-    return Operator(eng, ptr, None)
+    return Operator(eng, ptr, None, src=A)
+
+
+def _is_complex_value(x):
+    if torch is not None and isinstance(x, torch.Tensor):
+        return x.is_complex()
+    return np.iscomplexobj(x)
 
 
 def _to_device(x, eng: Engine):
     if torch is not None and isinstance(x, torch.Tensor):
-        if x.dtype != torch.float64:
-            raise ArgumentError("only Float64 vectors are supported")
+        if x.dtype not in (torch.float64, torch.complex128):
+            raise ArgumentError("only Float64 / ComplexF64 vectors are supported")
         if not x.is_cuda:
             return x.to(eng.device).contiguous(), False
         return x.contiguous(), False
-    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.complex128 if np.iscomplexobj(x) else np.float64))
     return torch.from_numpy(a).to(eng.device), True
 
 
@@ -226,7 +267,7 @@ class KrylovSubspace:
     (one basis vector per row, ldv padded to a multiple of 16) and exposed transposed through ``.V``.
     """
 
-    def __init__(self, n, maxiter=30, augmented=0, engine: Engine | None = None):
+    def __init__(self, n, maxiter=30, augmented=0, engine: Engine | None = None, dtype=np.float64):
         self.engine = engine or get_engine()
         self.n = int(n)
         self.m = int(maxiter)
@@ -234,10 +275,15 @@ class KrylovSubspace:
         self.augmented = int(augmented)
         self.beta = 0.0
         self.wasbreakdown = False
+        self.is_complex = np.dtype(dtype) == np.complex128
+        if self.is_complex and self.augmented:
+            raise _lib.UnsupportedError("augmented Krylov subspaces are real only")
         self.nrows = self.n + self.augmented
         self.ldv = _round_up(self.nrows, 16)
-        self.Vt = torch.zeros((self.maxiter + 1, self.ldv), dtype=torch.float64, device=self.engine.device)
-        self.H = np.zeros((self.maxiter + 1, self.maxiter + (1 if self.augmented else 0)), order="F")
+        self._tdtype = torch.complex128 if self.is_complex else torch.float64
+        self.Vt = torch.zeros((self.maxiter + 1, self.ldv), dtype=self._tdtype, device=self.engine.device)
+        self.H = np.zeros((self.maxiter + 1, self.maxiter + (1 if self.augmented else 0)), order="F",
+                          dtype=np.complex128 if self.is_complex else np.float64)
 
     @property
     def V(self):
@@ -252,8 +298,8 @@ class KrylovSubspace:
     def resize(self, maxiter):
         """Base.resize! (src/arnoldi.jl:80-93): contents are preserved only for augmented subspaces."""
         isaug = self.augmented != 0
-        Vt = torch.zeros((maxiter + 1, self.ldv), dtype=torch.float64, device=self.engine.device)
-        H = np.zeros((maxiter + 1, maxiter + (1 if isaug else 0)), order="F")
+        Vt = torch.zeros((maxiter + 1, self.ldv), dtype=self._tdtype, device=self.engine.device)
+        H = np.zeros((maxiter + 1, maxiter + (1 if isaug else 0)), order="F", dtype=self.H.dtype)
         if isaug:
             Vt[: self.Vt.shape[0]] = self.Vt
             H[: self.H.shape[0], : self.H.shape[1]] = self.H
@@ -276,6 +322,10 @@ def arnoldi_(Ks: KrylovSubspace, A, b, *, tol=1.0e-7, m=None, ishermitian=None, 
     (``w`` is n x numSteps, ``l`` the 1-based column)."""
     eng = Ks.engine
     op, B = _resolve_op(A, eng)
+    if Ks.is_complex:
+        return _arnoldi_z(Ks, op, b, tol=tol, m=m, ishermitian=ishermitian, iop=iop, init=init)
+    if op.is_complex or (not isinstance(b, tuple) and _is_complex_value(b)):
+        raise ArgumentError("complex operator or vector needs a complex KrylovSubspace (dtype=np.complex128)")
     if m is None:
         m = min(Ks.maxiter, op.n)
     herm = op.ishermitian if ishermitian is None else bool(ishermitian)
@@ -328,6 +378,36 @@ def arnoldi_(Ks: KrylovSubspace, A, b, *, tol=1.0e-7, m=None, ishermitian=None, 
     return Ks
 
 
+def _arnoldi_z(Ks, op, b, *, tol, m, ishermitian, iop, init):
+    """arnoldi!/lanczos! on a ComplexF64 basis (b200k_arnoldi_z)."""
+    eng = Ks.engine
+    op = op.as_complex()
+    if m is None:
+        m = min(Ks.maxiter, op.n)
+    herm = op.ishermitian if ishermitian is None else bool(ishermitian)
+    Ks.wasbreakdown = False
+    if m > Ks.maxiter:
+        Ks.resize(m)
+    else:
+        Ks.m = m
+    bd, _ = _to_device(b, eng)
+    bd = bd.reshape(-1).to(torch.complex128).contiguous()
+    if not (bd.numel() == op.n == Ks.nrows):
+        raise DimensionMismatch(f"length(b) [{bd.numel()}] == size(A,1) [{op.n}] == size(V,1) [{Ks.nrows}] doesn't hold")
+    opts = KrylovOpts()
+    eng.lib.b200k_krylov_opts_default(C.byref(opts))
+    opts.m, opts.tol, opts.iop, opts.hermitian, opts.init = int(m), float(tol), int(iop), int(herm), int(init)
+    beta = C.c_double(Ks.beta)
+    m_out, brk = C.c_int(), C.c_int()
+    eng.bind_stream()
+    st = eng.lib.b200k_arnoldi_z(eng.handle, op.ptr, C.c_void_p(bd.data_ptr()), C.byref(opts),
+                                 C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.maxiter, C.c_void_p(Ks.H.ctypes.data),
+                                 Ks.H.shape[0], C.byref(beta), C.byref(m_out), C.byref(brk))
+    eng.check(st)
+    Ks.beta, Ks.m, Ks.wasbreakdown = beta.value, m_out.value, bool(brk.value)
+    return Ks
+
+
 def lanczos_(Ks: KrylovSubspace, A, b, **kw):
     """lanczos!(Ks, A, b; tol, m, init, t, mu, l) -- src/arnoldi.jl:456-490."""
     kw.pop("ishermitian", None)
@@ -340,7 +420,8 @@ def arnoldi(A, b, *, m=None, ishermitian=None, **kw):
     n = int(np.prod(b.shape))
     if m is None:
         m = min(30, op.n)
-    Ks = KrylovSubspace(n, m, 0, engine=op.engine)
+    cplx = op.is_complex or _is_complex_value(b)  # T = promote_type(eltype(A), eltype(b))
+    Ks = KrylovSubspace(n, m, 0, engine=op.engine, dtype=np.complex128 if cplx else np.float64)
     return arnoldi_(Ks, op, b, m=m, ishermitian=ishermitian, **kw)
 
 
@@ -350,10 +431,37 @@ def arnoldi(A, b, *, m=None, ishermitian=None, **kw):
 def expv_(w, t, Ks: KrylovSubspace, *, cache=None):
     """expv!(w, t, Ks) -- src/krylov_phiv.jl:200-247.  ``w``: float64 CUDA tensor of length size(V,1)."""
     eng = Ks.engine
-    if not isinstance(t, (int, float, np.floating, np.integer)):
-        raise _lib.UnsupportedError("complex t is not supported by the B200 engine yet")
+    t_c = isinstance(t, (complex, np.complexfloating))
     if w.numel() != Ks.nrows:
         raise DimensionMismatch("Dimension mismatch")
+    if Ks.is_complex:  # expv!(w::Complex, t, Ks{Complex}) -- krylov_phiv.jl:200-280
+        if not w.is_complex():
+            raise ArgumentError("a complex Krylov subspace needs a complex output vector")
+        eng.bind_stream()
+        st = eng.lib.b200k_expv_ks_z(eng.handle, float(np.real(t)), float(np.imag(t)), C.c_void_p(Ks.Vt.data_ptr()),
+                                     Ks.ldv, Ks.nrows, C.c_void_p(Ks.H.ctypes.data), Ks.H.shape[0], Ks.m, Ks.beta,
+                                     C.c_void_p(w.data_ptr()))
+        eng.check(st)
+        return w
+    if t_c:  # real subspace, complex t: y is complex, w = beta V (re y) + i beta V (im y)
+        if not w.is_complex():
+            raise ArgumentError("complex t needs a complex output vector")
+        m = Ks.m
+        if Ks.beta == 0.0:
+            w.zero_()
+            return w
+        Hc = np.array(Ks.H[:m, :m], dtype=np.complex128, order="F")
+        y = np.zeros(m, dtype=np.complex128)
+        _lib.check(eng.lib.b200k_expv_small_z(m, C.c_void_p(Hc.ctypes.data), m, float(np.real(t)), float(np.imag(t)),
+                                              C.c_void_p(y.ctypes.data), None))
+        Y = np.asfortranarray(np.stack([y.real, y.imag], 1))
+        ld = _round_up(Ks.nrows, 2)
+        Wt = torch.empty((2, ld), dtype=torch.float64, device=eng.device)
+        eng.bind_stream()
+        eng.check(eng.lib.b200k_project(eng.handle, C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.nrows, m, Ks.beta,
+                                        Y.ctypes.data_as(_lib.c_double_p), m, 2, C.c_void_p(Wt.data_ptr()), ld))
+        w.copy_(torch.complex(Wt[0, : Ks.nrows], Wt[1, : Ks.nrows]))
+        return w
     eng.bind_stream()
     st = eng.lib.b200k_expv_ks(eng.handle, float(t), C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.nrows,
                                Ks.H.ctypes.data_as(_lib.c_double_p), Ks.H.shape[0], Ks.m, Ks.beta,
@@ -365,9 +473,11 @@ def expv_(w, t, Ks: KrylovSubspace, *, cache=None):
 def expv(t, A, b=None, *, mode="happy_breakdown", m=None, tol=1.0e-7, ishermitian=None, iop=0, opnorm=None,
          cache=None, expmethod=None, rtol=None, return_m=False):
     """expv(t, A, b; m, tol, ishermitian, iop, ...) or expv(t, Ks) -- src/krylov_phiv.jl:125-168."""
+    t_c = isinstance(t, (complex, np.complexfloating))
     if isinstance(A, KrylovSubspace):
         Ks = A
-        w = torch.empty(Ks.nrows, dtype=torch.float64, device=Ks.engine.device)
+        wdt = torch.complex128 if (Ks.is_complex or t_c) else torch.float64
+        w = torch.empty(Ks.nrows, dtype=wdt, device=Ks.engine.device)
         return expv_(w, t, Ks)
     if mode not in ("happy_breakdown", "error_estimate"):
         raise ArgumentError(f"Unknown Krylov iteration termination mode, {mode}")
@@ -379,6 +489,24 @@ def expv(t, A, b=None, *, mode="happy_breakdown", m=None, tol=1.0e-7, ishermitia
         raise DimensionMismatch("length(b) != size(A, 1)")
     if m is None:
         m = min(30, op.n)
+    if op.is_complex or bd.is_complex():  # ComplexF64 basis
+        if mode == "error_estimate":
+            raise _lib.UnsupportedError("mode=:error_estimate is real-only in the B200 engine")
+        opz = op.as_complex()
+        bz = bd.to(torch.complex128).contiguous()
+        opts = KrylovOpts()
+        eng.lib.b200k_krylov_opts_default(C.byref(opts))
+        opts.m, opts.tol, opts.iop = int(m), float(tol), int(iop)
+        opts.hermitian = -1 if ishermitian is None else int(bool(ishermitian))
+        w = torch.empty_like(bz)
+        eng.bind_stream()
+        eng.check(eng.lib.b200k_expv_z(eng.handle, opz.ptr, float(np.real(t)), float(np.imag(t)),
+                                       C.c_void_p(bz.data_ptr()), C.byref(opts), C.c_void_p(w.data_ptr()), None, None))
+        return _from_device(w, was_np)
+    if t_c:  # real operator and vector, complex t: real Krylov subspace, complex projection coefficients
+        Ks = arnoldi(op, bd, m=m, tol=tol, ishermitian=ishermitian, iop=iop)
+        w = torch.empty(Ks.nrows, dtype=torch.complex128, device=eng.device)
+        return _from_device(expv_(w, t, Ks), was_np)
     if mode == "error_estimate":  # _expv_ee (src/krylov_phiv.jl:145-160): atol = tol, rtol = sqrt(tol)
         herm = op.ishermitian if ishermitian is None else bool(ishermitian)
         if not herm:

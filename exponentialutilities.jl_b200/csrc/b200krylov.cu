@@ -17,6 +17,7 @@
 #include "aux_kernels.cuh"
 #include "krylov_kernel.cuh"
 #include "krylov_kernel_tma.cuh"
+#include "krylov_kernel_z.cuh"
 #include "smallexp_kernel.cuh"
 #include "smallmat.hpp"
 
@@ -100,6 +101,8 @@ struct b200k_context {
     // internal Krylov storage for the one-shot calls
     DevBuf V, bdev, wdev;
     DevBuf tsV, tsW, tsP, tsu;  // phiv_timestep workspace (basis, W, P, u)
+    DevBuf zV, zH, zpart, zxbuf, zw, zy;  // complex path: internal basis, device H, partial sums, gather buffers
+    HostBuf zHh;
     DevBuf kV, kB;  // kiops basis / flipped-u storage, kept across calls (cudaMalloc/cudaFree cost milliseconds)
     std::vector<double> H;
     smallmat::ExpWork expwork;
@@ -140,6 +143,7 @@ struct b200k_operator {
     b200k_context *ctx = nullptr;  // creating handle (NOT dereferenced on destroy: it may already be gone)
     int device = 0;
     int kind = 0;  // 0 CSR, 1 dense
+    int is_complex = 0;  // ComplexF64 entries: val / Ad hold interleaved (re, im) pairs
     long long n = 0, nnz = 0;
     DevBuf rowptr, colind, val;  // owned, 0-based, padded
     const double *Ad = nullptr;  // dense: alias (device input) or owned copy
@@ -544,6 +548,7 @@ void make_btail(int p, double t, double mu, double *out) {
 // Core of arnoldi!/lanczos! shared by b200k_arnoldi, the one-shots and kiops.
 int arnoldi_core(b200k_context *h, b200k_operator *op, const double *b, const b200k_krylov_opts *o, double *V,
                  long long ldv, int maxiter, double *H, int ldh, double *beta, int *m_out, int *breakdown) {
+    if (op->is_complex) return fail(h, B200K_EARG, "complex operator: use the b200k_*_z entry points");
     const long long n = op->n;
     const int p = o->p;
     const int m = o->m;
@@ -837,6 +842,7 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
             h->encode_tiled = fn;
     }
     if (const char *env = std::getenv("B200K_SMALLEXP")) h->host_smallexp = std::strcmp(env, "host") == 0 ? 1 : 0;
+    cudaFuncSetAttribute((const void *)krylov_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     cudaFuncSetAttribute((const void *)small_exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          6 * SE_MAXM * SE_MAXM * 8);
     cudaFuncSetAttribute((const void *)small_exp_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -852,10 +858,10 @@ int b200k_destroy(b200k_handle_t h) {
     if (!h) return B200K_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->tsV, &h->tsW, &h->tsP, &h->tsu, &h->tdev, &h->errdev, &h->kV, &h->kB, &h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
+    DevBuf *bufs[] = {&h->zV, &h->zH, &h->zpart, &h->zxbuf, &h->zw, &h->zy, &h->tsV, &h->tsW, &h->tsP, &h->tsu, &h->tdev, &h->errdev, &h->kV, &h->kB, &h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
                       &h->Y, &h->corr, &h->mvec, &h->betavec, &h->tmp, &h->V, &h->bdev, &h->wdev};
     for (DevBuf *b : bufs) b->release();
-    HostBuf *hb[] = {&h->errh, &h->Hh, &h->scalh, &h->stath, &h->Yh};
+    HostBuf *hb[] = {&h->zHh, &h->errh, &h->Hh, &h->scalh, &h->stath, &h->Yh};
     for (HostBuf *b : hb) b->release();
     for (int i = 0; i < 4; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -1678,6 +1684,326 @@ int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out
         stats[4] = m;
     }
     return B200K_OK;
+}
+
+// ---- ComplexF64 path ----------------------------------------------------------------------------
+namespace {
+typedef smallmat::cplx cplx;
+
+// y = exp(t H[0:m,0:m]) e1 for complex H and/or complex t; 0 ok, 1 eigensolver failure, 2 singular.
+int expv_small_z_ws(cplx t, const cplx *H, int ldh, int m, cplx *y, int *branch) {
+    // ishermitian(Hcopy) of a real-U (Lanczos) subspace: exactly real symmetric -> eigen!(SymTridiagonal(real(H)))
+    bool realsym = true;
+    for (int j = 0; j < m && realsym; ++j)
+        for (int i = 0; i < m; ++i) {
+            const cplx a = H[(size_t)j * ldh + i], bb = H[(size_t)i * ldh + j];
+            if (a.imag() != 0.0 || a.real() != bb.real()) { realsym = false; break; }
+        }
+    if (branch) *branch = realsym ? 1 : 0;
+    if (realsym) {
+        std::vector<double> d(m), e(std::max(m - 1, 0)), Z;
+        for (int i = 0; i < m; ++i) d[i] = H[(size_t)i * ldh + i].real();
+        for (int i = 0; i + 1 < m; ++i) e[i] = H[(size_t)i * ldh + i + 1].real();
+        if (!smallmat::symtridiag_eig(m, d, e, Z)) return 1;
+        for (int i = 0; i < m; ++i) y[i] = cplx(0.0, 0.0);
+        for (int k = 0; k < m; ++k) {
+            const cplx wk = std::exp(t * d[k]) * Z[(size_t)k * m + 0];
+            for (int i = 0; i < m; ++i) y[i] += Z[(size_t)k * m + i] * wk;
+        }
+        return 0;
+    }
+    std::vector<cplx> Hc((size_t)m * m);
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) Hc[(size_t)j * m + i] = t * H[(size_t)j * ldh + i];
+    smallmat::ExpWorkT<cplx> work;
+    if (smallmat::expm_higham2005base(m, Hc.data(), work)) return 2;
+    for (int i = 0; i < m; ++i) y[i] = Hc[i];
+    return 0;
+}
+
+int arnoldi_z_core(b200k_context *h, b200k_operator *op, const double *b, const b200k_krylov_opts *o, double *V,
+                   long long ldv, int maxiter, cplx *H, int ldh, double *beta, int *m_out, int *breakdown) {
+    if (!op->is_complex) return fail(h, B200K_EARG, "real operator: use the real entry points");
+    const long long n = op->n;
+    const int m = o->m;
+    if (m < 1) return fail(h, B200K_EARG, "m must be >= 1");
+    if (m > maxiter) return fail(h, B200K_EDIM, "m exceeds Ks.maxiter: resize the KrylovSubspace first");
+    if (m >= MAXCOL) return fail(h, B200K_EUNSUPPORTED, "Krylov dimension m must be < 256");
+    if (o->p != 0) return fail(h, B200K_EUNSUPPORTED, "the augmented operator is not available for complex types");
+    if (ldv < n) return fail(h, B200K_EDIM, "DimensionMismatch: size(V,1) != size(A,1)");
+    if (ldh < m + 1) return fail(h, B200K_EDIM, "H has fewer than m+1 rows");
+    if (o->init < 0 || o->init > m) return fail(h, B200K_EARG, "init must be in 0..m");
+    int herm = o->hermitian;
+    if (herm < 0) herm = op->is_herm;
+    *breakdown = 0;
+    *m_out = m;
+    if (o->init == 0) {
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < m + 1; ++i) H[(size_t)j * ldh + i] = cplx(0.0, 0.0);
+    } else if (*beta == 0.0) {
+        return B200K_OK;
+    }
+    Geom g = single_geom(h, n);
+    KrylovParamsZ P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = (int)n;
+    if (op->kind == 0) {
+        P.op_kind = OP_CSR_WARP;
+        P.rowptr = op->rowptr.as<int>();
+        P.colind = op->colind.as<int>();
+        P.val = op->val.as<double2>();
+        P.lanes_per_row = op->max_row_nnz <= 8 ? 4 : 32;
+    } else {
+        P.op_kind = OP_DENSE;
+        P.Ad = reinterpret_cast<const double2 *>(op->Ad);
+        P.lda = op->lda;
+    }
+    P.team_size = g.C;
+    P.slice = g.slice;
+    P.b = reinterpret_cast<const double2 *>(b);
+    P.V = reinterpret_cast<double2 *>(V);
+    P.ldv = ldv;
+    P.m = m;
+    P.lanczos = herm ? 1 : 0;
+    P.j0 = herm ? (o->init == 0 ? 0 : 1) : o->init;
+    P.iop = o->iop;
+    P.tol = o->tol;
+    const int ldhd = m + 1;
+    P.ldh = ldhd;
+    P.xlen = round_up(n, 16);
+    size_t smem = sizeof(SmemZ) + (size_t)g.slice * 16;
+    P.w_in_smem = smem <= SMEM_LIMIT ? 1 : 0;
+    if (!P.w_in_smem) smem = sizeof(SmemZ);
+    CK(h, h->zxbuf.ensure((size_t)2 * P.xlen * 16));
+    CK(h, h->zpart.ensure((size_t)2 * MAXCOL * CPAD * 16));
+    CK(h, h->partn.ensure((size_t)4 * CPAD * 8));
+    CK(h, h->bar.ensure(64));
+    CK(h, h->zH.ensure((size_t)ldhd * (m + 1) * 16));
+    CK(h, h->scal.ensure(64));
+    CK(h, h->stat.ensure(64));
+    if (!P.w_in_smem) CK(h, h->zw.ensure((size_t)n * 16));
+    P.xbuf = h->zxbuf.as<double2>();
+    P.part = h->zpart.as<double2>();
+    P.partn = h->partn.as<double>();
+    P.bar = h->bar.as<unsigned>();
+    P.Hd = h->zH.as<double2>();
+    P.scal = h->scal.as<double>();
+    P.stat = h->stat.as<int>();
+    P.wglob = h->zw.as<double2>();
+    CK(h, cudaMemsetAsync(P.bar, 0, 4, h->stream));
+    CK(h, cudaMemsetAsync(P.Hd, 0, (size_t)ldhd * (m + 1) * 16, h->stream));
+    CK(h, cudaMemsetAsync(P.scal, 0, 32, h->stream));
+    if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
+    void *args[] = {(void *)&P};
+    CK(h, cudaLaunchCooperativeKernel((const void *)krylov_z_kernel, dim3(g.C), dim3(NT), args, smem, h->stream));
+    if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
+    h->launches += 1;
+    h->last_kernel = 3;
+    const size_t hbytes = (size_t)ldhd * (m + 1) * 16;
+    CK(h, h->zHh.ensure(hbytes + 64));
+    CK(h, h->scalh.ensure(64));
+    CK(h, h->stath.ensure(64));
+    CK(h, cudaMemcpyAsync(h->zHh.p, h->zH.p, hbytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(h->scalh.p, h->scal.p, 32, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(h->stath.p, h->stat.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (o->init == 0) *beta = h->scalh.as<double>()[0];
+    if (*beta == 0.0) return B200K_OK;
+    *m_out = h->stath.as<int>()[0];
+    *breakdown = h->stath.as<int>()[1];
+    const cplx *Hh = h->zHh.as<cplx>();
+    const int jc0 = P.j0 == 0 ? 0 : P.j0 - 1;
+    for (int jc = jc0; jc < *m_out; ++jc)
+        for (int i = 0; i <= jc + 1; ++i) H[(size_t)jc * ldh + i] = Hh[(size_t)jc * ldhd + i];
+    if (herm)
+        for (int i = 0; i + 1 < m; ++i) H[(size_t)(i + 1) * ldh + i] = H[(size_t)i * ldh + i + 1];
+    return B200K_OK;
+}
+
+int expv_ks_z_core(b200k_context *h, cplx t, const double *V, long long ldv, long long nrows, const cplx *H, int ldh,
+                   int m, double beta, double *w) {
+    if (m < 1) return fail(h, B200K_EARG, "m must be >= 1");
+    if (m > MAXCOL) return fail(h, B200K_EUNSUPPORTED, "m must be <= 256");
+    if (ldv < nrows) return fail(h, B200K_EDIM, "Dimension mismatch");
+    if (beta == 0.0) {
+        CK(h, cudaMemsetAsync(w, 0, (size_t)nrows * 16, h->stream));
+        return B200K_OK;
+    }
+    std::vector<cplx> y(m);
+    const int st = expv_small_z_ws(t, H, ldh, m, y.data(), nullptr);
+    if (st == 1) return fail(h, B200K_ESINGULAR, "symmetric tridiagonal eigensolver did not converge");
+    if (st == 2) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
+    CK(h, h->zy.ensure((size_t)m * 16));
+    CK(h, cudaMemcpyAsync(h->zy.p, y.data(), (size_t)m * 16, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));  // y is a stack vector
+    const int blocks = (int)std::min<long long>((nrows + 255) / 256, (long long)h->sm_count * 8);
+    project_z_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const double2 *>(V), ldv, nrows, m, beta,
+                                                     h->zy.as<double2>(), reinterpret_cast<double2 *>(w));
+    CK(h, cudaGetLastError());
+    h->launches += 1;
+    return B200K_OK;
+}
+
+int op_create_z_finish(b200k_context *h, b200k_operator *op) {
+    cudaError_t e = h->tmp.ensure(64);
+    if (e != cudaSuccess) return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+    cudaMemsetAsync(h->tmp.p, 0, 64, h->stream);
+    int *d_max = h->tmp.as<int>();
+    int *d_non = d_max + 1;
+    double *d_norm = reinterpret_cast<double *>(h->tmp.as<char>() + 16);
+    if (op->kind == 0) {
+        const int blocks = (int)std::min<long long>((op->n + 255) / 256, 4096);
+        csr_analyze_z_kernel<<<blocks, 256, 0, h->stream>>>((int)op->n, op->rowptr.as<int>(), op->colind.as<int>(),
+                                                            op->val.as<double2>(), d_max, d_non, d_norm);
+    } else {
+        dense_analyze_z_kernel<<<(int)std::min<long long>((op->n + 127) / 128, 2048), 128, 0, h->stream>>>(
+            (int)op->n, reinterpret_cast<const double2 *>(op->Ad), op->lda, d_non, d_norm);
+    }
+    char raw[32];
+    e = cudaMemcpyAsync(raw, h->tmp.p, 32, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, B200K_ECUDA, cudaGetErrorString(e));
+    int mx, non;
+    double nrm;
+    std::memcpy(&mx, raw, 4);
+    std::memcpy(&non, raw + 4, 4);
+    std::memcpy(&nrm, raw + 16, 8);
+    op->max_row_nnz = mx;
+    op->is_herm = non ? 0 : 1;
+    op->opnorm_inf = nrm;
+    h->launches += 1;
+    return B200K_OK;
+}
+}  // namespace
+
+int b200k_op_csr_create_z(b200k_handle_t h, int64_t n, int64_t nnz, const int32_t *rowptr, const int32_t *colind,
+                          const double *val, int index_base, int location, b200k_op_t *out) {
+    if (!h || !out) return B200K_EARG;
+    *out = nullptr;
+    if (n < 1 || nnz < 0 || !rowptr || (nnz > 0 && (!colind || !val))) return fail(h, B200K_EARG, "invalid CSR description");
+    if (n > 2000000000LL || nnz > 2000000000LL) return fail(h, B200K_EUNSUPPORTED, "int32 CSR indices only");
+    if (index_base != 0 && index_base != 1) return fail(h, B200K_EARG, "index_base must be 0 or 1");
+    CK(h, cudaSetDevice(h->device));
+    b200k_operator *op = new b200k_operator();
+    op->ctx = h;
+    op->device = h->device;
+    op->kind = 0;
+    op->is_complex = 1;
+    op->n = n;
+    op->nnz = nnz;
+    const size_t pad = 64;
+    cudaError_t e = op->rowptr.ensure((size_t)(n + 1 + pad) * 4);
+    if (e == cudaSuccess) e = op->colind.ensure((size_t)(nnz + pad) * 4);
+    if (e == cudaSuccess) e = op->val.ensure((size_t)(nnz + pad) * 16);
+    if (e != cudaSuccess) {
+        b200k_op_destroy(op);
+        return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+    }
+    const cudaMemcpyKind kind = location == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    cudaMemsetAsync(op->colind.p, 0, op->colind.cap, h->stream);
+    cudaMemsetAsync(op->val.p, 0, op->val.cap, h->stream);
+    cudaMemcpyAsync(op->rowptr.p, rowptr, (size_t)(n + 1) * 4, kind, h->stream);
+    if (nnz > 0) {
+        cudaMemcpyAsync(op->colind.p, colind, (size_t)nnz * 4, kind, h->stream);
+        cudaMemcpyAsync(op->val.p, val, (size_t)nnz * 16, kind, h->stream);
+    }
+    if (index_base == 1) {
+        rebase_kernel<<<256, 256, 0, h->stream>>>(op->rowptr.as<int>(), op->rowptr.as<int>(), n + 1, 1);
+        if (nnz > 0) rebase_kernel<<<1024, 256, 0, h->stream>>>(op->colind.as<int>(), op->colind.as<int>(), nnz, 1);
+    }
+    const int st = op_create_z_finish(h, op);
+    if (st) {
+        b200k_op_destroy(op);
+        return st;
+    }
+    *out = op;
+    return B200K_OK;
+}
+
+int b200k_op_dense_create_z(b200k_handle_t h, int64_t n, const double *A, int64_t lda, int location, b200k_op_t *out) {
+    if (!h || !out) return B200K_EARG;
+    *out = nullptr;
+    if (n < 1 || !A || lda < n) return fail(h, B200K_EARG, "invalid dense description");
+    CK(h, cudaSetDevice(h->device));
+    b200k_operator *op = new b200k_operator();
+    op->ctx = h;
+    op->device = h->device;
+    op->kind = 1;
+    op->is_complex = 1;
+    op->n = n;
+    op->nnz = n * n;
+    if (location == 1) {
+        cudaError_t e = op->Aown.ensure((size_t)n * n * 16);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(op->Aown.p, (size_t)n * 16, A, (size_t)lda * 16, (size_t)n * 16, (size_t)n,
+                                  cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) {
+            b200k_op_destroy(op);
+            return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+        }
+        op->Ad = op->Aown.as<double>();
+        op->lda = n;
+    } else {
+        op->Ad = A;
+        op->lda = lda;
+    }
+    const int st = op_create_z_finish(h, op);
+    if (st) {
+        b200k_op_destroy(op);
+        return st;
+    }
+    *out = op;
+    return B200K_OK;
+}
+
+int b200k_arnoldi_z(b200k_handle_t h, b200k_op_t op, const double *b, const b200k_krylov_opts *opts, double *V,
+                    int64_t ldv, int maxiter, double *H, int ldh, double *beta, int *m_out, int *breakdown) {
+    if (!h || !op || !b || !opts || !V || !H || !beta || !m_out || !breakdown) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    return arnoldi_z_core(h, op, b, opts, V, ldv, maxiter, reinterpret_cast<cplx *>(H), ldh, beta, m_out, breakdown);
+}
+
+int b200k_expv_ks_z(b200k_handle_t h, double t_re, double t_im, const double *V, int64_t ldv, int64_t nrows,
+                    const double *H, int ldh, int m, double beta, double *w) {
+    if (!h || !V || !H || !w) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    return expv_ks_z_core(h, cplx(t_re, t_im), V, ldv, nrows, reinterpret_cast<const cplx *>(H), ldh, m, beta, w);
+}
+
+int b200k_expv_z(b200k_handle_t h, b200k_op_t op, double t_re, double t_im, const double *b,
+                 const b200k_krylov_opts *opts, double *w, int *m_out, int *breakdown) {
+    if (!h || !op || !b || !opts || !w) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    if (opts->p != 0 || opts->init != 0) return fail(h, B200K_EARG, "one-shot expv takes a plain operator, init = 0");
+    b200k_krylov_opts o = *opts;
+    o.m = (int)std::min<long long>(o.m, op->n);
+    const long long ldv = round_up(op->n, 8);
+    CK(h, h->zV.ensure((size_t)ldv * (o.m + 1) * 16));
+    const int ldh = o.m + 2;
+    std::vector<cplx> H((size_t)ldh * (o.m + 1), cplx(0.0, 0.0));
+    double beta = 0.0;
+    int mo = 0, bd = 0;
+    int st = arnoldi_z_core(h, op, b, &o, h->zV.as<double>(), ldv, o.m, H.data(), ldh, &beta, &mo, &bd);
+    if (st) return st;
+    if (m_out) *m_out = mo;
+    if (breakdown) *breakdown = bd;
+    return expv_ks_z_core(h, cplx(t_re, t_im), h->zV.as<double>(), ldv, op->n, H.data(), ldh, mo, beta, w);
+}
+
+int b200k_expv_small_z(int m, const double *H, int ldh, double t_re, double t_im, double *y, int *branch) {
+    if (m < 1 || !H || !y || ldh < m) return B200K_EARG;
+    const int st = expv_small_z_ws(cplx(t_re, t_im), reinterpret_cast<const cplx *>(H), ldh, m,
+                                   reinterpret_cast<cplx *>(y), branch);
+    return st ? B200K_ESINGULAR : B200K_OK;
+}
+
+int b200k_project(b200k_handle_t h, const double *V, int64_t ldv, int64_t nrows, int m, double beta, const double *Y,
+                  int ldy, int nc, double *W, int64_t ldw) {
+    if (!h || !V || !Y || !W || m < 1 || nc < 1 || ldy < m) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    if (ldv < nrows || ldw < nrows) return fail(h, B200K_EDIM, "Dimension mismatch");
+    return launch_project(h, V, ldv, nrows, m, beta, Y, ldy, nc, W, ldw, nullptr);
 }
 
 // ---- phiv_timestep! (src/krylov_phiv_adaptive.jl:260-501) --------------------------------------------------

@@ -16,6 +16,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -36,25 +37,35 @@ struct Mat {  // owning column-major square/rectangular matrix
     const double *col(int j) const { return a.data() + (size_t)j * r; }
 };
 
+// The functions below are templates on the scalar S = double or std::complex<double> (the reference's
+// exponential! covers all BlasFloat types; the complex instance serves the ComplexF64 Krylov path).
+typedef std::complex<double> cplx;
+inline double absval(double x) { return std::fabs(x); }
+inline double absval(const cplx &x) { return std::abs(x); }
+inline double abs2(double x) { return x * x; }
+inline double abs2(const cplx &x) { return std::norm(x); }
+
 // C = A * B, all n x n.  j-k-i loop order: unit stride on the inner loop (column-major).
-inline void matmul(int n, const double *A, const double *B, double *C) {
-    std::fill(C, C + (size_t)n * n, 0.0);
+template <typename S>
+inline void matmul(int n, const S *A, const S *B, S *C) {
+    std::fill(C, C + (size_t)n * n, S(0.0));
     for (int j = 0; j < n; ++j) {
-        double *cj = C + (size_t)j * n;
+        S *cj = C + (size_t)j * n;
         for (int k = 0; k < n; ++k) {
-            const double bkj = B[(size_t)j * n + k];
-            if (bkj == 0.0) continue;
-            const double *ak = A + (size_t)k * n;
+            const S bkj = B[(size_t)j * n + k];
+            if (bkj == S(0.0)) continue;
+            const S *ak = A + (size_t)k * n;
             for (int i = 0; i < n; ++i) cj[i] += ak[i] * bkj;
         }
     }
 }
 
-inline double norm1(int n, const double *A) {
+template <typename S>
+inline double norm1(int n, const S *A) {
     double best = 0.0;
     for (int j = 0; j < n; ++j) {
         double s = 0.0;
-        for (int i = 0; i < n; ++i) s += std::fabs(A[(size_t)j * n + i]);
+        for (int i = 0; i < n; ++i) s += absval(A[(size_t)j * n + i]);
         if (s > best || s != s) best = s;
     }
     return best;
@@ -66,14 +77,16 @@ struct Balance {
     std::vector<double> scale;   // permutation targets outside [ilo, ihi], scale factors inside
 };
 
-inline void swap_rc(int n, double *A, int i, int j, int rows_hi /*swap columns over rows 0..rows_hi*/,
+template <typename S>
+inline void swap_rc(int n, S *A, int i, int j, int rows_hi /*swap columns over rows 0..rows_hi*/,
                     int cols_lo /*swap rows over columns cols_lo..n-1*/) {
     if (i == j) return;
     for (int r = 0; r <= rows_hi; ++r) std::swap(A[(size_t)i * n + r], A[(size_t)j * n + r]);
     for (int c = cols_lo; c < n; ++c) std::swap(A[(size_t)c * n + i], A[(size_t)c * n + j]);
 }
 
-inline void balance(int n, double *A, Balance &bal) {
+template <typename S>
+inline void balance(int n, S *A, Balance &bal) {
     bal.scale.assign(n, 1.0);
     int k = 0, l = n - 1;
     if (n == 0) { bal.ilo = 0; bal.ihi = -1; return; }
@@ -84,7 +97,7 @@ inline void balance(int n, double *A, Balance &bal) {
         for (int i = l; i >= 0; --i) {
             bool canswap = true;
             for (int j = 0; j <= l; ++j)
-                if (i != j && A[(size_t)j * n + i] != 0.0) { canswap = false; break; }
+                if (i != j && A[(size_t)j * n + i] != S(0.0)) { canswap = false; break; }
             if (canswap) {
                 bal.scale[l] = (double)i;
                 swap_rc(n, A, i, l, l, k);
@@ -102,7 +115,7 @@ inline void balance(int n, double *A, Balance &bal) {
         for (int j = k; j <= l; ++j) {
             bool canswap = true;
             for (int i = k; i <= l; ++i)
-                if (i != j && A[(size_t)j * n + i] != 0.0) { canswap = false; break; }
+                if (i != j && A[(size_t)j * n + i] != S(0.0)) { canswap = false; break; }
             if (canswap) {
                 bal.scale[k] = (double)j;
                 swap_rc(n, A, j, k, l, k);
@@ -124,14 +137,14 @@ inline void balance(int n, double *A, Balance &bal) {
         for (int i = k; i <= l; ++i) {
             double c = 0.0, r = 0.0;
             for (int q = k; q <= l; ++q) {
-                c += A[(size_t)i * n + q] * A[(size_t)i * n + q];
-                r += A[(size_t)q * n + i] * A[(size_t)q * n + i];
+                c += abs2(A[(size_t)i * n + q]);
+                r += abs2(A[(size_t)q * n + i]);
             }
             c = std::sqrt(c);
             r = std::sqrt(r);
             double ca = 0.0, ra = 0.0;
-            for (int q = 0; q <= l; ++q) ca = std::max(ca, std::fabs(A[(size_t)i * n + q]));
-            for (int q = k; q < n; ++q) ra = std::max(ra, std::fabs(A[(size_t)q * n + i]));
+            for (int q = 0; q <= l; ++q) ca = std::max(ca, absval(A[(size_t)i * n + q]));
+            for (int q = k; q < n; ++q) ra = std::max(ra, absval(A[(size_t)q * n + i]));
             if (c == 0.0 || r == 0.0) continue;
             if (!(c + ca + r + ra == c + ca + r + ra)) { bal.ilo = k; bal.ihi = l; return; }  // NaN guard
             double g = r / sclfac, f = 1.0;
@@ -162,7 +175,8 @@ inline void balance(int n, double *A, Balance &bal) {
 }
 
 // X <- (D P) X (D P)^{-1}: undo the scaling, then the permutations in reverse order.
-inline void unbalance(int n, double *X, const Balance &bal) {
+template <typename S>
+inline void unbalance(int n, S *X, const Balance &bal) {
     // ilo == ihi: the block is 1 x 1 and scale[ilo] holds a permutation index, not a factor (xGEBAK).
     for (int j = bal.ilo; j <= bal.ihi && bal.ilo < bal.ihi; ++j) {
         const double s = bal.scale[j];
@@ -180,43 +194,44 @@ inline void unbalance(int n, double *X, const Balance &bal) {
 }
 
 // ---- LU solve: A X = B in place (B <- X).  Returns false on an exactly singular pivot. -----------
-inline bool lu_solve(int n, double *A, double *B, int nrhs) {
+template <typename S>
+inline bool lu_solve(int n, S *A, S *B, int nrhs) {
     std::vector<int> piv(n);
     for (int k = 0; k < n; ++k) {
         int p = k;
-        double best = std::fabs(A[(size_t)k * n + k]);
+        double best = absval(A[(size_t)k * n + k]);
         for (int i = k + 1; i < n; ++i) {
-            const double v = std::fabs(A[(size_t)k * n + i]);
+            const double v = absval(A[(size_t)k * n + i]);
             if (v > best) { best = v; p = i; }
         }
         piv[k] = p;
         if (best == 0.0) return false;
         if (p != k)
             for (int j = 0; j < n; ++j) std::swap(A[(size_t)j * n + k], A[(size_t)j * n + p]);
-        const double inv = 1.0 / A[(size_t)k * n + k];
+        const S inv = S(1.0) / A[(size_t)k * n + k];
         for (int i = k + 1; i < n; ++i) A[(size_t)k * n + i] *= inv;
         for (int j = k + 1; j < n; ++j) {
-            const double akj = A[(size_t)j * n + k];
-            if (akj == 0.0) continue;
-            double *cj = A + (size_t)j * n;
-            const double *lk = A + (size_t)k * n;
+            const S akj = A[(size_t)j * n + k];
+            if (akj == S(0.0)) continue;
+            S *cj = A + (size_t)j * n;
+            const S *lk = A + (size_t)k * n;
             for (int i = k + 1; i < n; ++i) cj[i] -= lk[i] * akj;
         }
     }
     for (int c = 0; c < nrhs; ++c) {
-        double *b = B + (size_t)c * n;
+        S *b = B + (size_t)c * n;
         for (int k = 0; k < n; ++k)
             if (piv[k] != k) std::swap(b[k], b[piv[k]]);
         for (int k = 0; k < n; ++k) {  // L y = b (unit lower)
-            const double bk = b[k];
-            if (bk == 0.0) continue;
-            const double *lk = A + (size_t)k * n;
+            const S bk = b[k];
+            if (bk == S(0.0)) continue;
+            const S *lk = A + (size_t)k * n;
             for (int i = k + 1; i < n; ++i) b[i] -= lk[i] * bk;
         }
         for (int k = n - 1; k >= 0; --k) {  // U x = y
             b[k] /= A[(size_t)k * n + k];
-            const double bk = b[k];
-            const double *uk = A + (size_t)k * n;
+            const S bk = b[k];
+            const S *uk = A + (size_t)k * n;
             for (int i = 0; i < k; ++i) b[i] -= uk[i] * bk;
         }
     }
@@ -234,9 +249,10 @@ static const double PADE_C13[] = {64764752532480000.0, 32382376266240000.0, 7771
                                   670442572800.0, 33522128640.0, 1323241920.0, 40840800.0, 960960.0,
                                   16380.0, 182.0, 1.0};
 
-struct ExpWork {  // the (A2, P, U, V, temp) tuple of alloc_mem (exp_baseexp.jl:14-40)
+template <typename S>
+struct ExpWorkT {  // the (A2, P, U, V, temp) tuple of alloc_mem (exp_baseexp.jl:14-40)
     int n = 0;
-    std::vector<double> A2, P, U, V, T;
+    std::vector<S> A2, P, U, V, T;
     void reserve(int n_) {
         if (n_ == n) return;
         n = n_;
@@ -245,13 +261,16 @@ struct ExpWork {  // the (A2, P, U, V, temp) tuple of alloc_mem (exp_baseexp.jl:
     }
 };
 
+typedef ExpWorkT<double> ExpWork;
+
 // X (= A, in place) <- r_N(A); returns false if the denominator is singular.
-inline bool pade_evaluate(int n, double *A, const double *C, int N, ExpWork &w) {
+template <typename S>
+inline bool pade_evaluate(int n, S *A, const double *C, int N, ExpWorkT<S> &w) {
     const size_t s = (size_t)n * n;
-    double *A2 = w.A2.data(), *P = w.P.data(), *U = w.U.data(), *V = w.V.data(), *T = w.T.data();
+    S *A2 = w.A2.data(), *P = w.P.data(), *U = w.U.data(), *V = w.V.data(), *T = w.T.data();
     matmul(n, A, A, A2);
-    std::fill(P, P + s, 0.0);
-    for (int i = 0; i < n; ++i) P[(size_t)i * n + i] = 1.0;
+    std::fill(P, P + s, S(0.0));
+    for (int i = 0; i < n; ++i) P[(size_t)i * n + i] = S(1.0);
     for (size_t i = 0; i < s; ++i) { U[i] = C[1] * P[i]; V[i] = C[0] * P[i]; }
     for (int k = 1; k <= N / 2 - 1; ++k) {
         matmul(n, P, A2, T);
@@ -267,7 +286,8 @@ inline bool pade_evaluate(int n, double *A, const double *C, int N, ExpWork &w) 
 
 // exponential!(A) in place on a dense n x n column-major matrix with leading dimension n.
 // Returns 0, or 3 (ESINGULAR).
-inline int expm_higham2005base(int n, double *A, ExpWork &w) {
+template <typename S>
+inline int expm_higham2005base(int n, S *A, ExpWorkT<S> &w) {
     if (n == 0) return 0;
     w.reserve(n);
     Balance bal;
@@ -290,10 +310,10 @@ inline int expm_higham2005base(int n, double *A, ExpWork &w) {
         }
         ok = pade_evaluate(n, A, PADE_C13, 14, w);
         if (ok && s > 0) {
-            double *T = w.T.data();
+            S *T = w.T.data();
             for (int q = 0; q < si; ++q) {
                 matmul(n, A, A, T);
-                std::memcpy(A, T, sz * sizeof(double));
+                std::copy(T, T + sz, A);
             }
         }
     }

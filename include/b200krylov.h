@@ -168,6 +168,30 @@ int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out
                 const double *U, int64_t ldu, int ppo, const b200k_kiops_opts *opts, double *W,
                 int64_t ldw, int64_t *stats);
 
+/* ---- ComplexF64 element types and complex t (src/arnoldi.jl:412-421, src/krylov_phiv.jl:252-280) ----
+ * Complex data is passed as interleaved (re, im) doubles, i.e. Julia's Vector/Matrix{ComplexF64} memory; leading
+ * dimensions and lengths count COMPLEX elements.  H is always complex here (for a Hermitian operator the Lanczos
+ * coefficients are real: the imaginary parts are zero and the host mirror stores the real parts, as the reference's
+ * KrylovSubspace{T, U = real(T)} does).  Not available for the augmented (kiops) operator or row sharding. */
+int b200k_op_csr_create_z(b200k_handle_t h, int64_t n, int64_t nnz, const int32_t *rowptr, const int32_t *colind,
+                          const double *val, int index_base, int location, b200k_op_t *op);
+int b200k_op_dense_create_z(b200k_handle_t h, int64_t n, const double *A, int64_t lda, int location, b200k_op_t *op);
+/* arnoldi!/lanczos! on a complex basis (b: device, n complex values; V: device, complex, ldv; H: HOST, complex, ldh). */
+int b200k_arnoldi_z(b200k_handle_t h, b200k_op_t op, const double *b, const b200k_krylov_opts *opts, double *V,
+                    int64_t ldv, int maxiter, double *H, int ldh, double *beta, int *m_out, int *breakdown);
+/* expv!(w, t, Ks) with complex w and real or complex t = t_re + i t_im (krylov_phiv.jl:200-280). */
+int b200k_expv_ks_z(b200k_handle_t h, double t_re, double t_im, const double *V, int64_t ldv, int64_t nrows,
+                    const double *H, int ldh, int m, double beta, double *w);
+/* expv(t, A, b) one-shot on a complex operator. */
+int b200k_expv_z(b200k_handle_t h, b200k_op_t op, double t_re, double t_im, const double *b,
+                 const b200k_krylov_opts *opts, double *w, int *m_out, int *breakdown);
+/* Host small dense phase for complex H and/or complex t: y = exp(t H[1:m,1:m]) e1 (branch as b200k_expv_small). */
+int b200k_expv_small_z(int m, const double *H, int ldh, double t_re, double t_im, double *y, int *branch);
+/* W (device, nrows x nc) = beta * V[:, 1:m] * Y for a REAL basis V and a HOST coefficient matrix Y (m x nc, ldy):
+ * the projection step on its own.  Used for a real Krylov subspace with complex t (Y = [re(y) im(y)]). */
+int b200k_project(b200k_handle_t h, const double *V, int64_t ldv, int64_t nrows, int m, double beta, const double *Y,
+                  int ldy, int nc, double *W, int64_t ldw);
+
 /* ---- phiv_timestep! / expv_timestep! (src/krylov_phiv_adaptive.jl:57-114, 260-501) ------------------------
  * u(t) = phi_0(tA) b_0 + t phi_1(tA) b_1 + ... + t^p phi_p(tA) b_p at the times ts, by internal time stepping
  * with the Niesen-Wright adaptation of (tau, m) when `adaptive`.  Keyword arguments of the reference, same

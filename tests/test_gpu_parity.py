@@ -405,3 +405,59 @@ def test_batched_device_exponential(gpu, oracle):
     assert relerr(E[0], oracle.exponential_higham2005base(Bs[0])) < 1e-9
     with pytest.raises(gpu.UnsupportedError):
         gpu.exponential_batched_(np.zeros((2, 49, 49)))
+
+
+def test_complex_values(gpu, oracle):
+    """test/basictests.jl:650-664 "Complex Value": {Hermitian complex, Hermitian real, general complex, general real}
+    x {complex b, real b} x t in {real, imaginary, complex}, n = 20, m = 10 -- against dense exp and the oracle."""
+    rng = np.random.default_rng(3)
+    n, m = 20, 10
+    X = rng.random((n, n)) + 1j * rng.random((n, n))
+    mats = {"herm_c": X + X.conj().T, "herm_r": X.real + X.real.T, "gen_c": X, "gen_r": X.real}
+    for name, A in mats.items():
+        for b in (rng.random(n) + 1j * rng.random(n), rng.random(n)):
+            for t in (1e-2, 1e-2j, 1e-2 + 1e-2j):
+                w = gpu.expv(t, A, b, m=m)
+                assert relerr_c(w, sla.expm(t * A) @ b) < 1.5e-8, (name, b.dtype, t)
+                assert relerr_c(w, oracle.expv(t, A, b, m=m)) < RTOL, (name, b.dtype, t)
+
+
+def relerr_c(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def test_complex_sparse_and_factorisation(gpu, oracle):
+    """The reference's GPU test shape (test/gpu/gputests.jl:41-58): complex sparse operator, expv vs the CPU path;
+    plus H / V parity of the complex Arnoldi and Hermitian-Lanczos factorisations and a Schroedinger-type case."""
+    rng = np.random.default_rng(5)
+    n = 1000
+    A = (sp.random(n, n, density=0.01, random_state=1) + 1j * sp.random(n, n, density=0.01, random_state=2)).tocsr()
+    A = (sp.triu(A) + 0.1 * sp.identity(n)).tocsr()
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    assert relerr_c(gpu.expv(0.3, A, b, m=30), oracle.expv(0.3, A, b, m=30)) < RTOL
+    assert relerr_c(gpu.expv(0.3 - 0.2j, A, b, m=30), oracle.expv(0.3 - 0.2j, A, b, m=30)) < RTOL
+    Ks = gpu.arnoldi(A, b, m=15)
+    Ko = oracle.arnoldi(A, b, m=15)
+    assert Ks.is_complex and Ks.m == Ko.m and abs(Ks.beta - Ko.beta) < 1e-12
+    assert np.abs(Ks.getH() - Ko.getH()).max() < 1e-11
+    assert np.abs(Ks.getV().cpu().numpy() - Ko.getV()).max() < 1e-11
+    # Hermitian complex operator: -i * (Laplacian + complex Hermitian coupling), Lanczos with real coefficients
+    L = laplacian2d(40, 30)
+    Cc = sp.diags([1j * np.ones(1199), -1j * np.ones(1199)], [1, -1])
+    Hm = (L + 0.5 * Cc).tocsr()
+    psi = rng.standard_normal(1200) + 1j * rng.standard_normal(1200)
+    opH = gpu.operator(Hm)
+    assert opH.is_complex and opH.ishermitian
+    Ks = gpu.arnoldi(opH, psi, m=20)
+    Ko = oracle.arnoldi(Hm, psi, m=20)
+    assert np.abs(Ks.getH().imag).max() == 0.0 and np.abs(Ks.getH().real - Ko.getH()).max() < 1e-11
+    w = gpu.expv(-0.2j, opH, psi, m=30)   # unitary propagation
+    assert relerr_c(w, oracle.expv(-0.2j, Hm, psi, m=30)) < RTOL
+    assert abs(np.linalg.norm(w) - np.linalg.norm(psi)) < 1e-8 * np.linalg.norm(psi)
+    # zero vector and happy breakdown
+    assert np.linalg.norm(gpu.expv(0.1, A, np.zeros(n, dtype=complex), m=10)) == 0.0
+    v = rng.standard_normal(20) + 1j * rng.standard_normal(20)
+    v /= np.linalg.norm(v)
+    Kb = gpu.arnoldi(np.outer(v, v.conj()), rng.standard_normal(20) + 0j)
+    assert Kb.m == 2 and Kb.wasbreakdown
