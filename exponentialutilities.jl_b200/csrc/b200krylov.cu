@@ -110,6 +110,7 @@ struct b200k_context {
     int timing = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float krylov_ms = 0.f, project_ms = 0.f;
+    bool ev_k = false, ev_p = false;  // which event pairs have been recorded (elapsed time on unrecorded events errors)
 };
 
 struct b200k_comm {
@@ -452,6 +453,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
     void *args[] = {(void *)&P, (void *)&tmapA};
     CK(h, cudaLaunchCooperativeKernel(kern, dim3(c.g.C * c.g.nteams), dim3(threads), args, smem, h->stream));
     if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
+    if (h->timing) { h->ev_k = true; h->ev_p = false; }
     h->launches += 1;
     return B200K_OK;
 }
@@ -466,7 +468,7 @@ int fetch_krylov(b200k_context *h, int nprob, int m) {
     CK(h, cudaMemcpyAsync(h->scalh.p, h->scal.p, (size_t)nprob * 4 * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaMemcpyAsync(h->stath.p, h->stat.p, (size_t)nprob * 4 * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    if (h->timing) cudaEventElapsedTime(&h->krylov_ms, h->ev[0], h->ev[1]);
+    if (h->timing && h->ev_k) cudaEventElapsedTime(&h->krylov_ms, h->ev[0], h->ev[1]);
     return B200K_OK;
 }
 
@@ -527,6 +529,7 @@ int launch_project(b200k_context *h, const double *V, long long ldv, long long n
     launch_project_kernel(P, grid, h->stream);
     CK(h, cudaGetLastError());
     if (h->timing) CK(h, cudaEventRecord(h->ev[3], h->stream));
+    if (h->timing) h->ev_p = true;
     h->launches += 1;
     return B200K_OK;
 }
@@ -733,6 +736,7 @@ int launch_smallexp_project(b200k_context *h, int nprob, int m, int lanczos, con
     }
     CK(h, cudaGetLastError());
     if (h->timing) CK(h, cudaEventRecord(h->ev[3], h->stream));
+    if (h->timing) h->ev_p = true;
     // the (practically impossible) singular Pade denominator is reported by the next synchronising call
     CK(h, cudaMemcpyAsync(h->errh.p, h->errdev.p, 4, cudaMemcpyDeviceToHost, h->stream));
     return B200K_OK;
@@ -918,10 +922,14 @@ int b200k_last_kernel(b200k_handle_t h, int *which) {
 
 int b200k_last_timing(b200k_handle_t h, float *krylov_ms, float *project_ms) {
     if (!h) return B200K_EARG;
-    if (h->timing) {
+    if (h->timing && h->ev_k) {
         cudaEventSynchronize(h->ev[1]);
         cudaEventElapsedTime(&h->krylov_ms, h->ev[0], h->ev[1]);
-        if (cudaEventQuery(h->ev[3]) == cudaSuccess) cudaEventElapsedTime(&h->project_ms, h->ev[2], h->ev[3]);
+        h->project_ms = 0.f;
+        if (h->ev_p) {
+            cudaEventSynchronize(h->ev[3]);
+            cudaEventElapsedTime(&h->project_ms, h->ev[2], h->ev[3]);
+        }
     }
     if (krylov_ms) *krylov_ms = h->krylov_ms;
     if (project_ms) *project_ms = h->project_ms;
@@ -1414,6 +1422,7 @@ int b200k_expv_batched(b200k_handle_t h, b200k_op_t op, int nb, const double *t,
     }
     CK(h, cudaGetLastError());
     if (h->timing) CK(h, cudaEventRecord(h->ev[3], h->stream));
+    if (h->timing) h->ev_p = true;
     return B200K_OK;
 }
 
@@ -1752,7 +1761,7 @@ int arnoldi_z_core(b200k_context *h, b200k_operator *op, const double *b, const 
         P.rowptr = op->rowptr.as<int>();
         P.colind = op->colind.as<int>();
         P.val = op->val.as<double2>();
-        P.lanes_per_row = op->max_row_nnz <= 8 ? 4 : 32;
+        P.lanes_per_row = op->max_row_nnz <= 8 ? 1 : (op->max_row_nnz <= 24 ? 4 : 32);
     } else {
         P.op_kind = OP_DENSE;
         P.Ad = reinterpret_cast<const double2 *>(op->Ad);
@@ -1797,6 +1806,7 @@ int arnoldi_z_core(b200k_context *h, b200k_operator *op, const double *b, const 
     void *args[] = {(void *)&P};
     CK(h, cudaLaunchCooperativeKernel((const void *)krylov_z_kernel, dim3(g.C), dim3(NT), args, smem, h->stream));
     if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
+    if (h->timing) { h->ev_k = true; h->ev_p = false; }
     h->launches += 1;
     h->last_kernel = 3;
     const size_t hbytes = (size_t)ldhd * (m + 1) * 16;

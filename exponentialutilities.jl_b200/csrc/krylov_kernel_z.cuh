@@ -18,7 +18,7 @@ struct KrylovParamsZ {
     const int *rowptr;
     const int *colind;
     const double2 *val;
-    int lanes_per_row;  // 4 or 32 (CSR)
+    int lanes_per_row;  // CSR: 1 (rows of <= 8 entries, one row per thread), 4 or 32
     const double2 *Ad;
     long long lda;
     int team_size;
@@ -158,7 +158,27 @@ __global__ void __launch_bounds__(NT, 1) krylov_z_kernel(const __grid_constant__
         double *partn = P.partn + par * CPAD;
 
         // ---- mat-vec: ws = xscale * (A x)[slice] ----
-        if (P.op_kind == OP_CSR_WARP) {
+        if (P.op_kind == OP_CSR_WARP && P.lanes_per_row == 1) {
+            // short rows (<= 8 entries): one row per thread, all gathers of the row in flight before the first FMA
+            for (int rl = tid; rl < nrows; rl += NT) {
+                const int e0 = P.rowptr[r0 + rl], e1 = P.rowptr[r0 + rl + 1];
+                double2 av[8], xv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool ok = e0 + u < e1;
+                    av[u] = make_double2(0.0, 0.0);
+                    xv[u] = make_double2(0.0, 0.0);
+                    if (ok) {
+                        av[u] = P.val[e0 + u];
+                        xv[u] = xsrc[P.colind[e0 + u]];
+                    }
+                }
+                double2 sum = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sum = zfma(av[u], xv[u], sum);
+                ws[rl] = make_double2(sum.x * xscale, sum.y * xscale);
+            }
+        } else if (P.op_kind == OP_CSR_WARP) {
             const int G = P.lanes_per_row;  // 4 or 32
             const int gl = lane % G, gi = lane / G, rows_per_it = NW * (32 / G);
             for (int rbase = 0; rbase < nrows; rbase += rows_per_it) {

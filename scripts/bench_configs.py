@@ -91,4 +91,25 @@ if "ts" in which:
     wo, mo = O.expv_ee(1.0, A, Bh[:, 0], m=30, tol=1e-7, return_m=True)
     out["ee_expv_error_estimate"] = {"ms": ms, "m_stop": mm, "m_stop_oracle": mo,
                                     "relerr_vs_oracle": float(np.linalg.norm(w.cpu().numpy() - wo) / np.linalg.norm(wo))}
+if "z" in which:
+    # Schroedinger-type propagation exp(-i t H) psi, H = -Laplacian (complex Hermitian path -> Lanczos)
+    # and a general complex operator (Arnoldi), n = 1e6, m = 30, next to the CPU oracle
+    from oracle import oracle as O
+    import scipy.sparse as sp
+    L = laplacian2d(1000, 1000); n = 10**6
+    Hs = (-1.0 * L).astype(np.complex128).tocsr()
+    Cz = sp.diags([0.3j * np.ones(n - 1), 0.3j * np.ones(n - 1)], [1, -1])
+    Az = (L.astype(np.complex128) + Cz).tocsr()          # complex symmetric, not Hermitian -> Arnoldi
+    rng = np.random.default_rng(12)
+    psi_h = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    psi = torch.from_numpy(psi_h).cuda()
+    for name, M, t in (("z_hermitian_lanczos", Hs, -0.5j), ("z_general_arnoldi", Az, 0.5)):
+        op = eu.operator(M)
+        f = lambda: eu.expv(t, op, psi, m=30)
+        w = f(); ms = timeit(f, reps=10); k = kernel_ms(f, 5)
+        t0 = time.time(); wo = O.expv(t, M, psi_h, m=30); cpu_s = time.time() - t0
+        S_A = 20 * M.nnz + 4 * (n + 1)
+        B = 30 * (S_A + 48 * n) + 32 * n if op.ishermitian else 30 * (S_A + 32 * n) + 16 * n * 30 * 31 + 32 * n
+        out[name] = {"ms": ms, "kernel_ms": k, "alg_gbs": B / k / 1e6, "cpu_oracle_s": cpu_s,
+                     "relerr_vs_oracle": float(np.linalg.norm(w.cpu().numpy() - wo) / np.linalg.norm(wo)), "kernel": eng.last_kernel()}
 print(json.dumps(out, indent=1))
