@@ -461,3 +461,49 @@ def test_complex_sparse_and_factorisation(gpu, oracle):
     v /= np.linalg.norm(v)
     Kb = gpu.arnoldi(np.outer(v, v.conj()), rng.standard_normal(20) + 0j)
     assert Kb.m == 2 and Kb.wasbreakdown
+
+
+def test_abi_status_codes(gpu):
+    """Error behaviour at the C ABI itself (status codes + last_error), bypassing the Python argument checks."""
+    import ctypes as C
+    import torch
+    from importlib import import_module
+    L = import_module("eu_b200._lib")
+    lib, eng = gpu.load(), gpu.get_engine()
+    op = gpu.operator(laplacian2d(10, 10))
+    opts = L.KrylovOpts()
+    lib.b200k_krylov_opts_default(C.byref(opts))
+    assert (opts.m, opts.tol, opts.iop, opts.hermitian, opts.init, opts.p) == (30, 1e-7, 0, -1, 0, 0)
+    V = torch.zeros((11, 112), dtype=torch.float64, device="cuda")
+    H = np.zeros((11, 10), order="F")
+    b = torch.ones(100, dtype=torch.float64, device="cuda")
+    beta, mo, bd = C.c_double(), C.c_int(), C.c_int()
+
+    def call(m, ldv, maxiter, ldh):
+        opts.m = m
+        return lib.b200k_arnoldi(eng.handle, op.ptr, C.c_void_p(b.data_ptr()), C.byref(opts), C.c_void_p(V.data_ptr()),
+                                 ldv, maxiter, H.ctypes.data_as(L.c_double_p), ldh, C.byref(beta), C.byref(mo), C.byref(bd))
+
+    assert call(10, 112, 10, 11) == L.OK and mo.value == 10
+    assert call(11, 112, 10, 11) == L.EDIM and b"maxiter" in lib.b200k_last_error(eng.handle)      # resize! is the host's job
+    assert call(10, 99, 10, 11) == L.EDIM                                                           # size(V,1) < size(A,1)
+    assert call(10, 112, 10, 5) == L.EDIM                                                           # H too small
+    assert call(0, 112, 10, 11) == L.EARG
+    assert lib.b200k_arnoldi(eng.handle, op.ptr, None, C.byref(opts), None, 0, 0, None, 0, None, None, None) == L.EARG
+    opts.m, opts.p = 10, 17
+    assert call(10, 128, 10, 11) == L.EUNSUPPORTED                                                  # p > 16
+    opts.p = 0
+    # a complex operator through a real entry point (and vice versa) is an argument error
+    opz = gpu.operator(laplacian2d(10, 10).astype(np.complex128))
+    assert lib.b200k_arnoldi(eng.handle, opz.ptr, C.c_void_p(b.data_ptr()), C.byref(opts), C.c_void_p(V.data_ptr()), 112,
+                             10, H.ctypes.data_as(L.c_double_p), 11, C.byref(beta), C.byref(mo), C.byref(bd)) == L.EARG
+    ko = L.KiopsOpts()
+    lib.b200k_kiops_opts_default(C.byref(ko))
+    assert (ko.mmin, ko.mmax, ko.m, ko.tol, ko.iop) == (10, 128, 10, 1e-7, 2)
+    # kiops with several output times is a DimensionMismatch in the reference (checkdims) and here
+    tau = np.array([0.5, 1.0])
+    W = torch.zeros((2, 100), dtype=torch.float64, device="cuda")
+    stats = (C.c_int64 * 5)()
+    assert lib.b200k_kiops(eng.handle, op.ptr, 2, tau.ctypes.data_as(L.c_double_p), 1, C.c_void_p(b.data_ptr()), 100, 1,
+                           C.byref(ko), C.c_void_p(W.data_ptr()), 100, stats) == L.EDIM
+    assert lib.b200k_status_string(L.EDIM) == b"dimension mismatch"
