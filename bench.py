@@ -290,7 +290,7 @@ def main():
                 "ms_per_step": ms_e2e_total / args.steps,
                 "note": "b200k_expv_host through the C ABI; operator resident (uploaded once at ingestion)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": {"ldg": "krylov_persistent_kernel", "tma": "krylov_tma_kernel"}.get(eng.last_kernel(), "?"), "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": {"ldg": "krylov_persistent_kernel", "tma": "krylov_tma_kernel", "tma_xl": "krylov_tma_kernel<XL>"}.get(eng.last_kernel(), "?"), "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "algorithmic_bytes_per_launch": fact_bytes, "kernel_ms": k_ms, "peak_source": peak_src,
                      "project_kernel_ms": p_ms, "project_bytes": proj_bytes,

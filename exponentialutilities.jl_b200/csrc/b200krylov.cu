@@ -90,8 +90,12 @@ struct b200k_context {
     int host_smallexp = 0;  // B200K_SMALLEXP=host: one-shot / batched expv do the small exponential on the host
     DevBuf tdev, errdev;
     HostBuf errh;
+    int no_xl = 0;     // B200K_FLAG_NO_XL / B200K_XL=0: never use the short-window (XL) instance
+    int last_xl = 0;   // the last persistent launch used the XL instance
+    DevBuf llpkt;      // packet all-reduce inboxes of the XL instance [2][LLQ][CPAD dest][CPAD src] x 16 B, zeroed at allocation
+    unsigned ll_seq = 0;  // packet sequence numbers consumed by earlier launches
     int force_ldg = 0; // B200K_KERNEL=ldg: use the LDG kernel even where the TMA-ring kernel applies
-    int last_kernel = 0;  // 1 = LDG kernel, 2 = TMA-ring kernel
+    int last_kernel = 0;  // 1 = LDG kernel, 2 = TMA-ring kernel, 3 = complex kernel, 4 = TMA-ring kernel, XL instance
     std::string err;
     int64_t launches = 0;
     // scratch (device)
@@ -418,6 +422,39 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
                 P.dense_box_rows = box_rows;
             }
         }
+        // short-window instance (Lanczos / IOP-q): second slice buffer for the resident basis vector
+        bool xl = false;
+        if (P.op_kind == OP_CSR_STREAM && !h->no_xl && P.w_in_smem && (c.lanczos || c.iop > 0)) {
+            const int ns2 = (int)((SMEM_LIMIT - fixed - 2 * wsb) / SLOT_BYTES);
+            if (SMEM_LIMIT >= fixed + 2 * wsb && ns2 >= 2) {
+                xl = true;
+                nslot = std::min(ns2, MAXSLOT);
+                P.nslot = nslot;
+                wsb *= 2;
+            }
+        }
+        P.xl = xl ? 1 : 0;
+        if (xl) {
+            const size_t pbytes = (size_t)2 * LLQ * CPAD * CPAD * sizeof(uint4);  // [parity][quantity][dest CTA][source rank]
+            if (pbytes > h->llpkt.cap) {
+                CK(h, h->llpkt.ensure(pbytes));
+                CK(h, cudaMemsetAsync(h->llpkt.p, 0, h->llpkt.cap, h->stream));
+                h->ll_seq = 0;
+            }
+            // sequence numbers are unique per team across launches; a team passes at most 2 reductions per step
+            // plus one per firststep! of each of its problems
+            const unsigned rounds = (unsigned)((c.nprob + nt - 1) / nt);
+            const unsigned need = rounds * (2u * (unsigned)c.m + 4u) + 8u;
+            if (h->ll_seq > 0xffffffffu - need - 16u) {  // wrap: clear the stale packets and start over
+                CK(h, cudaMemsetAsync(h->llpkt.p, 0, h->llpkt.cap, h->stream));
+                h->ll_seq = 0;
+            }
+            P.llpkt = h->llpkt.as<uint4>();
+            if (!cm) {
+                P.seq_base = h->ll_seq;
+                h->ll_seq += need;
+            }
+        }
         // L2 policy for the operator stream (see producer_problem)
         P.l2hint = 0;
         P.hintA_cols = 1 << 30;
@@ -438,13 +475,18 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
         {
             const bool aug = c.p > 0;
             switch (P.op_kind) {
-                case OP_CSR_STREAM: kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false>; break;
-                case OP_CSR_WARP: kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_WARP, true> : (const void *)krylov_tma_kernel<OP_CSR_WARP, false>; break;
-                default: kern = aug ? (const void *)krylov_tma_kernel<OP_DENSE, true> : (const void *)krylov_tma_kernel<OP_DENSE, false>; break;
+                case OP_CSR_STREAM:
+                    if (xl && op->max_row_nnz <= 5) kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5>;
+                    else if (xl) kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 8> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 8>;
+                    else kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, false> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, false>;
+                    break;
+                case OP_CSR_WARP: kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_WARP, true, false> : (const void *)krylov_tma_kernel<OP_CSR_WARP, false, false>; break;
+                default: kern = aug ? (const void *)krylov_tma_kernel<OP_DENSE, true, false> : (const void *)krylov_tma_kernel<OP_DENSE, false, false>; break;
             }
         }
         threads = NT2;
-        h->last_kernel = 2;
+        h->last_kernel = xl ? 4 : 2;
+        h->last_xl = xl ? 1 : 0;
     } else {
         h->last_kernel = 1;
     }
@@ -826,14 +868,16 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
         delete h;
         return B200K_ECUDA;
     }
-    const void *tma_kernels[] = {(const void *)krylov_tma_kernel<OP_CSR_STREAM, false>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true>,
-                                 (const void *)krylov_tma_kernel<OP_CSR_WARP, false>, (const void *)krylov_tma_kernel<OP_CSR_WARP, true>,
-                                 (const void *)krylov_tma_kernel<OP_DENSE, false>, (const void *)krylov_tma_kernel<OP_DENSE, true>};
+    const void *tma_kernels[] = {(const void *)krylov_tma_kernel<OP_CSR_STREAM, false, false>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, false>,
+                                 (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 8>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 8>,
+                                 (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5>,
+                                 (const void *)krylov_tma_kernel<OP_CSR_WARP, false, false>, (const void *)krylov_tma_kernel<OP_CSR_WARP, true, false>,
+                                 (const void *)krylov_tma_kernel<OP_DENSE, false, false>, (const void *)krylov_tma_kernel<OP_DENSE, true, false>};
     bool attr_ok = true;
     for (const void *k : tma_kernels)
         attr_ok = attr_ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) == cudaSuccess;
     if (!attr_ok ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, krylov_tma_kernel<OP_CSR_STREAM, false>, NT2, SMEM_LIMIT) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, krylov_tma_kernel<OP_CSR_STREAM, false, false>, NT2, SMEM_LIMIT) != cudaSuccess ||
         per_sm < 1) {
         delete h;
         return B200K_ECUDA;
@@ -851,6 +895,7 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
                          6 * SE_MAXM * SE_MAXM * 8);
     cudaFuncSetAttribute((const void *)small_exp_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          6 * SE_MAXM * SE_MAXM * 8);
+    if (const char *env = std::getenv("B200K_XL")) h->no_xl = std::strcmp(env, "0") == 0 ? 1 : 0;
     if (const char *env = std::getenv("B200K_KERNEL")) h->force_ldg = std::strcmp(env, "ldg") == 0 ? 1 : 0;
     h->max_ctas = std::min(h->sm_count, CPAD);  // one CTA per SM
     for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
@@ -862,7 +907,7 @@ int b200k_destroy(b200k_handle_t h) {
     if (!h) return B200K_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->zV, &h->zH, &h->zpart, &h->zxbuf, &h->zw, &h->zy, &h->tsV, &h->tsW, &h->tsP, &h->tsu, &h->tdev, &h->errdev, &h->kV, &h->kB, &h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
+    DevBuf *bufs[] = {&h->zV, &h->zH, &h->zpart, &h->zxbuf, &h->zw, &h->zy, &h->tsV, &h->tsW, &h->tsP, &h->tsu, &h->tdev, &h->errdev, &h->llpkt, &h->kV, &h->kB, &h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
                       &h->Y, &h->corr, &h->mvec, &h->betavec, &h->tmp, &h->V, &h->bdev, &h->wdev};
     for (DevBuf *b : bufs) b->release();
     HostBuf *hb[] = {&h->zHh, &h->errh, &h->Hh, &h->scalh, &h->stath, &h->Yh};
@@ -909,6 +954,7 @@ int b200k_set_flag(b200k_handle_t h, int flag, int value) {
     if (!h) return B200K_EARG;
     if (flag == B200K_FLAG_FORCE_LDG) h->force_ldg = value ? 1 : 0;
     else if (flag == B200K_FLAG_HOST_SMALLEXP) h->host_smallexp = value ? 1 : 0;
+    else if (flag == B200K_FLAG_NO_XL) h->no_xl = value ? 1 : 0;
     else if (flag == B200K_FLAG_L2HINT) h->l2hint = value < 0 ? -1 : (value ? 1 : 0);
     else return fail(h, B200K_EARG, "unknown flag");
     return B200K_OK;
@@ -2387,5 +2433,14 @@ int b200k_phiv_dense(int m, const double *A, int lda, const double *v, int k, do
     const int st = smallmat::phiv_dense(m, A, lda, v, k, w, ldw, work);
     return st ? B200K_ESINGULAR : B200K_OK;
 }
+
+#ifdef B200K_PHASE_TIMING
+// profiling builds only: copy the per-phase clock64 stamps of the last krylov_tma_kernel launch to the host
+int b200k_debug_phase_ts(long long *out, long long count) {
+    const long long total = (long long)PT_CTAS * PT_STEPS * PT_MARKS;
+    if (count > total) count = total;
+    return (int)cudaMemcpyFromSymbol(out, g_phase_ts, (size_t)count * 8);
+}
+#endif
 
 }  // extern "C"

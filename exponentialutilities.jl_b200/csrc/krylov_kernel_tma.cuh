@@ -33,6 +33,7 @@ constexpr int MAXSLOT = 6;
 constexpr int TILE_ROWS_MAX = SLOT_BYTES / 8;    // 4096 rows per basis tile
 constexpr int PPT = TILE_ROWS_MAX / 2 / NTC;     // row pairs per consumer thread per tile (4)
 constexpr int MAXCH2 = 64;                       // chunk-table capacity
+constexpr int LLQ = 4;                           // quantities one packet all-reduce (ll_publish / ll_collect) carries
 
 struct __align__(128) SmemTma {
     uint64_t full[MAXSLOT];
@@ -45,13 +46,46 @@ struct __align__(128) SmemTma {
     int chunk_a0[MAXCH2];
     int chunk_cnt[MAXCH2];
     int slot_a0[MAXSLOT];
+    int chunk_local[MAXCH2];  // XL: every column of the chunk lies in this CTA's slice (learnt by the first mat-vec)
     double bc[2];             // reduced scalars (squared norm) broadcast to the CTA
+    double llv[LLQ][CPAD];    // packets of a fused barrier + all-reduce (ll_collect), one value per CTA of the team
     volatile int cols_ready;  // number of complete basis columns of the current problem
     volatile int stop_seq;    // consumers finished local problem #stop_seq (1-based)
 };
 
+// Per-phase timestamps (profiling builds only: -DB200K_PHASE_TIMING, scripts/phase_timing.py).
+#ifdef B200K_PHASE_TIMING
+constexpr int PT_STEPS = 64, PT_MARKS = 16, PT_CTAS = 160;
+__device__ long long g_phase_ts[PT_CTAS * PT_STEPS * PT_MARKS];
+#define PT_MARK(rank, step, k)                                                                    \
+    do {                                                                                          \
+        if (threadIdx.x == 0 && (rank) < PT_CTAS && (step) < PT_STEPS)                            \
+            g_phase_ts[((rank) * PT_STEPS + (step)) * PT_MARKS + (k)] = clock64();                \
+    } while (0)
+#else
+#define PT_MARK(rank, step, k) do { } while (0)
+#endif
+
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Explicit shared-memory accesses by 32-bit shared address.  The two slice buffers of the XL instance swap roles
+// every step, so the compiler cannot prove their address space and emits generic LD / ST with 64-bit address
+// arithmetic (measured: the mat-vec is instruction-issue bound); these keep them LDS / STS.
+__device__ __forceinline__ double lds1(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts1(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+__device__ __forceinline__ void sts2(uint32_t a, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y));
+}
 
 // ---- team barrier and team-wide reduction -----------------------------------------------------------------------
 // Single GPU: the cooperative-groups grid-sync protocol on one counter, then every CTA sums the per-CTA partials in
@@ -91,6 +125,38 @@ __device__ __forceinline__ void team_barrier_c(Team &tm, const KrylovParams &P, 
         __threadfence();
     }
     consumer_sync();
+}
+
+// ---- single-GPU fused barrier + all-reduce of <= LLQ scalars (short orthogonalisation windows) --------------------
+// The counter barrier costs three dependent L2 round trips and two MEMBARs per reduction (partial store + fence +
+// atomic, poll, fence, partial loads: ~2.4 us measured, one third of a Lanczos step).  Here every CTA sends its
+// partial as a self-validating 16-byte packet {lo32, seq, hi32, seq} to the inbox of EVERY CTA of its team (C plain
+// stores, no hot spot) and polls only its own inbox, adding the C packets in CTA order (bitwise identical
+// everywhere): data and notification travel together, one L2 round trip.  (A single shared packet table polled by
+// all 148 CTAs was measured first: 148 x 148 spinning loads on 19 cache lines made it slower than the counter.)
+// Two packet sets (parity of seq) suffice: a CTA can only be one reduction ahead of the slowest CTA of its team.
+// `release` / `acquire` = the reduction also orders this step's gather-buffer stores before the next mat-vec's
+// gathers: MEMBAR before the packet stores, ld.acquire polls (LDG.STRONG + CCTL.IVALL, no MEMBAR) on the other side.
+__device__ __forceinline__ uint4 *ll_slot(const KrylovParams &P, unsigned seq, int ci, int dest_cta, int src_rank) {
+    return P.llpkt + ((((long long)(seq & 1u)) * LLQ + ci) * CPAD + dest_cta) * CPAD + src_rank;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ double ll_poll_acquire(const uint4 *p, unsigned seq) {
+    unsigned lo, f1, hi, f2;
+    do {
+        asm volatile("ld.acquire.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2)
+                     : "l"(p)
+                     : "memory");
+    } while (f1 != seq || f2 != seq);
+    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+// Called by ALL lanes of one warp with the same value v (CTA partial of quantity ci).
+__device__ __forceinline__ void ll_publish_warp(const KrylovParams &P, int team, const Team &tm, unsigned seq, int ci,
+                                                double v, int lane, bool release) {
+    if (release) fence_acq_rel_gpu();
+    const int base = team * tm.C;
+    for (int d = lane; d < tm.C; d += 32) ll_push(ll_slot(P, seq, ci, base + d, tm.rank), v, seq);
 }
 
 struct Ring {
@@ -133,7 +199,7 @@ __device__ __forceinline__ bool prod_wait_col(SmemTma *S, int col, int seq, int)
     return true;
 }
 
-template <int OPK, bool AUG>
+template <int OPK, bool AUG, bool XL>
 __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, SmemTma *S, Ring &rg,
                                  const TmaGeom &G, const double *V, int seq, unsigned &issued, int lane) {
     const long long ldv = P.ldv;
@@ -153,8 +219,19 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
         // operator + two basis passes); in narrow-window steps (Lanczos, IOP, early Arnoldi) it stays resident.
         const bool hintA = (jc - (P.lanczos ? jc : max(0, jc - iopw + 1)) + 1) >= P.hintA_cols;
         if (OPK == OP_CSR_STREAM) {
+#ifdef B200K_PHASE_TIMING
+            long long pt_acq = 0;
+            const long long pt_begin = clock64();
+#endif
             for (int c = 0; c < G.nch; ++c) {
+#ifdef B200K_PHASE_TIMING
+                const long long pa0 = clock64();
+                const bool got = prod_acquire(S, rg, seq, lane);
+                pt_acq += clock64() - pa0;
+                if (!got) { stopped = true; break; }
+#else
                 if (!prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
+#endif
                 if (lane == 0) {
                     const int rs = G.r0 + c * P.ch_rows;
                     const int re = min(G.r0 + G.nrows, rs + P.ch_rows);
@@ -190,6 +267,13 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
                 rg.advance();
                 ++issued;
             }
+#ifdef B200K_PHASE_TIMING
+            if (blockIdx.x < PT_CTAS && j < PT_STEPS) {
+                long long *q = g_phase_ts + ((long long)blockIdx.x * PT_STEPS + j) * PT_MARKS + 13;
+                q[0] = pt_acq;
+                q[1] = clock64() - pt_begin;
+            }
+#endif
             if (stopped) break;
         } else if (OPK == OP_DENSE && P.dense_cpt > 0 && G.nrows > 0) {
             // dense operator: a tile = dense_cpt columns x the CTA's row slice, fetched as slice/box_rows
@@ -211,7 +295,8 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
             if (stopped) break;
         }
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
-        const int hi = jc;
+        // XL: column jc is the shared-memory resident vector -- no tiles for it in either pass
+        const int hi = XL ? jc - 1 : jc;
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
         for (int cb = lo; cb <= hi && !stopped; cb += CB) {
             const int nb = min(CB, hi - cb + 1);
@@ -236,7 +321,8 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
         for (int k = 0; k < G.ntk && !stopped; ++k) {
             const int rows = min(G.TR, G.nrows - k * G.TR);
             for (int col = hi; col >= ulo; --col) {
-                if (!prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
+                // (XL: column jc - 1 is written lazily during the previous step's update phase)
+                if ((XL && !prod_wait_col(S, col, seq, lane)) || !prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
                 if (lane == 0) {
                     mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 8u);
                     {
@@ -265,6 +351,9 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
 struct Cons {
     SmemTma *S;
     double *ws;
+    double *xin;  // XL: this CTA's slice of the (unnormalised) current basis vector, resident in shared memory
+    uint32_t xin_a, ws_a;  // XL: shared addresses of xin / ws (lds1 / sts1 ...)
+    int team;
     int tid, lane, warp;
     unsigned seq;  // team barriers passed so far (the LL packets of barrier #seq carry it)
     Ring rg;
@@ -322,6 +411,27 @@ __device__ void team_reduce_c(const KrylovParams &P, Cons &cx, Team &tm, const d
     consumer_sync();
 }
 
+// Collect side of the packet all-reduce: out[ci] (shared memory) = sum over the team of quantity ci.
+__device__ void ll_collect(const KrylovParams &P, Cons &cx, const Team &tm, int ncols, double *out, bool acquire) {
+    SmemTma *S = cx.S;
+    cx.seq += 1u;
+    const unsigned seq = cx.seq;
+    const int total = ncols * tm.C;
+    for (int idx = cx.tid; idx < total; idx += NTC) {
+        const int ci = idx / tm.C, r = idx - ci * tm.C;
+        const uint4 *slot = ll_slot(P, seq, ci, (int)blockIdx.x, r);
+        S->llv[ci][r] = acquire ? ll_poll_acquire(slot, seq) : ll_poll(slot, seq);
+    }
+    consumer_sync();
+    for (int ci = cx.warp; ci < ncols; ci += NW) {
+        double s = 0.0;
+        for (int q = cx.lane; q < tm.C; q += 32) s += S->llv[ci][q];
+        s = warp_sum(s);
+        if (cx.lane == 0) out[ci] = s;
+    }
+    consumer_sync();
+}
+
 // Push this CTA's rows that other GPUs gather (halo) into their gather buffers (peer stores over NVLink).
 __device__ __forceinline__ void push_halo(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm,
                                           long long xoff) {
@@ -329,6 +439,122 @@ __device__ __forceinline__ void push_halo(const KrylovParams &P, Cons &cx, const
     const int e1 = P.send_ofs[tm.rank + 1];
     for (int e = P.send_ofs[tm.rank] + cx.tid; e < e1; e += NTC)
         P.peer_xbuf[P.send_peer[e]][xoff + P.send_pos[e]] = cx.ws[P.send_row[e] - G.r0];
+}
+
+// XL mat-vec (CSR stream): entries whose column lies in this CTA's own row slice are gathered from the shared-memory
+// resident slice cx.xin instead of L2 (for stencil-like operators that is almost every entry), the result goes to the
+// other buffer cx.ws, and the inner product of the new w with the current basis vector is accumulated on the fly --
+// returned UNSCALED per thread: sum over this thread's rows of xin[row] * (A x)[row].
+// The phase is instruction-issue bound (16 warps, one row per thread: measured 820 cycles per 512-row chunk without
+// any x load), so (a) the gather batch width GW is a template parameter (5 for operators with <= 5 entries per row),
+// and (b) chunks whose columns ALL lie in the slice take a loop without the local/remote select or any global
+// address arithmetic; which chunks those are is learnt by the first mat-vec of a launch (`learn`).
+template <bool AUG, int GW>
+__device__ double matvec_xl(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *xsrc, double xscale,
+                            bool learn, int pt_step = 0) {
+    double selfacc = 0.0;
+    SmemTma *S = cx.S;
+    const int tid = cx.tid;
+    const int n = P.n, p = AUG ? P.p : 0;
+    const uint32_t ws_a = cx.ws_a, xin_a = cx.xin_a;
+    const uint32_t xl_a = xin_a - 8u * (uint32_t)G.r0;  // shared address of x(column) for own-slice columns
+    if (p > 0) {
+        if (tid < p) S->xtail[tid] = xsrc[n + P.nhalo + tid];
+        consumer_sync();
+        if (tid < p) S->wtail[tid] = (tid < p - 1) ? S->xtail[tid + 1] * xscale : 0.0;
+    }
+    const int nnz_cap = P.nnz_cap;
+#ifdef B200K_PHASE_TIMING
+    long long pt_wait = 0, pt_comp = 0;
+#endif
+    for (int c = 0; c < G.nch; ++c) {
+        const int rl = c * P.ch_rows + tid;
+        const bool active = tid < P.ch_rows && rl < G.nrows;
+        const bool fast = !learn && c < MAXCH2 && S->chunk_local[c] != 0;
+#ifdef B200K_PHASE_TIMING
+        const long long pt0 = clock64();
+#endif
+        cx.wait_full();
+#ifdef B200K_PHASE_TIMING
+        const long long pt1 = clock64();
+#endif
+        bool loc = true;
+#ifdef B200K_EXP_NOCOMPUTE  // profiling experiment: pure operator-stream rate of the mat-vec phase
+        if (false) {
+#else
+        if (active) {
+#endif
+            const unsigned char *base = cx.rg.ptr();
+            const double *vs = reinterpret_cast<const double *>(base);
+            const int *cs = reinterpret_cast<const int *>(base + (size_t)nnz_cap * 8);
+            const int *rp = reinterpret_cast<const int *>(base + (size_t)nnz_cap * 12);
+            const int a0 = S->slot_a0[cx.rg.slot];
+            const int e0 = rp[tid] - a0, e1 = rp[tid + 1] - a0;
+            double sum = 0.0;
+            if (fast) {
+#pragma unroll 1
+                for (int eb = e0; eb < e1; eb += GW) {
+                    double av[GW], xv[GW];
+#pragma unroll
+                    for (int u = 0; u < GW; ++u) {
+                        const bool ok = eb + u < e1;
+                        av[u] = ok ? vs[eb + u] : 0.0;
+                        xv[u] = 0.0;
+                        if (ok) xv[u] = lds1(xl_a + 8u * (uint32_t)cs[eb + u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < GW; ++u) sum = fma(av[u], xv[u], sum);
+                }
+            } else {
+#pragma unroll 1
+                for (int eb = e0; eb < e1; eb += GW) {
+                    double av[GW], xv[GW];
+#pragma unroll
+                    for (int u = 0; u < GW; ++u) {
+                        const bool ok = eb + u < e1;
+                        av[u] = ok ? vs[eb + u] : 0.0;
+                        xv[u] = 0.0;
+#ifdef B200K_EXP_NOGATHER  // profiling experiment: no x loads at all
+                        if (ok) xv[u] = 1.0 + (double)cs[eb + u];
+                        else
+#endif
+                        if (ok) {
+                            const int col = cs[eb + u];
+                            const unsigned lc = (unsigned)(col - G.r0);
+                            const bool here = lc < (unsigned)G.nrows;
+                            loc = loc && here;
+                            if (here) xv[u] = lds1(xin_a + 8u * lc);
+                            else xv[u] = xsrc[col];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < GW; ++u) sum = fma(av[u], xv[u], sum);
+                }
+            }
+            if (p > 0) {
+                const double *brow = P.Bm + (G.r0 + rl);
+                for (int k = 0; k < p; ++k) sum = fma(brow[(long long)k * P.ldb], S->xtail[k], sum);
+            }
+            selfacc = fma(lds1(xin_a + 8u * (uint32_t)rl), sum, selfacc);
+            sts1(ws_a + 8u * (uint32_t)rl, sum * xscale);
+        }
+        if (learn && c < MAXCH2) {
+            if (!__all_sync(0xffffffffu, loc) && cx.lane == 0) S->chunk_local[c] = 0;
+        }
+        cx.release();
+#ifdef B200K_PHASE_TIMING
+        pt_wait += pt1 - pt0;
+        pt_comp += clock64() - pt1;
+#endif
+    }
+#ifdef B200K_PHASE_TIMING
+    if ((tid == 0 || tid == 480) && blockIdx.x < PT_CTAS && pt_step < PT_STEPS) {
+        long long *q = g_phase_ts + ((long long)blockIdx.x * PT_STEPS + pt_step) * PT_MARKS + (tid == 0 ? 9 : 11);
+        q[0] = pt_wait;
+        q[1] = pt_comp;
+    }
+#endif
+    return selfacc;  // (no trailing barrier: the block reduction of the fused inner product is the barrier)
 }
 
 template <int OPK, bool AUG>
@@ -703,23 +929,29 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         const long long part = part0 + (long long)par * MAXCOL * P.cpad;
         const long long partn = partn0 + (long long)par * P.cpad;
 
+        PT_MARK(blockIdx.x, j, 0);
         matvec_phase_c<OPK, AUG>(P, cx, G, xsrc, xscale);
+        PT_MARK(blockIdx.x, j, 1);
 
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
         const int hi = jc;
         dots_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, hi, part);
+        PT_MARK(blockIdx.x, j, 2);
         const int nc = hi - lo + 1;
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
         team_reduce_c(P, cx, tm, lpart + part, nc, S->hs + (lo - ulo), false);
+        PT_MARK(blockIdx.x, j, 3);
         if (tm.rank == 0)
             for (int ci = tid; ci < nc; ci += NTC) Hd[(long long)jc * ldh + lo + ci] = S->hs[lo + ci - ulo];
         if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = beta_prev;
         consumer_sync();
 
         const double nrm = update_phase_c<OPK, AUG>(P, cx, G, tm, V, ulo, hi, xout);
+        PT_MARK(blockIdx.x, j, 4);
         block_sum_to_c(P, cx, nrm, partn + tm.rank);
         push_halo(P, cx, G, tm, xoff);  // after block_sum's CTA barrier: the whole w slice is in place
         team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, sharded);
+        PT_MARK(blockIdx.x, j, 5);
 
         const double beta = sqrt(S->bc[0]);
         if (tm.rank == 0 && tid == 0) Hd[(long long)jc * ldh + jc + 1] = beta;
@@ -736,6 +968,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         fence_proxy_async();  // the producer's TMA reads of this column must see these generic-proxy stores
         consumer_sync();
         if (tid == 0) S->cols_ready = jc + 2;
+        PT_MARK(blockIdx.x, j, 6);
         xsrc = xout;
         xscale = 1.0 / beta;
         beta_prev = beta;
@@ -751,16 +984,377 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
     }
 }
 
+template <int OPK, bool AUG, bool XL>
+__device__ void dots_phase_xl(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
+                             int lo, int hi, long long part_off, bool use_ll) {
+    SmemTma *S = cx.S;
+    const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
+    const uint32_t ws_a = cx.ws_a;
+    int batch = 0;
+    for (int cb = lo; cb <= hi; cb += CB, ++batch) {
+        const int nb = min(CB, hi - cb + 1);
+        double acc[CB];
+#pragma unroll
+        for (int u = 0; u < CB; ++u) acc[u] = 0.0;
+        for (int k = 0; k < G.ntk; ++k) {
+            const int pairs = min(G.TR, G.nrows - k * G.TR) >> 1;
+            const int pbase = (k * G.TR) >> 1;
+            double2 wr[PPT];
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) {
+                const int idx = tid + q * NTC;
+                wr[q] = idx < pairs ? lds2(ws_a + 16u * (uint32_t)(pbase + idx)) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < CB; ++u) {
+                if (u < nb) {
+                    cx.wait_full();
+                    const double2 *vt = reinterpret_cast<const double2 *>(cx.rg.ptr());
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        const int idx = tid + q * NTC;
+                        if (idx < pairs) {
+                            const double2 v2 = vt[idx];
+                            acc[u] = fma(v2.x, wr[q].x, fma(v2.y, wr[q].y, acc[u]));
+                        }
+                    }
+                    cx.release();
+                }
+            }
+        }
+        if (AUG && P.p > 0 && tm.rank == 0 && P.myrank == 0 && tid == 0) {  // augmented tail rows (direct loads)
+#pragma unroll
+            for (int u = 0; u < CB; ++u)
+                if (u < nb)
+                    for (int kk = 0; kk < P.p; ++kk)
+                        acc[u] = fma(V[(long long)(cb + u) * P.ldv + P.n + kk], S->wtail[kk], acc[u]);
+        }
+        const double r = warp_reduce8(acc, lane);
+        const int buf = batch & 1;
+        if ((lane & 3) == 0) S->red[buf][warp][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = r;
+        consumer_sync();
+        if (XL && use_ll) {
+            if (warp == 0) {
+                double s = 0.0;
+                if (lane < nb) {
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) s += S->red[buf][w][lane];
+                }
+                for (int u = 0; u < nb; ++u)
+                    ll_publish_warp(P, cx.team, tm, cx.seq + 1u, cb - lo + u, __shfl_sync(0xffffffffu, s, u), lane, false);
+            }
+        } else if (tid < nb) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += S->red[buf][w][tid];
+            P.peer_part[P.myrank][part_off + (long long)(cb - lo + tid) * P.cpad + tm.rank] = s;
+        }
+    }
+}
+
+// XL: column uhi + 1 (the current basis vector) is cx.xin * xscale in shared memory (`vlazy`: where its augmented
+// tail rows are stored, nullptr = already in V; the slice itself is stored by the caller, see consumer_problem).
+template <int OPK, bool AUG, bool XL>
+__device__ double update_phase_xl(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
+                                 int ulo, int uhi, double *xout, double xscale, double *vlazy) {
+    SmemTma *S = cx.S;
+    const int tid = cx.tid;
+    const uint32_t ws_a = cx.ws_a, xin_a = cx.xin_a;
+    double2 *xo2 = reinterpret_cast<double2 *>(xout + G.r0);
+    const double *hs = S->hs;
+    double nrm = 0.0;
+    for (int k = 0; k < G.ntk; ++k) {
+        const int pairs = min(G.TR, G.nrows - k * G.TR) >> 1;
+        const int pbase = (k * G.TR) >> 1;
+        double2 wr[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            const int idx = tid + q * NTC;
+            wr[q] = idx < pairs ? lds2(ws_a + 16u * (uint32_t)(pbase + idx)) : make_double2(0.0, 0.0);
+        }
+        if (XL) {
+            const double hc = hs[uhi + 1 - ulo] * xscale;
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) {
+                const int idx = tid + q * NTC;
+                if (idx < pairs) {
+                    const double2 x2 = lds2(xin_a + 16u * (uint32_t)(pbase + idx));
+                    wr[q].x = fma(-hc, x2.x, wr[q].x);
+                    wr[q].y = fma(-hc, x2.y, wr[q].y);
+                }
+            }
+        }
+        for (int col = uhi; col >= ulo; --col) {
+            const double hc = hs[col - ulo];
+            cx.wait_full();
+            const double2 *vt = reinterpret_cast<const double2 *>(cx.rg.ptr());
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) {
+                const int idx = tid + q * NTC;
+                if (idx < pairs) {
+                    const double2 v2 = vt[idx];
+                    wr[q].x = fma(-hc, v2.x, wr[q].x);
+                    wr[q].y = fma(-hc, v2.y, wr[q].y);
+                }
+            }
+            cx.release();
+        }
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            const int idx = tid + q * NTC;
+            if (idx < pairs) {
+                sts2(ws_a + 16u * (uint32_t)(pbase + idx), wr[q]);
+                xo2[pbase + idx] = wr[q];
+                nrm = fma(wr[q].x, wr[q].x, fma(wr[q].y, wr[q].y, nrm));
+            }
+        }
+    }
+    if (AUG && P.p > 0 && tid < P.p) {
+        double wt = S->wtail[tid];
+        if (XL) {
+            const double vt = S->xtail[tid] * xscale;  // tail of the resident column
+            wt = fma(-hs[uhi + 1 - ulo], vt, wt);
+            if (vlazy && tm.rank == 0) vlazy[P.n + tid] = vt;
+        }
+        for (int c = uhi; c >= ulo; --c) wt = fma(-hs[c - ulo], V[(long long)c * P.ldv + P.n + tid], wt);
+        S->wtail[tid] = wt;
+        if (tm.rank == 0) {
+            xout[P.n + P.nhalo + tid] = wt;
+            if (P.myrank == 0) nrm = fma(wt, wt, nrm);
+        }
+    }
+    return nrm;
+}
+
+// One problem on the consumer side, short-window (XL) instance.
+//
+// XL instance (short windows: Lanczos / IOP-q on a CSR-stream operator whose slice fits twice in shared memory):
+//   * two slice buffers: xin = unnormalised current basis vector (v_j = xin * xscale), ws = the new w; swapped per step;
+//   * mat-vec gathers own-slice columns from xin (shared memory) and accumulates <v_j, w> on the fly;
+//   * v_j is stored to V during the update phase of step j (one step late), the last column by an epilogue;
+//   * on one GPU both reductions of a step are packet all-reduces (ll_publish / ll_collect).
+// Measured per Lanczos step at C2 before / after: see DESIGN.md 3.1c.
+template <int OPK, bool AUG, bool XL, int GW>
+__device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGeom &G, Team &tm, int prob, int nlocal,
+                                 double *xb0, double *xb1, long long xoff0, long long part0, long long partn0) {
+    SmemTma *S = cx.S;
+    const int tid = cx.tid;
+    const int n = P.n, p = AUG ? P.p : 0;
+    double *V = P.V + (long long)prob * P.V_stride;
+    double *Hd = P.Hd + (long long)prob * P.H_stride;
+    const double *b = P.b + (long long)prob * P.b_stride;
+    const long long ldv = P.ldv;
+    const int ldh = P.ldh;
+    const int units = G.nrows >> 1;
+    const uint32_t stage_a = cx.xin_a;                // firststep! stages b in the x buffer
+    const double *xsrc;
+    double xscale;
+    int jstart;
+    int m_out = P.m, breakdown = 0;
+    const bool sharded = P.nranks > 1;
+    const bool via_xb0 = p > 0 || sharded;            // first gather source must carry tail / halo entries
+    const double *lpart = P.peer_part[P.myrank];      // this GPU's inboxes
+    const double *lpartn = P.peer_partn[P.myrank];
+    const int xt = n + P.nhalo;                       // offset of the augmented tail in the gather buffers
+    bool lazy_first = true;                           // XL: the first step's resident column still has to be stored
+    if (XL && nlocal == 0)                            // chunk flags are learnt once per launch (geometry only)
+        for (int c = tid; c < MAXCH2; c += NTC) S->chunk_local[c] = 1;
+
+    if (P.j0 == 0) {  // firststep! (arnoldi.jl:230-250 / 257-279)
+        double nrm = 0.0;
+        for (int i = tid; i < units; i += NTC) {
+            const double2 b2 = reinterpret_cast<const double2 *>(b + G.r0)[i];
+            sts2(stage_a + 16u * (uint32_t)i, b2);
+            if (via_xb0) reinterpret_cast<double2 *>(xb0 + G.r0)[i] = b2;
+            nrm = fma(b2.x, b2.x, fma(b2.y, b2.y, nrm));
+        }
+        if (p > 0 && tm.rank == 0 && tid < p) {
+            const double bt = P.btail[tid];
+            xb0[xt + tid] = bt;
+            if (P.myrank == 0) nrm = fma(bt, bt, nrm);
+        }
+        const long long pslot = partn0 + (long long)(2 + (nlocal & 1)) * P.cpad;
+        block_sum_to_c(P, cx, nrm, pslot + tm.rank);
+        if (XL && sharded) {  // push_halo reads the staged slice through cx.ws
+            double *t = cx.ws; cx.ws = cx.xin; push_halo(P, cx, G, tm, xoff0); cx.ws = t;
+        } else {
+            push_halo(P, cx, G, tm, xoff0);
+        }
+        team_reduce_c(P, cx, tm, lpartn + pslot, 1, S->bc, sharded);
+        const double beta = sqrt(S->bc[0]);
+        if (tm.rank == 0 && tid == 0) P.scal[prob * 4] = beta;
+        if (beta == 0.0) {
+            if (tm.rank == 0 && tid == 0) {
+                P.stat[prob * 4 + 0] = P.m;
+                P.stat[prob * 4 + 1] = 0;
+            }
+            return;
+        }
+        xsrc = via_xb0 ? xb0 : b;  // v_1 = b / beta is stored by the first step's update phase
+        xscale = 1.0 / beta;
+        jstart = 1;
+    } else {
+        const double *vj = V + (long long)(P.j0 - 1) * ldv;
+        if (sharded) {  // the resumed column has no halo: stage it in the gather buffer and push the halo
+            for (int i = tid; i < units; i += NTC) {
+                const double2 v2 = reinterpret_cast<const double2 *>(vj + G.r0)[i];
+                sts2(stage_a + 16u * (uint32_t)i, v2);
+                reinterpret_cast<double2 *>(xb0 + G.r0)[i] = v2;
+            }
+            if (p > 0 && tm.rank == 0 && tid < p) xb0[xt + tid] = vj[n + tid];
+            block_sum_to_c(P, cx, 0.0, partn0 + 2LL * P.cpad + tm.rank);  // (has the CTA barrier the push needs)
+            if (XL) {
+                double *t = cx.ws; cx.ws = cx.xin; push_halo(P, cx, G, tm, xoff0); cx.ws = t;
+            } else {
+                push_halo(P, cx, G, tm, xoff0);
+            }
+            team_reduce_c(P, cx, tm, lpartn + partn0 + 2LL * P.cpad, 1, S->bc, true);  // every GPU's halo is in place
+            xsrc = xb0;
+        } else {
+            if (XL) {
+                for (int i = tid; i < units; i += NTC)
+                    sts2(stage_a + 16u * (uint32_t)i, reinterpret_cast<const double2 *>(vj + G.r0)[i]);
+                consumer_sync();
+            }
+            xsrc = vj;
+        }
+        lazy_first = false;  // the resumed column is already in V
+        xscale = 1.0;
+        jstart = P.j0;
+    }
+
+    double beta_prev = 0.0;
+    const int iopw = P.iop > 0 ? P.iop : P.m;
+    for (int j = jstart; j <= P.m; ++j) {
+        const int jc = j - 1;
+        const int par = j & 1;
+        double *xout = par ? xb1 : xb0;
+        const long long xoff = xoff0 + (par ? P.xlen : 0);
+        const long long part = part0 + (long long)par * MAXCOL * P.cpad;
+        const long long partn = partn0 + (long long)par * P.cpad;
+        const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
+        const int hi = jc;
+        const int nc = hi - lo + 1;
+        const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
+
+        PT_MARK(blockIdx.x, j, 0);
+        const double selfacc = matvec_xl<AUG, GW>(P, cx, G, xsrc, xscale, nlocal == 0 && j == jstart, j);
+        PT_MARK(blockIdx.x, j, 1);
+
+        double beta;
+        {
+            const bool use_ll = !sharded && nc <= LLQ;
+            // <v_jc, w> was accumulated by the mat-vec (unscaled); its block reduction is also the barrier that
+            // completes the w slice.  Columns lo..jc-1 come through the ring as before.
+            {
+                const double v = warp_sum(selfacc);
+                if (cx.lane == 0) S->redn[cx.warp] = v;
+                consumer_sync();
+                if (cx.warp == 0) {  // (every lane computes the same sum)
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) s += S->redn[w];
+                    s *= xscale * xscale;
+                    if (AUG && p > 0 && tm.rank == 0 && P.myrank == 0)
+                        for (int kk = 0; kk < p; ++kk) s = fma(S->xtail[kk] * xscale, S->wtail[kk], s);
+                    if (use_ll) ll_publish_warp(P, cx.team, tm, cx.seq + 1u, nc - 1, s, cx.lane, false);
+                    else if (cx.lane == 0) P.peer_part[P.myrank][part + (long long)(nc - 1) * P.cpad + tm.rank] = s;
+                }
+            }
+            if (nc > 1) dots_phase_xl<OPK, AUG, XL>(P, cx, G, tm, V, lo, hi - 1, part, use_ll);
+            PT_MARK(blockIdx.x, j, 2);
+            if (use_ll) ll_collect(P, cx, tm, nc, S->hs + (lo - ulo), false);
+            else team_reduce_c(P, cx, tm, lpart + part, nc, S->hs + (lo - ulo), false);
+            PT_MARK(blockIdx.x, j, 3);
+            if (tm.rank == 0)
+                for (int ci = tid; ci < nc; ci += NTC) Hd[(long long)jc * ldh + lo + ci] = S->hs[lo + ci - ulo];
+            if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = beta_prev;
+            consumer_sync();
+
+            double *vlazy = (j > jstart || lazy_first) ? V + (long long)jc * ldv : nullptr;
+            const double nrm = update_phase_xl<OPK, AUG, XL>(P, cx, G, tm, V, ulo, hi - 1, xout, xscale, vlazy);
+            PT_MARK(blockIdx.x, j, 4);
+            // block reduction of the squared norm; the release fence covers exactly the gather-buffer stores
+            {
+                const double v = warp_sum(nrm);
+                if (cx.lane == 0) S->redn[cx.warp] = v;
+                consumer_sync();
+                if (cx.warp == 0) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) s += S->redn[w];
+                    if (!sharded) ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 0, s, cx.lane, true);
+                    else if (cx.lane == 0) P.peer_partn[P.myrank][partn + tm.rank] = s;
+                }
+            }
+            PT_MARK(blockIdx.x, j, 7);
+            if (sharded) push_halo(P, cx, G, tm, xoff);
+            // the resident column v_jc = xin * xscale goes to V now, one step late: its stores overlap the wait
+            // for the norm instead of forming a phase of their own behind it
+            if (vlazy) {
+                const uint32_t xin_a = cx.xin_a;
+                double2 *vl2 = reinterpret_cast<double2 *>(vlazy + G.r0);
+                for (int i = tid; i < units; i += NTC) {
+                    const double2 x2 = lds2(xin_a + 16u * (uint32_t)i);
+                    vl2[i] = make_double2(x2.x * xscale, x2.y * xscale);
+                }
+                fence_proxy_async();  // fetched by this CTA's TMA producer in later steps
+            }
+            PT_MARK(blockIdx.x, j, 8);
+            if (!sharded) ll_collect(P, cx, tm, 1, S->bc, true);
+            else team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, true);
+            if (tid == 0) S->cols_ready = jc + 1;
+            PT_MARK(blockIdx.x, j, 5);
+            beta = sqrt(S->bc[0]);
+            if (tm.rank == 0 && tid == 0) Hd[(long long)jc * ldh + jc + 1] = beta;
+            {  // the new w becomes the resident vector of the next step
+                double *t = cx.ws;
+                cx.ws = cx.xin;
+                cx.xin = t;
+                const uint32_t ta = cx.ws_a;
+                cx.ws_a = cx.xin_a;
+                cx.xin_a = ta;
+            }
+            PT_MARK(blockIdx.x, j, 6);
+        }
+        xsrc = xout;
+        xscale = 1.0 / beta;
+        beta_prev = beta;
+        if (beta < P.tol) {
+            m_out = j;
+            breakdown = 1;
+        }
+        if (XL && (breakdown || j == P.m)) {
+            // epilogue: the last column v_{j+1} = w / beta (true division: beta may be tiny on breakdown,
+            // arnoldi.jl:306 runs before the breakdown test)
+            double *vn = V + (long long)(jc + 1) * ldv;
+            const uint32_t xin_a = cx.xin_a;
+            for (int i = tid; i < units; i += NTC) {
+                double2 w2 = lds2(xin_a + 16u * (uint32_t)i);
+                w2.x /= beta;
+                w2.y /= beta;
+                reinterpret_cast<double2 *>(vn + G.r0)[i] = w2;
+            }
+            if (p > 0 && tm.rank == 0 && tid < p) vn[n + tid] = S->wtail[tid] / beta;
+        }
+        if (breakdown) break;
+    }
+    if (tm.rank == 0 && tid == 0) {
+        P.stat[prob * 4 + 0] = m_out;
+        P.stat[prob * 4 + 1] = breakdown;
+    }
+}
+
 // One instance per (operator kind, augmented or not): the persistent kernel is sensitive to code size (an unused
 // extra mat-vec loop cost 3-5 % everywhere), so each instance carries only the paths it can take.
-template <int OPK, bool AUG>
+template <int OPK, bool AUG, bool XL, int GW = 8>
 __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constant__ KrylovParams P,
                                                             const __grid_constant__ CUtensorMap tmA) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemTma *S = reinterpret_cast<SmemTma *>(smem_raw);
     const size_t ws_bytes = P.w_in_smem ? (((size_t)P.slice * 8 + 127) & ~(size_t)127) : 0;
     double *ws_smem = reinterpret_cast<double *>(smem_raw + sizeof(SmemTma));
-    unsigned char *ring = smem_raw + sizeof(SmemTma) + ws_bytes;
+    unsigned char *ring = smem_raw + sizeof(SmemTma) + ws_bytes * (XL ? 2 : 1);
 
     const int tid = threadIdx.x;
     const int team = blockIdx.x / P.team_size;
@@ -808,6 +1402,10 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
     Cons cx;
     cx.S = S;
     cx.ws = P.w_in_smem ? ws_smem : (P.wglob + (long long)team * P.n + G.r0);
+    cx.xin = XL ? ws_smem + ws_bytes / 8 : nullptr;
+    cx.ws_a = smem_u32(ws_smem);
+    cx.xin_a = cx.ws_a + (uint32_t)ws_bytes;
+    cx.team = team;
     cx.tid = tid;
     cx.lane = tid & 31;
     cx.warp = tid >> 5;
@@ -820,12 +1418,13 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
             if (tid == NTC) {
                 Ring rg{ring, P.nslot, 0, 0u};
                 unsigned issued = 0;
-                producer_problem<OPK, AUG>(P, &tmA, S, rg, G, P.V + (long long)prob * P.V_stride, nlocal + 1, issued, 0);
+                producer_problem<OPK, AUG, XL>(P, &tmA, S, rg, G, P.V + (long long)prob * P.V_stride, nlocal + 1, issued, 0);
             }
             __syncwarp();
         } else {
             cx.rg = Ring{ring, P.nslot, 0, 0u};
-            consumer_problem<OPK, AUG>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
+            if constexpr (XL) consumer_problem_xl<OPK, AUG, true, GW>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
+            else consumer_problem<OPK, AUG>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
             consumer_sync();
             if (tid == 0) S->stop_seq = nlocal + 1;
         }

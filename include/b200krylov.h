@@ -264,7 +264,8 @@ int b200k_last_timing(b200k_handle_t h, float *krylov_ms, float *project_ms);
 /* Enable (1) / disable (0) the event timing above; off by default. */
 int b200k_set_timing(b200k_handle_t h, int enabled);
 /* Which Krylov kernel the last factorisation used: 1 = LDG kernel (krylov_persistent_kernel, any layout),
- * 2 = TMA-ring kernel (krylov_tma_kernel; needs even n / ldv and 16-byte aligned bases).  The environment
+ * 2 = TMA-ring kernel (krylov_tma_kernel; needs even n / ldv and 16-byte aligned bases), 3 = complex kernel,
+ * 4 = the short-window (Lanczos / IOP) instance of the TMA-ring kernel (resident basis vector).  The environment
  * variable B200K_KERNEL=ldg, read at b200k_create, forces 1 (A/B measurements). */
 int b200k_last_kernel(b200k_handle_t h, int *which);
 /* Runtime switches (A/B measurements and tests): B200K_FLAG_FORCE_LDG = 1 uses krylov_persistent_kernel even
@@ -274,6 +275,8 @@ int b200k_last_kernel(b200k_handle_t h, int *which);
 #define B200K_FLAG_HOST_SMALLEXP 2
 #define B200K_FLAG_L2HINT 3 /* L2::evict_first on the CSR operator stream: -1 automatic (default: only in steps
                                whose working set exceeds the L2), 0 never, 1 always */
+#define B200K_FLAG_NO_XL 4  /* 1: never use the short-window (Lanczos / IOP) instance of the TMA-ring kernel that keeps
+                               the current basis vector in shared memory and reduces with packet all-reduces */
 int b200k_set_flag(b200k_handle_t h, int flag, int value);
 
 #ifdef __cplusplus

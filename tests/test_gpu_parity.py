@@ -277,6 +277,63 @@ def test_kernel_variants_agree(gpu, oracle):
     assert np.abs(K1.getH() - K2.getH()).max() < 1e-12
 
 
+def test_short_window_instance_xl(gpu, oracle):
+    """The short-window (XL) instance of the TMA-ring kernel -- resident basis vector in shared memory, inner product
+    fused into the mat-vec, lazily stored basis columns, packet all-reduces -- against the general instance and
+    the oracle: Lanczos, IOP-2, IOP-6 (window wider than one packet set), continuation, kiops, a batch."""
+    eng = gpu.get_engine()
+    A = convdiff2d(130, 90)
+    L = laplacian2d(130, 90)
+    n = 130 * 90
+    b = np.random.default_rng(5).standard_normal(n)
+    opA, opL = gpu.operator(A), gpu.operator(L)
+    res = {}
+    try:
+        for no_xl in (False, True):
+            eng.set_flag("no_xl", no_xl)
+            want = "tma" if no_xl else "tma_xl"
+            r = {}
+            Ks = gpu.arnoldi(opL, b, m=30)  # Hermitian -> lanczos!
+            assert eng.last_kernel() == want
+            r["lan_H"], r["lan_V"], r["lan_beta"] = Ks.getH().copy(), Ks.getV().cpu().numpy().copy(), Ks.beta
+            r["lan_w"] = gpu.expv(0.8, opL, b, m=30)
+            for q in (2, 6):
+                Ks = gpu.arnoldi(opA, b, m=30, iop=q)
+                assert eng.last_kernel() == want
+                r[f"iop{q}_H"], r[f"iop{q}_V"] = Ks.getH().copy(), Ks.getV().cpu().numpy().copy()
+                r[f"iop{q}_w"] = gpu.expv(0.8, opA, b, m=30, iop=q)
+            Ks = gpu.KrylovSubspace(n, 20)
+            gpu.arnoldi_(Ks, opA, b, m=10, iop=3)
+            gpu.arnoldi_(Ks, opA, b, m=20, iop=3, init=10)
+            r["cont_H"], r["cont_V"] = Ks.getH().copy(), Ks.getV().cpu().numpy().copy()
+            u = np.stack([b, 0.3 * b[::-1]], 1)
+            for herm in (True, False):
+                w, st = gpu.kiops(1.0, opL if herm else opA, u, ishermitian=herm)
+                r[f"kiops{int(herm)}"], r[f"kiops{int(herm)}_st"] = w, st
+            Bm = np.random.default_rng(6).standard_normal((n, 5))
+            r["batch"] = gpu.expv_batched([0.2, 0.4, 0.6, 0.8, 1.0], opL, Bm, m=25)
+            res[no_xl] = r
+    finally:
+        eng.set_flag("no_xl", False)
+    x, g = res[False], res[True]
+    for k in x:
+        if k.endswith("_st"):
+            assert x[k] == g[k], k
+        elif k == "lan_beta":
+            assert abs(x[k] - g[k]) <= 1e-14 * abs(g[k])
+        else:
+            assert relerr(x[k], g[k]) < 1e-11, (k, relerr(x[k], g[k]))
+    assert relerr(x["lan_w"], oracle.expv(0.8, L, b, m=30)) < RTOL
+    assert relerr(x["iop2_w"], oracle.expv(0.8, A, b, m=30, iop=2)) < RTOL
+    assert relerr(x["iop6_w"], oracle.expv(0.8, A, b, m=30, iop=6)) < RTOL
+    Ko = oracle.arnoldi(A, b, m=20, iop=3)
+    assert np.abs(x["cont_H"] - Ko.getH()).max() < 1e-10
+    # orthonormality of neighbouring Lanczos vectors and the three-term relation A V_m = V_{m+1} H
+    V, H = x["lan_V"], x["lan_H"]
+    assert np.abs(V[:, :5].T @ V[:, :5] - np.eye(5)).max() < 1e-12
+    assert relerr(L @ V[:, :30], V @ H) < 1e-12
+
+
 def test_device_small_exp_branches(gpu, oracle):
     """Fused expv (device Pade) across the Pade orders: scale t so that ||tH|| hits C3..C13 and several squarings."""
     A = convdiff2d(60, 50)
@@ -365,7 +422,7 @@ def test_edge_layouts_and_breakdown_in_stream_mode(gpu, oracle):
     for herm in (True, False):
         Ks = gpu.arnoldi(Dg, bn, m=30, ishermitian=herm)
         Ko = oracle.arnoldi(Dg, bn, m=30, ishermitian_=herm)
-        assert eng.last_kernel() == "tma"
+        assert eng.last_kernel() == ("tma_xl" if herm else "tma")
         assert Ks.m == Ko.m == 3 and Ks.wasbreakdown
         w = gpu.expv(0.9, Dg, bn, m=30, ishermitian=herm)
         assert relerr(w, np.exp(0.9 * d) * bn) < 1e-9
