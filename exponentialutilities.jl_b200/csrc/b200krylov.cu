@@ -2441,6 +2441,7 @@ int b200k_debug_phase_ts(long long *out, long long count) {
     if (count > total) count = total;
     return (int)cudaMemcpyFromSymbol(out, g_phase_ts, (size_t)count * 8);
 }
+int b200k_debug_se_ts(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_se_ts, 16 * 8); }
 #endif
 
 }  // extern "C"

@@ -297,7 +297,8 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
         // XL: column jc is the shared-memory resident vector -- no tiles for it in either pass
         const int hi = XL ? jc - 1 : jc;
-        const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
+        // (XL Lanczos: v_{j-1} is folded into the mat-vec out of shared memory -- the ring carries the operator only)
+        const int ulo = (XL && P.lanczos) ? jc : ((P.lanczos && jc >= 1) ? jc - 1 : lo);
         for (int cb = lo; cb <= hi && !stopped; cb += CB) {
             const int nb = min(CB, hi - cb + 1);
             for (int k = 0; k < G.ntk && !stopped; ++k) {
@@ -451,7 +452,7 @@ __device__ __forceinline__ void push_halo(const KrylovParams &P, Cons &cx, const
 // address arithmetic; which chunks those are is learnt by the first mat-vec of a launch (`learn`).
 template <bool AUG, int GW>
 __device__ double matvec_xl(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *xsrc, double xscale,
-                            bool learn, int pt_step = 0) {
+                            bool learn, bool fold, double foldc, int pt_step = 0) {
     double selfacc = 0.0;
     SmemTma *S = cx.S;
     const int tid = cx.tid;
@@ -535,8 +536,14 @@ __device__ double matvec_xl(const KrylovParams &P, Cons &cx, const TmaGeom &G, c
                 const double *brow = P.Bm + (G.r0 + rl);
                 for (int k = 0; k < p; ++k) sum = fma(brow[(long long)k * P.ldb], S->xtail[k], sum);
             }
-            selfacc = fma(lds1(xin_a + 8u * (uint32_t)rl), sum, selfacc);
-            sts1(ws_a + 8u * (uint32_t)rl, sum * xscale);
+            // Lanczos: the output buffer still holds the unnormalised v_{j-1} (it was the resident vector of the
+            // previous step) and beta_{j-1} is known, so its term of the three-term recurrence is subtracted here,
+            // by the thread that overwrites the entry -- no basis tile, no second pass.  The inner product with
+            // v_j is taken before that, as lanczos_step! does (arnoldi.jl:396-399).
+            double wv = sum * xscale;
+            selfacc = fma(lds1(xin_a + 8u * (uint32_t)rl), wv, selfacc);
+            if (fold) wv = fma(-foldc, lds1(ws_a + 8u * (uint32_t)rl), wv);
+            sts1(ws_a + 8u * (uint32_t)rl, wv);
         }
         if (learn && c < MAXCH2) {
             if (!__all_sync(0xffffffffu, loc) && cx.lane == 0) S->chunk_local[c] = 0;
@@ -1084,7 +1091,7 @@ __device__ double update_phase_xl(const KrylovParams &P, Cons &cx, const TmaGeom
                 }
             }
         }
-        for (int col = uhi; col >= ulo; --col) {
+        for (int col = P.lanczos ? ulo - 1 : uhi; col >= ulo; --col) {  // (Lanczos: v_{j-1} was folded into the mat-vec)
             const double hc = hs[col - ulo];
             cx.wait_full();
             const double2 *vt = reinterpret_cast<const double2 *>(cx.rg.ptr());
@@ -1223,7 +1230,7 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
         jstart = P.j0;
     }
 
-    double beta_prev = 0.0;
+    double beta_prev = 0.0, xscale_prev = 0.0;
     const int iopw = P.iop > 0 ? P.iop : P.m;
     for (int j = jstart; j <= P.m; ++j) {
         const int jc = j - 1;
@@ -1238,7 +1245,9 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
 
         PT_MARK(blockIdx.x, j, 0);
-        const double selfacc = matvec_xl<AUG, GW>(P, cx, G, xsrc, xscale, nlocal == 0 && j == jstart, j);
+        const bool fold = P.lanczos && j > jstart;  // (the first step has no v_{j-1}: lanczos! restarts the recurrence)
+        const double selfacc = matvec_xl<AUG, GW>(P, cx, G, xsrc, xscale, nlocal == 0 && j == jstart, fold,
+                                                  beta_prev * xscale_prev, j);
         PT_MARK(blockIdx.x, j, 1);
 
         double beta;
@@ -1254,7 +1263,7 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
                     double s = 0.0;
 #pragma unroll
                     for (int w = 0; w < NW; ++w) s += S->redn[w];
-                    s *= xscale * xscale;
+                    s *= xscale;
                     if (AUG && p > 0 && tm.rank == 0 && P.myrank == 0)
                         for (int kk = 0; kk < p; ++kk) s = fma(S->xtail[kk] * xscale, S->wtail[kk], s);
                     if (use_ll) ll_publish_warp(P, cx.team, tm, cx.seq + 1u, nc - 1, s, cx.lane, false);
@@ -1289,8 +1298,10 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
             }
             PT_MARK(blockIdx.x, j, 7);
             if (sharded) push_halo(P, cx, G, tm, xoff);
-            // the resident column v_jc = xin * xscale goes to V now, one step late: its stores overlap the wait
-            // for the norm instead of forming a phase of their own behind it
+            // the resident column v_jc = xin * xscale goes to V now, one step late, between publishing this CTA's
+            // norm partial and collecting everybody's: the stores overlap the packet flight time.  (After the
+            // collect they cost 2.2k cycles of their own per step -- measured; in front of the release fence
+            // they would have to drain before the packets may leave.)
             if (vlazy) {
                 const uint32_t xin_a = cx.xin_a;
                 double2 *vl2 = reinterpret_cast<double2 *>(vlazy + G.r0);
@@ -1298,13 +1309,13 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
                     const double2 x2 = lds2(xin_a + 16u * (uint32_t)i);
                     vl2[i] = make_double2(x2.x * xscale, x2.y * xscale);
                 }
-                fence_proxy_async();  // fetched by this CTA's TMA producer in later steps
+                if (!P.lanczos) fence_proxy_async();  // fetched by this CTA's TMA producer in later steps
             }
             PT_MARK(blockIdx.x, j, 8);
             if (!sharded) ll_collect(P, cx, tm, 1, S->bc, true);
             else team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, true);
-            if (tid == 0) S->cols_ready = jc + 1;
             PT_MARK(blockIdx.x, j, 5);
+            if (tid == 0) S->cols_ready = jc + 1;
             beta = sqrt(S->bc[0]);
             if (tm.rank == 0 && tid == 0) Hd[(long long)jc * ldh + jc + 1] = beta;
             {  // the new w becomes the resident vector of the next step
@@ -1318,6 +1329,7 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
             PT_MARK(blockIdx.x, j, 6);
         }
         xsrc = xout;
+        xscale_prev = xscale;
         xscale = 1.0 / beta;
         beta_prev = beta;
         if (beta < P.tol) {

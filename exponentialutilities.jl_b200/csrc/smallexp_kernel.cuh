@@ -7,7 +7,7 @@
 // Algorithm = exponential!(A, ExpMethodHigham2005Base()) of the reference (src/exp_baseexp.jl:112-161), as in
 // smallmat.hpp: balance (power-of-two diagonal scaling; the permutation phase of xGEBAL is skipped -- it is
 // the identity for an unreduced Hessenberg matrix) -> 1-norm switch Pade 3/5/7/9/13 (generic even/odd power
-// loop) -> LU solve with partial pivoting -> squaring -> unbalance.  The reference takes an eigen-decomposition
+// loop) -> LU solve with (implicit) partial pivoting -> squaring -> unbalance.  The reference takes an eigen-decomposition
 // branch when H is exactly symmetric (krylov_phiv.jl:225-229); on the device the Pade path is used for both
 // (agrees with the eigen branch to rounding, see tests); the host path b200k_expv_ks keeps both branches.
 #pragma once
@@ -15,8 +15,31 @@
 
 namespace b200k {
 
+#ifdef B200K_PHASE_TIMING
+__device__ long long g_se_ts[16];
+#define SE_MARK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_se_ts[k] = clock64(); } while (0)
+#else
+#define SE_MARK(k) do { } while (0)
+#endif
+
+__device__ __forceinline__ double se_lds(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void se_sts(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
 constexpr int SE_NT = 1024;
 constexpr int SE_MAXM = 48;  // 6 m^2 doubles of shared memory (110 KB at m = 48)
+
+// Pade coefficient tuples of exp_baseexp.jl:65-77, concatenated: [C3 | C5 | C7 | C9 | C13]
+__constant__ double SE_PADE[4 + 6 + 8 + 10 + 14] = {
+    120.0, 60.0, 12.0, 1.0,
+    30240.0, 15120.0, 3360.0, 420.0, 30.0, 1.0,
+    17297280.0, 8648640.0, 1995840.0, 277200.0, 25200.0, 1512.0, 56.0, 1.0,
+    17643225600.0, 8821612800.0, 2075673600.0, 302702400.0, 30270240.0, 2162160.0, 110880.0, 3960.0, 90.0, 1.0,
+    64764752532480000.0, 32382376266240000.0, 7771770303897600.0, 1187353796428800.0, 129060195264000.0,
+    10559470521600.0, 670442572800.0, 33522128640.0, 1323241920.0, 40840800.0, 960960.0, 16380.0, 182.0, 1.0};
 
 struct SmallExpParams {
     const double *Hd;   // [nprob][ldh * (hcols)] device H written by the Krylov kernel
@@ -35,14 +58,34 @@ struct SmallExpParams {
     int *err;            // set to 1 if a Pade denominator is singular
 };
 
+// C = A * B, column-major n x n in shared memory, on the fp64 tensor-core path: one warp per 8 x 8 output tile,
+// mma.sync.m8n8k4.f64 over k (zero-padded at the edges by predicated loads).  The scalar version (one thread per
+// entry, 2 LDS per FMA) was shared-memory-bandwidth bound: 4.2k cycles per 30 x 30 product, nine of them per
+// exponential; this one needs 2 LDS per 256 FMAs.  Fragment layout (PTX ISA, m8n8k4 .f64): A[g][t], B[t][g],
+// C[g][2t], C[g][2t+1] with g = lane / 4, t = lane % 4.  Summation order differs from the scalar loop (rounding).
 __device__ __forceinline__ void se_matmul(int n, const double *A, const double *B, double *C) {
-    // C = A * B, column-major n x n in shared memory; thread -> (i, j)
-    for (int idx = threadIdx.x; idx < n * n; idx += SE_NT) {
-        const int i = idx % n, j = idx / n;
-        double s = 0.0;
-#pragma unroll 6
-        for (int k = 0; k < n; ++k) s = fma(A[k * n + i], B[j * n + k], s);
-        C[idx] = s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int nt = (n + 7) >> 3;
+    for (int tile = warp; tile < nt * nt; tile += SE_NT / 32) {
+        const int ti = tile % nt, tj = tile / nt;
+        const int row = ti * 8 + g;          // row of the A fragment / of both C entries
+        const int colb = tj * 8 + g;         // column of the B fragment
+        double c0 = 0.0, c1 = 0.0;
+        const bool rok = row < n, cok = colb < n;
+        for (int k0 = 0; k0 < n; k0 += 4) {
+            const int k = k0 + t;
+            const double a = (rok && k < n) ? A[k * n + row] : 0.0;
+            const double b = (cok && k < n) ? B[colb * n + k] : 0.0;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(c0), "+d"(c1)
+                         : "d"(a), "d"(b));
+        }
+        const int cc = tj * 8 + 2 * t;
+        if (rok) {
+            if (cc < n) C[cc * n + row] = c0;
+            if (cc + 1 < n) C[(cc + 1) * n + row] = c1;
+        }
     }
     __syncthreads();
 }
@@ -51,11 +94,11 @@ __device__ __forceinline__ void se_matmul(int n, const double *A, const double *
 // Returns a pointer (into sm) to the exponential of the BALANCED matrix: exp(A)[i, j] = sc[i] * X[i, j] / sc[j];
 // nullptr if the Pade denominator is singular.  `full` = all columns are needed (otherwise only column 0).
 __device__ double *se_expm_core(int n, double *sm, double *sc, double *colsum, bool full) {
-    __shared__ double s_nA;
-    __shared__ int s_piv, s_flag;
+    __shared__ int s_cfg[3];
     const int tid = threadIdx.x;
     const int nn = n * n;
     double *A = sm, *A2 = sm + nn, *Pm = sm + 2 * nn, *U = sm + 3 * nn, *V = sm + 4 * nn, *T = sm + 5 * nn;
+    SE_MARK(1);
     if (tid < n) sc[tid] = 1.0;
     __syncthreads();
 
@@ -121,6 +164,7 @@ __device__ double *se_expm_core(int n, double *sm, double *sc, double *colsum, b
     }
     __syncthreads();
 
+    SE_MARK(2);
     // ---- nA = opnorm(A, 1) ----
     if (tid < n) {
         double s = 0.0;
@@ -128,43 +172,39 @@ __device__ double *se_expm_core(int n, double *sm, double *sc, double *colsum, b
         colsum[tid] = s;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {  // 1-norm, Pade order and number of squarings: one thread, broadcast through shared memory
         double best = 0.0;
         for (int j = 0; j < n; ++j)
             if (colsum[j] > best || colsum[j] != colsum[j]) best = colsum[j];
-        s_nA = best;
+        int off, N_, si_ = 0;
+        if (best <= 2.1) {
+            if (best > 0.95) { off = 18; N_ = 10; }
+            else if (best > 0.25) { off = 10; N_ = 8; }
+            else if (best > 0.015) { off = 4; N_ = 6; }
+            else { off = 0; N_ = 4; }
+        } else {
+            off = 28;
+            N_ = 14;
+            const double s2 = log2(best / 5.4);
+            if (s2 > 0) si_ = (int)ceil(s2);
+        }
+        s_cfg[0] = off;
+        s_cfg[1] = N_;
+        s_cfg[2] = si_;
     }
     __syncthreads();
-    const double nA = s_nA;
-    const double C3[] = {120.0, 60.0, 12.0, 1.0};
-    const double C5[] = {30240.0, 15120.0, 3360.0, 420.0, 30.0, 1.0};
-    const double C7[] = {17297280.0, 8648640.0, 1995840.0, 277200.0, 25200.0, 1512.0, 56.0, 1.0};
-    const double C9[] = {17643225600.0, 8821612800.0, 2075673600.0, 302702400.0, 30270240.0,
-                         2162160.0, 110880.0, 3960.0, 90.0, 1.0};
-    const double C13[] = {64764752532480000.0, 32382376266240000.0, 7771770303897600.0, 1187353796428800.0,
-                          129060195264000.0, 10559470521600.0, 670442572800.0, 33522128640.0, 1323241920.0,
-                          40840800.0, 960960.0, 16380.0, 182.0, 1.0};
-    const double *C;
-    int N, si = 0;
-    if (nA <= 2.1) {
-        if (nA > 0.95) { C = C9; N = 10; }
-        else if (nA > 0.25) { C = C7; N = 8; }
-        else if (nA > 0.015) { C = C5; N = 6; }
-        else { C = C3; N = 4; }
-    } else {
-        C = C13;
-        N = 14;
-        const double s = log2(nA / 5.4);
-        if (s > 0) {
-            si = (int)ceil(s);
-            const double f = ldexp(1.0, si);
-            for (int idx = tid; idx < nn; idx += SE_NT) A[idx] /= f;
-            __syncthreads();
-        }
+    const double *C = SE_PADE + s_cfg[0];
+    const int N = s_cfg[1], si = s_cfg[2];
+    if (si > 0) {
+        const double f = ldexp(1.0, si);
+        for (int idx = tid; idx < nn; idx += SE_NT) A[idx] /= f;
+        __syncthreads();
     }
 
+    SE_MARK(3);
     // ---- Pade numerator / denominator (generic even/odd power loop, exp_baseexp.jl:84-105) ----
     se_matmul(n, A, A, A2);
+    SE_MARK(4);
     for (int idx = tid; idx < nn; idx += SE_NT) {
         const double p = (idx % n == idx / n) ? 1.0 : 0.0;
         Pm[idx] = p;
@@ -182,6 +222,7 @@ __device__ double *se_expm_core(int n, double *sm, double *sc, double *colsum, b
         }
         __syncthreads();
     }
+    SE_MARK(5);
     se_matmul(n, A, U, T);  // U = A * U  (in T)
     // X (in A) = V + U ; D (in A2) = V - U
     for (int idx = tid; idx < nn; idx += SE_NT) {
@@ -191,76 +232,122 @@ __device__ double *se_expm_core(int n, double *sm, double *sc, double *colsum, b
     }
     __syncthreads();
 
+    SE_MARK(6);
     // ---- LU with partial pivoting on D (A2), applied to the right-hand sides X (A) ----
+    // Pivoting is IMPLICIT: rows are never swapped, a row that has served as pivot is skipped from then on, and the
+    // pivot sequence is remembered for the back substitution.  Per step: warp 0 finds the pivot (arg-max of |.| on
+    // the INTEGER image of the doubles -- monotone for non-negative values -- because fp64 compares are scarce on
+    // this SM: 32 warps each doing the search redundantly cost 1400 cycles per step, measured) and its reciprocal,
+    // publishes both through shared memory; then thread (row = lane, column group = warp) eliminates, loading
+    // everything it needs before its first store.  The pivot row and column k are not written during step k.
+    // Same arithmetic as xGETF2/xGETRS: multipliers l_ik = D(i,k) * (1 / D(p,k)), partial pivoting by max |.|.
+    // (History: warp-0 search + physical swap + idx % rows: ~2500 cycles per step; this: see profiles/.)
     double *D = A2, *X = A;
-    for (int k = 0; k < n; ++k) {
-        if (tid < 32) {
-            double best = -1.0;
-            int bi = k;
-            for (int i = k + tid; i < n; i += 32) {
-                const double v = fabs(D[k * n + i]);
-                if (v > best) { best = v; bi = i; }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            if (tid == 0) {
-                s_piv = bi;
-                s_flag = (best == 0.0 || best != best) ? 1 : 0;
-            }
-        }
-        __syncthreads();
-        if (s_flag) return nullptr;  // singular Pade denominator (uniform for the CTA)
-        const int pv = s_piv;
-        if (pv != k) {  // swap rows k and pv of D and X
-            for (int j = tid; j < 2 * n; j += SE_NT) {
-                double *M = j < n ? D : X;
-                const int jj = j < n ? j : j - n;
-                const double a = M[jj * n + k];
-                M[jj * n + k] = M[jj * n + pv];
-                M[jj * n + pv] = a;
-            }
-            __syncthreads();
-        }
-        // trailing update of D (columns k+1..) and forward elimination of X (all columns); the multipliers
-        // l_ik = D(i,k) / D(k,k) are applied on the fly (L itself is not needed afterwards)
-        const double inv = 1.0 / D[k * n + k];
-        const int rows = n - k - 1;
-        for (int idx = tid; idx < rows * (rows + n); idx += SE_NT) {
-            const int i = k + 1 + idx % rows;
-            const int jc = idx / rows;
-            const double l = D[k * n + i] * inv;
-            if (jc < rows) {
-                const int j = k + 1 + jc;
-                D[j * n + i] = fma(-l, D[j * n + k], D[j * n + i]);
-            } else {
-                const int j = jc - rows;
-                X[j * n + i] = fma(-l, X[j * n + k], X[j * n + i]);
-            }
-        }
-        __syncthreads();
-    }
-    // back substitution U x = y: sequential in k, parallel over (row, right-hand side).  Only column 0 is
-    // needed when no squaring follows.
     const int nrhs = (si > 0 || full) ? n : 1;
-    for (int k = n - 1; k >= 0; --k) {
-        const double dkk = D[k * n + k];
-        for (int j = tid; j < nrhs; j += SE_NT) X[j * n + k] /= dkk;
+    __shared__ int s_pivrow[SE_MAXM];     // s_pivrow[k] = row used as the k-th pivot
+    __shared__ int s_pivpos[SE_MAXM];     // inverse: s_pivpos[row] = k, -1 while the row is still active
+    __shared__ double s_rdiag[SE_MAXM];   // 1 / U(k, k)
+    __shared__ int s_pv;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = SE_NT / 32;
+    if (tid < SE_MAXM) s_pivpos[tid] = -1;
+    __syncthreads();
+    const uint32_t sm_a = (uint32_t)__cvta_generic_to_shared(sm);
+    for (int k = 0; k < n; ++k) {
+        if (k == 5) SE_MARK(11);
+        const uint32_t dk_a = sm_a + 8u * (uint32_t)(nn + k * n);  // column k of D
+        if (warp == 0) {
+            unsigned long long key = 0ull;  // bits of |d| + 1 (0 = no candidate); NaN sorts above everything
+            int bi = n;
+            double bval = 0.0;
+            for (int r = lane; r < n; r += 32) {
+                if (s_pivpos[r] < 0) {
+                    const double d = D[k * n + r];
+                    const unsigned long long kk = ((unsigned long long)__double_as_longlong(d) & 0x7fffffffffffffffull) + 1ull;
+                    if (kk > key) { key = kk; bi = r; bval = d; }
+                }
+            }
+            unsigned long long mx = key;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long ok = __shfl_xor_sync(0xffffffffu, mx, o);
+                mx = ok > mx ? ok : mx;
+            }
+            const unsigned win = __ballot_sync(0xffffffffu, key == mx);
+            const int src = __ffs(win) - 1;
+            bi = __shfl_sync(0xffffffffu, bi, src);
+            bval = __shfl_sync(0xffffffffu, bval, src);
+            // mx == 1: every candidate is +-0 (singular); NaN pivot: singular as well (SingularException)
+            const bool bad = mx <= 1ull || bval != bval || bi >= n;
+            if (lane == 0) {
+                s_pv = bad ? -1 : bi;
+                if (!bad) {
+                    s_pivrow[k] = bi;
+                    s_pivpos[bi] = k;
+                    s_rdiag[k] = 1.0 / bval;
+                }
+            }
+        }
         __syncthreads();
-        for (int idx = tid; idx < k * nrhs; idx += SE_NT) {
-            const int i = idx % k, j = idx / k;
-            X[j * n + i] = fma(-D[k * n + i], X[j * n + k], X[j * n + i]);
+        if (k == 5) SE_MARK(13);
+        const int pv = s_pv;
+        if (pv < 0) return nullptr;  // singular Pade denominator (uniform for the CTA)
+        const double inv = s_rdiag[k];
+        // eliminate column k from the active rows.  [D | X] is one logical matrix of n + nrhs columns: logical
+        // column c lives at sm[(c < n ? nn : -nn) + c * n ...] (D = sm + nn, X = sm).  The phase is instruction-issue
+        // bound (32 warps, tiny work), so warps without a column leave at once and addresses are 32-bit shared.
+        const int ctot = n + nrhs;
+#pragma unroll 1
+        for (int c = k + 1 + warp; c < ctot; c += NWARP) {
+            const uint32_t cb = sm_a + 8u * (uint32_t)(c * n + (c < n ? nn : -nn));
+            const double pvv = se_lds(cb + 8u * (uint32_t)pv);
+#pragma unroll 1
+            for (int r = lane; r < n; r += 32) {
+                if (s_pivpos[r] >= 0) continue;
+                const double l = se_lds(dk_a + 8u * (uint32_t)r) * inv;
+                const uint32_t a = cb + 8u * (uint32_t)r;
+                se_sts(a, fma(-l, pvv, se_lds(a)));
+            }
+        }
+        if (k == 5) SE_MARK(14);
+        __syncthreads();
+        if (k == 5) SE_MARK(15);
+    }
+    SE_MARK(7);
+    // back substitution U x = y in pivot order: x_k = y(p_k) / U(p_k, k); rows that became pivots earlier
+    // (position < k) subtract U(row, k) * x_k.  x_k goes to its natural place k of the output T, which also
+    // undoes the row permutation.  One barrier per step; reciprocals of the diagonal come from the factorisation.
+    const uint32_t t_a = (uint32_t)__cvta_generic_to_shared(T);
+    for (int k = n - 1; k >= 0; --k) {
+        const int pr = s_pivrow[k];
+        const double rk = s_rdiag[k];
+        const uint32_t dk = sm_a + 8u * (uint32_t)(nn + k * n);
+#pragma unroll 1
+        for (int j = warp; j < nrhs; j += NWARP) {
+            const uint32_t xb = sm_a + 8u * (uint32_t)(j * n);
+            const double xk = se_lds(xb + 8u * (uint32_t)pr) * rk;
+#pragma unroll 1
+            for (int r = lane; r < n; r += 32) {
+                const int pos = s_pivpos[r];
+                if (pos > k) continue;
+                if (pos == k) se_sts(t_a + 8u * (uint32_t)(j * n + k), xk);
+                else {
+                    const uint32_t a = xb + 8u * (uint32_t)r;
+                    se_sts(a, fma(-se_lds(dk + 8u * (uint32_t)r), xk, se_lds(a)));
+                }
+            }
         }
         __syncthreads();
     }
+    X = T;
+    SE_MARK(8);
     // ---- squaring ----
     double *Xc = X, *Xn = U;
     for (int q = 0; q < si; ++q) {
         se_matmul(n, Xc, Xc, Xn);
         double *tmp = Xc; Xc = Xn; Xn = tmp;
     }
+    SE_MARK(9);
     return Xc;
 }
 
@@ -270,6 +357,7 @@ __global__ void __launch_bounds__(SE_NT) small_exp_kernel(const SmallExpParams P
     __shared__ double colsum[SE_MAXM];
     const int prob = blockIdx.x;
     const int tid = threadIdx.x;
+    SE_MARK(0);
     const double beta = P.scal[prob * 4];
     int n = P.stat[prob * 4 + 0];
     if (beta == 0.0) n = P.m;
@@ -300,6 +388,7 @@ __global__ void __launch_bounds__(SE_NT) small_exp_kernel(const SmallExpParams P
     }
     // unbalance and take the first column: exp(tH)[i, 0] = sc[i] * X[i, 0] / sc[0]
     for (int i = tid; i < P.ldy; i += SE_NT) yout[i] = i < n ? Xc[i] * sc[i] / sc[0] : 0.0;
+    SE_MARK(10);
 }
 
 // Batched exponential!(A_b, ExpMethodHigham2005Base()) for many small matrices resident on the device

@@ -77,6 +77,16 @@ def main(which):
                                "warp15_wait": float(full[:, 3:, 11].mean()), "warp15_compute": float(full[:, 3:, 12].mean()),
                                "producer_wait_empty": float(full[:, 3:, 13].mean()),
                                "producer_chunks_total": float(full[:, 3:, 14].mean())}
+    if hasattr(lib, "b200k_debug_se_ts") and which in ("lanczos", "arnoldi"):
+        se = np.zeros(16, dtype=np.int64)
+        lib.b200k_debug_se_ts.argtypes = [C.c_void_p]
+        lib.b200k_debug_se_ts(se.ctypes.data)
+        names_se = ["load_H", "balance", "norm_scale", "A2", "pade_powers", "A_times_U_and_split", "lu", "backsub",
+                    "squaring", "unbalance_store"]
+        out["small_exp_cycles"] = {nm: int(se[i + 1] - se[i]) for i, nm in enumerate(names_se)}
+        out["small_exp_cycles"]["total"] = int(se[10] - se[0])
+        out["small_exp_lu_step5"] = {"pivot_and_barrier": int(se[13] - se[11]), "eliminate": int(se[14] - se[13]),
+                                     "barrier": int(se[15] - se[14])}
     out["gap_between_steps"] = float((ts_[:, 1:, 0] - ts_[:, :-1, 6])[:, 3:].mean())
     out["by_step_matvec_mean"] = [float(v) for v in d[:, :, 0].mean(0)]
     print(json.dumps(out, indent=1))
