@@ -199,7 +199,34 @@ Geom single_geom(b200k_context *h, long long n) {
 }
 
 // Team size for a batch of nb problems: maximise problems in flight x SM use, w slice in shared memory.
-Geom batch_geom(b200k_context *h, long long n, int nb) {
+// Short-window batches (Lanczos / IOP on the XL instance) are latency-bound, not bandwidth-bound: a step costs a
+// fixed part (two packet all-reduces, ~7000 + 40 C cycles for a team of C CTAs -- measured at C = 37 and 148) plus
+// ~3 cycles per row of the CTA's slice, so smaller teams (more problems in flight) win as long as the two slice
+// buffers and two ring slots still fit in shared memory.  B200K_BATCH_TEAM=C forces the team size (experiments).
+Geom batch_geom(b200k_context *h, long long n, int nb, bool short_window) {
+    if (const char *env = std::getenv("B200K_BATCH_TEAM")) {
+        const int C = std::max(1, std::min(std::atoi(env), h->max_ctas));
+        return make_geom(n, C, std::min(h->max_ctas / C, nb));
+    }
+    if (short_window && !h->no_xl) {
+        Geom bestx;
+        double best_cost = -1.0;
+        for (int C = 1; C <= h->max_ctas; ++C) {
+            const int nteams = std::min(h->max_ctas / C, nb);
+            if (nteams < 1) break;
+            Geom g = make_geom(n, C, nteams);
+            if ((long long)g.slice * (C - 1) >= n && C > 1) continue;  // empty trailing CTAs
+            const size_t need = sizeof(SmemTma) + 2 * (size_t)round_up((long long)g.slice * 8, 128) + 2 * (size_t)SLOT_BYTES;
+            if (need > SMEM_LIMIT) continue;
+            const int rounds = (nb + nteams - 1) / nteams;
+            const double cost = (double)rounds * (7000.0 + 40.0 * C + 3.0 * g.slice);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                bestx = g;
+            }
+        }
+        if (best_cost >= 0) return bestx;
+    }
     Geom best;
     double best_score = -1.0;
     for (int C = 1; C <= h->max_ctas; ++C) {
@@ -1366,7 +1393,7 @@ int b200k_expv_batched(b200k_handle_t h, b200k_op_t op, int nb, const double *t,
     c.B = nullptr;
     c.ldb = 0;
     c.btail_host = nullptr;
-    c.g = batch_geom(h, n, nb);
+    c.g = batch_geom(h, n, nb, op->kind == 0 && (c.lanczos || c.iop > 0));
     int st = launch_krylov(h, c);
     if (st) return st;
     if (!h->host_smallexp && m <= SE_MAXM) {

@@ -111,3 +111,15 @@ def test_error_mapping(eu):
         eu.phiv_dense(np.zeros((3, 3)), np.zeros(4), 2)
     import eu_b200._lib as L
     assert L.load().b200k_status_string(3).decode().startswith("singular")
+
+
+def test_runtime_flags_match_header(eu):
+    """The B200K_FLAG_* constants of include/b200krylov.h are the ones the host mirror passes to b200k_set_flag."""
+    import inspect
+    txt = open(os.path.join(ROOT, "include", "b200krylov.h")).read()
+    flags = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"#define\s+B200K_FLAG_(\w+)\s+(\d+)", txt)}
+    assert flags == {"force_ldg": 1, "host_smallexp": 2, "l2hint": 3, "no_xl": 4}
+    src = inspect.getsource(eu.api.Engine.set_flag)
+    for name, val in flags.items():
+        assert f'"{name}": {val}' in src, name
+
