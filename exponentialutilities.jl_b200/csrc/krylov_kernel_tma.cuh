@@ -338,8 +338,7 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
         }
     }
     // the consumers decide when the problem is over (m steps, happy breakdown, or beta == 0)
-    while (S->stop_seq < seq) {
-    }
+    while (S->stop_seq < seq) __nanosleep(256);  // (do not steal issue slots from the consumers while waiting)
     // every copy that was issued must have landed before the ring is re-initialised / the CTA exits
     const unsigned ns = (unsigned)rg.nslot;
     const unsigned first = issued > ns ? issued - ns : 0u;
@@ -450,6 +449,10 @@ __device__ __forceinline__ void push_halo(const KrylovParams &P, Cons &cx, const
 // any x load), so (a) the gather batch width GW is a template parameter (5 for operators with <= 5 entries per row),
 // and (b) chunks whose columns ALL lie in the slice take a loop without the local/remote select or any global
 // address arithmetic; which chunks those are is learnt by the first mat-vec of a launch (`learn`).
+// (Negative result, measured in one A/B call: reading a SELL-16 copy of the operator straight from L2 into registers
+// with coalesced read-only loads, two rows per thread in flight and no shared-memory staging at all, took 30.6 k
+// cycles per C2 mat-vec against 17.0 k for this ring version -- like the v1 LDG kernel, direct loads do not keep
+// enough bytes in flight per SM.  The code was removed again.)
 template <bool AUG, int GW>
 __device__ double matvec_xl(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *xsrc, double xscale,
                             bool learn, bool fold, double foldc, int pt_step = 0) {

@@ -35,8 +35,11 @@ def convdiff2d(nx, ny, c=0.3):
 
 
 def relerr(a, b):
-    a = np.asarray(a, dtype=float)
-    b = np.asarray(b, dtype=float)
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if not (np.iscomplexobj(a) or np.iscomplexobj(b)):
+        a = a.astype(float)
+        b = b.astype(float)
     nb = np.linalg.norm(b)
     return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
 

@@ -147,3 +147,44 @@ def test_error_estimate_lanczos_mode(oracle):
     w, mm = oracle.expv_ee(t, A, b, m=m, tol=1e-10, rtol=1e-10, return_m=True)
     assert relerr(w, sla.expm(t * A) @ b) < 1e-9 and 1 <= mm <= m
     assert np.linalg.norm(oracle.expv_ee(t, A, np.zeros(n), m=m)) == 0.0          # :783
+
+
+def test_complex_value_testset(oracle):
+    """test/basictests.jl:650-664 "Complex Value": Hermitian / general, complex / real A, complex / real b, real /
+    imaginary / complex t, n = 20, m = 10: exp(t A) b ~ expv(t, A, b; m) at isapprox's default rtol."""
+    n, m = 20, 10
+    rng = np.random.default_rng(21)
+
+    def herm(M):
+        return (M + M.conj().T) / 2
+
+    Az = rng.random((n, n)) + 1j * rng.random((n, n))
+    Ar = rng.random((n, n))
+    for A in (herm(Az), herm(Ar), Az, Ar):
+        for b in (rng.random(n) + 1j * rng.random(n), rng.random(n)):
+            for t in (1e-2, 1e-2j, 1e-2 + 1e-2j):
+                w = oracle.expv(t, A, b, m=m)
+                assert relerr(w, sla.expm(t * A) @ b) < SQRT_EPS
+
+
+def test_gpu_testset_inputs_on_the_oracle(oracle):
+    """test/gpu/gputests.jl:41-58, 62-77: the inputs of the reference's own GPU test (sparse ComplexF64 strictly upper
+    triangular + sparse perturbation, n = 1000; a 4 x 4 complex Arnoldi with imaginary dt) pin the oracle to
+    exp(tA)b -- the GPU tests then compare the CUDA path with the oracle on the same kind of input."""
+    n = 1000
+    rng = np.random.default_rng(22)
+
+    def sprand_c(density):
+        M = sp.random(n, n, density=density, random_state=rng, format="csr")
+        M.data = M.data + 1j * rng.random(M.nnz)
+        return M
+
+    A = (sp.triu(sprand_c(10 / n), 1) + sprand_c(1 / n)).tocsr()
+    b = rng.random(n) + 1j * rng.random(n)
+    w = oracle.expv(0.1, A, b)
+    assert relerr(w, sla.expm(0.1 * A.toarray()) @ b) < SQRT_EPS
+    A4 = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+    v0 = rng.standard_normal(4) + 1j * rng.standard_normal(4)
+    Ks = oracle.arnoldi(A4, v0, tol=1e-7, ishermitian_=False)
+    assert relerr(oracle.expv_ks(0.01j, Ks), sla.expm(0.01j * A4) @ v0) < SQRT_EPS
+
