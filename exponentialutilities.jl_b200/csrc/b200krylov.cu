@@ -129,10 +129,14 @@ struct b200k_comm {
     bool connected = false;
     unsigned bar_base = 0;  // local arrivals accumulated by all previous launches (identical on every rank)
     unsigned seq_base = 0;  // team barriers passed by all previous launches
-    // layout of each rank's buffer: [header: barrier counter @0, LL packet inbox @1024: 2 x (MAXCOL+1) x 8 x 16 B]
+    // layout of each rank's buffer: [header: barrier counter @0, LL packet inbox @1024: 2 x (MAXCOL+1) x 8 x 16 B,
+    // local packet inbox of the XL instance]
     // [part 2*MAXCOL*cpad][partn 4*cpad][xbuf 2*xlen] doubles
     static constexpr size_t PKT_BYTES = (size_t)2 * (MAXCOL + 1) * 8 * 16;
-    static constexpr size_t HDR = 1024 + PKT_BYTES;
+    // + this GPU's own packet inbox of the short-window instance: [2 parities][LLQ quantities][CPAD source CTAs]
+    static constexpr size_t LLLOC_BYTES = (size_t)2 * LLQ * CPAD * 16;
+    static constexpr size_t HDR = 1024 + PKT_BYTES + LLLOC_BYTES;
+    uint4 *llloc() const { return reinterpret_cast<uint4 *>(reinterpret_cast<char *>(local) + 1024 + PKT_BYTES); }
     unsigned *bar_of(int r) const { return reinterpret_cast<unsigned *>(peer[r]); }
     uint4 *pkt_of(int r) const { return reinterpret_cast<uint4 *>(reinterpret_cast<char *>(peer[r]) + 1024); }
     double *part_of(int r) const { return reinterpret_cast<double *>(reinterpret_cast<char *>(peer[r]) + HDR); }
@@ -477,6 +481,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
                 h->ll_seq = 0;
             }
             P.llpkt = h->llpkt.as<uint4>();
+            if (cm) P.llloc = cm->llloc();
             if (!cm) {
                 P.seq_base = h->ll_seq;
                 h->ll_seq += need;
@@ -525,6 +530,27 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
     if (h->timing) { h->ev_k = true; h->ev_p = false; }
     h->launches += 1;
     return B200K_OK;
+}
+
+// Row-sharded launches never reset the barrier counter / sequence number of the communicator: account for what the
+// launch consumed.  Steps js..je ran; every step passes two reductions (sequence numbers), but the XL instance
+// replaces the counter barrier by packet all-reduces for the norm and for inner-product windows of <= LLQ columns.
+void account_sharded(b200k_context *h, b200k_comm *cm, const KrylovCall &c, bool ran, int js, int je) {
+    unsigned nseq = 1, nbar = 1;  // firststep! (or the halo staging barrier of a resumed factorisation)
+    if (ran) {
+        const int iopw = c.iop > 0 ? c.iop : c.m;
+        for (int j = js; j <= je; ++j) {
+            nseq += 2u;
+            if (!h->last_xl) {
+                nbar += 2u;
+            } else {
+                const int nc = c.lanczos ? 1 : std::min(j, iopw);
+                if (nc > LLQ) nbar += 1u;
+            }
+        }
+    }
+    cm->bar_base += nbar * (unsigned)c.g.C;
+    cm->seq_base += nseq;
 }
 
 // Copy H / beta / (m, breakdown) of nprob problems to pinned host memory and wait.
@@ -672,13 +698,8 @@ int arnoldi_core(b200k_context *h, b200k_operator *op, const double *b, const b2
     if (st) return st;
     if (op->comm) {  // the multi-GPU barrier counters are never reset: account for this launch's arrivals
         const double b0 = o->init == 0 ? h->scalh.as<double>()[0] : *beta;
-        unsigned nbar = 1;  // firststep! barrier, or the halo staging barrier of a resumed factorisation
-        if (b0 != 0.0) {
-            const int js = c.j0 == 0 ? 1 : c.j0;
-            nbar += 2u * (unsigned)(h->stath.as<int>()[0] - js + 1);
-        }
-        op->comm->bar_base += nbar * (unsigned)c.g.C;
-        op->comm->seq_base += nbar;
+        const int js = c.j0 == 0 ? 1 : c.j0;
+        account_sharded(h, op->comm, c, b0 != 0.0, js, h->stath.as<int>()[0]);
     }
     const double *Hh = h->Hh.as<double>();
     const int ldhd = m + 1;
@@ -1253,10 +1274,7 @@ int b200k_expv(b200k_handle_t h, b200k_op_t op, double t, const double *b, const
             mo = beta == 0.0 ? o.m : h->stath.as<int>()[0];
             bd = beta == 0.0 ? 0 : h->stath.as<int>()[1];
             if (op->comm) {
-                unsigned nbar = 1;
-                if (beta != 0.0) nbar += 2u * (unsigned)mo;
-                op->comm->bar_base += nbar * (unsigned)c.g.C;
-                op->comm->seq_base += nbar;
+                account_sharded(h, op->comm, c, beta != 0.0, 1, mo);
             }
             if (*h->errh.as<int>()) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
             if (m_out) *m_out = mo;

@@ -432,6 +432,69 @@ __device__ void ll_collect(const KrylovParams &P, Cons &cx, const Team &tm, int 
     consumer_sync();
 }
 
+// ---- row-sharded short windows: two-level packet all-reduce (no counter barrier, no trailing fence) ------------------
+// Level 1 (inside the GPU): every CTA sends its partial of quantity ci to the inbox of ONE owner CTA (CTA ci); the
+// owner adds the C packets in CTA order.  Level 2 (NVLink): the owner pushes the GPU's sum to every GPU's inbox, every
+// CTA polls the R packets of each quantity of its own GPU's inbox and adds them in rank order.  `ordered` = the
+// reduction also publishes this step's gather-buffer stores and halo pushes: a CTA fences (system scope if it pushed
+// rows to a peer) before its level-1 packet, the owner acquires, fences at system scope before the level-2 pushes,
+// and the final polls are ld.acquire.sys (which also invalidates L1 for the halo rows peers wrote into this GPU).
+// Replaces per reduction: counter barrier (atomic + spin + 2 fences), partial-sum loads, trailing __threadfence_system.
+__device__ __forceinline__ double ll_poll_acquire_sys(const uint4 *p, unsigned seq) {
+    unsigned lo, f1, hi, f2;
+    do {
+        asm volatile("ld.acquire.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2)
+                     : "l"(p)
+                     : "memory");
+    } while (f1 != seq || f2 != seq);
+    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+__device__ __forceinline__ uint4 *llloc_slot(const KrylovParams &P, unsigned seq, int ci, int src) {
+    return P.llloc + (((long long)(seq & 1u)) * LLQ + ci) * CPAD + src;
+}
+// Called by ALL lanes of warp 0 with the CTA partial v of quantity ci.
+__device__ __forceinline__ void shard_publish_warp(const KrylovParams &P, const Team &tm, unsigned seq, int ci, double v,
+                                                   int lane, bool ordered, bool pushed) {
+    if (ordered) {
+        if (pushed) asm volatile("fence.acq_rel.sys;" ::: "memory");
+        else fence_acq_rel_gpu();
+    }
+    if (lane == 0) ll_push(llloc_slot(P, seq, ci, tm.rank), v, seq);
+}
+__device__ void shard_collect(const KrylovParams &P, Cons &cx, const Team &tm, int ncols, double *out, bool ordered) {
+    SmemTma *S = cx.S;
+    cx.seq += 1u;
+    const unsigned seq = cx.seq;
+    const long long pbase = (long long)(seq & 1u) * (MAXCOL + 1) * 8;
+    if (tm.rank < ncols) {  // owner of quantity ci = tm.rank (uniform for the CTA)
+        const int ci = tm.rank;
+        for (int r = cx.tid; r < tm.C; r += NTC) {
+            const uint4 *slot = llloc_slot(P, seq, ci, r);
+            S->llv[0][r] = ordered ? ll_poll_acquire(slot, seq) : ll_poll(slot, seq);
+        }
+        consumer_sync();
+        if (cx.warp == 0) {
+            double s = 0.0;
+            for (int q = cx.lane; q < tm.C; q += 32) s += S->llv[0][q];
+            s = warp_sum(s);
+            if (ordered) asm volatile("fence.acq_rel.sys;" ::: "memory");
+            if (cx.lane < P.nranks) ll_push(P.peer_pkt[cx.lane] + pbase + (long long)ci * 8 + P.myrank, s, seq);
+        }
+    }
+    for (int ci = cx.warp; ci < ncols; ci += NW) {
+        double v = 0.0;
+        if (cx.lane < P.nranks) {
+            const uint4 *slot = P.peer_pkt[P.myrank] + pbase + (long long)ci * 8 + cx.lane;
+            v = ordered ? ll_poll_acquire_sys(slot, seq) : ll_poll(slot, seq);
+        }
+        double s = 0.0;
+        for (int r = 0; r < P.nranks; ++r) s += __shfl_sync(0xffffffffu, v, r);
+        if (cx.lane == 0) out[ci] = s;
+    }
+    consumer_sync();
+}
+
 // Push this CTA's rows that other GPUs gather (halo) into their gather buffers (peer stores over NVLink).
 __device__ __forceinline__ void push_halo(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm,
                                           long long xoff) {
@@ -1050,8 +1113,11 @@ __device__ void dots_phase_xl(const KrylovParams &P, Cons &cx, const TmaGeom &G,
 #pragma unroll
                     for (int w = 0; w < NW; ++w) s += S->red[buf][w][lane];
                 }
-                for (int u = 0; u < nb; ++u)
-                    ll_publish_warp(P, cx.team, tm, cx.seq + 1u, cb - lo + u, __shfl_sync(0xffffffffu, s, u), lane, false);
+                for (int u = 0; u < nb; ++u) {
+                    const double su = __shfl_sync(0xffffffffu, s, u);
+                    if (P.nranks > 1) shard_publish_warp(P, tm, cx.seq + 1u, cb - lo + u, su, lane, false, false);
+                    else ll_publish_warp(P, cx.team, tm, cx.seq + 1u, cb - lo + u, su, lane, false);
+                }
             }
         } else if (tid < nb) {
             double s = 0.0;
@@ -1241,7 +1307,6 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
         double *xout = par ? xb1 : xb0;
         const long long xoff = xoff0 + (par ? P.xlen : 0);
         const long long part = part0 + (long long)par * MAXCOL * P.cpad;
-        const long long partn = partn0 + (long long)par * P.cpad;
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
         const int hi = jc;
         const int nc = hi - lo + 1;
@@ -1255,7 +1320,7 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
 
         double beta;
         {
-            const bool use_ll = !sharded && nc <= LLQ;
+            const bool use_ll = nc <= LLQ;  // packet all-reduce (one GPU: ll_*, row-sharded: shard_*)
             // <v_jc, w> was accumulated by the mat-vec (unscaled); its block reduction is also the barrier that
             // completes the w slice.  Columns lo..jc-1 come through the ring as before.
             {
@@ -1269,13 +1334,15 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
                     s *= xscale;
                     if (AUG && p > 0 && tm.rank == 0 && P.myrank == 0)
                         for (int kk = 0; kk < p; ++kk) s = fma(S->xtail[kk] * xscale, S->wtail[kk], s);
-                    if (use_ll) ll_publish_warp(P, cx.team, tm, cx.seq + 1u, nc - 1, s, cx.lane, false);
+                    if (use_ll && sharded) shard_publish_warp(P, tm, cx.seq + 1u, nc - 1, s, cx.lane, false, false);
+                    else if (use_ll) ll_publish_warp(P, cx.team, tm, cx.seq + 1u, nc - 1, s, cx.lane, false);
                     else if (cx.lane == 0) P.peer_part[P.myrank][part + (long long)(nc - 1) * P.cpad + tm.rank] = s;
                 }
             }
             if (nc > 1) dots_phase_xl<OPK, AUG, XL>(P, cx, G, tm, V, lo, hi - 1, part, use_ll);
             PT_MARK(blockIdx.x, j, 2);
-            if (use_ll) ll_collect(P, cx, tm, nc, S->hs + (lo - ulo), false);
+            if (use_ll && sharded) shard_collect(P, cx, tm, nc, S->hs + (lo - ulo), false);
+            else if (use_ll) ll_collect(P, cx, tm, nc, S->hs + (lo - ulo), false);
             else team_reduce_c(P, cx, tm, lpart + part, nc, S->hs + (lo - ulo), false);
             PT_MARK(blockIdx.x, j, 3);
             if (tm.rank == 0)
@@ -1291,16 +1358,21 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
                 const double v = warp_sum(nrm);
                 if (cx.lane == 0) S->redn[cx.warp] = v;
                 consumer_sync();
+                bool pushed = false;
+                if (sharded) {  // halo rows go to the peers' gather buffers before this CTA's packet may leave
+                    pushed = P.send_ofs[tm.rank + 1] > P.send_ofs[tm.rank];
+                    push_halo(P, cx, G, tm, xoff);
+                    consumer_sync();
+                }
                 if (cx.warp == 0) {
                     double s = 0.0;
 #pragma unroll
                     for (int w = 0; w < NW; ++w) s += S->redn[w];
                     if (!sharded) ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 0, s, cx.lane, true);
-                    else if (cx.lane == 0) P.peer_partn[P.myrank][partn + tm.rank] = s;
+                    else shard_publish_warp(P, tm, cx.seq + 1u, 0, s, cx.lane, true, pushed);
                 }
             }
             PT_MARK(blockIdx.x, j, 7);
-            if (sharded) push_halo(P, cx, G, tm, xoff);
             // the resident column v_jc = xin * xscale goes to V now, one step late, between publishing this CTA's
             // norm partial and collecting everybody's: the stores overlap the packet flight time.  (After the
             // collect they cost 2.2k cycles of their own per step -- measured; in front of the release fence
@@ -1316,7 +1388,7 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
             }
             PT_MARK(blockIdx.x, j, 8);
             if (!sharded) ll_collect(P, cx, tm, 1, S->bc, true);
-            else team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, true);
+            else shard_collect(P, cx, tm, 1, S->bc, true);
             PT_MARK(blockIdx.x, j, 5);
             if (tid == 0) S->cols_ready = jc + 1;
             beta = sqrt(S->bc[0]);

@@ -100,6 +100,20 @@ if "c4" in which:
         for _ in range(3): w, st = P.kiops_sharded(1.0, sop, ul, ishermitian=h, return_device=True)
         torch.cuda.synchronize(); dist.barrier(); dt = (time.perf_counter() - t0) / 3
         res[f"herm{int(h)}"] = {"s_per_solve": dt, "stats": st}
+    # per-Krylov-step cost at the C4 size (120 MB Lanczos / 150 MB IOP-2 per step per GPU at 8 GPUs)
+    bl = torch.randn(nl, dtype=torch.float64, device="cuda")
+    for name, kw in (("lanczos", dict(ishermitian=True)), ("iop2", dict(ishermitian=False, iop=2))):
+        f = lambda: eu.expv(1.0, sop.op, bl, m=30, **kw)
+        ms = timed(f, 10)
+        sop.engine.set_timing(True); ks = []
+        for _ in range(5):
+            f(); torch.cuda.synchronize(); ks.append(sop.engine.last_timing()["krylov_ms"])
+        sop.engine.set_timing(False)
+        nnz_l = 49_987_000 / world; n_l = n / world
+        step_bytes = (12 * nnz_l + 4 * n_l) + (24 * n_l if name == "lanczos" else 16 * n_l + 32 * n_l)
+        us = float(np.mean(ks)) * 1e3 / 30
+        res[f"expv_m30_{name}"] = {"ms_per_expv": ms, "us_per_krylov_step": us, "kernel": sop.engine.last_kernel(),
+                                   "alg_gbs_per_gpu": step_bytes / us / 1e3}
     log(json.dumps({"c4_kiops_row_sharded": res, "n_gpus": world}))
     dist.barrier(); sop.close()
 dist.destroy_process_group()
