@@ -358,6 +358,8 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
         if (!vec2 || h->force_ldg || c.nprob != 1 || c.g.nteams != 1)
             return fail(h, B200K_EUNSUPPORTED, "row-sharded operators need even nloc/ldv, 16-byte aligned vectors, one problem");
         if (n + op->nhalo + c.p > cm->xlen) return fail(h, B200K_EDIM, "communicator gather buffer (xlen) too small");
+        if (cm->seq_base > 0xf0000000u)  // packet sequence numbers are never reused: ~7e7 factorisations of 30 steps
+            return fail(h, B200K_ECOMM, "communicator sequence numbers exhausted: destroy and re-create the communicator");
         P.nranks = cm->nranks;
         P.myrank = cm->rank;
         P.nhalo = (int)op->nhalo;

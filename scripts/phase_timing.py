@@ -46,6 +46,16 @@ def main(which):
         b = torch.randn(10**6, dtype=torch.float64, device="cuda")
         f = lambda: eu.expv(1.0, op, b, m=m, ishermitian=(which == "lanczos"))
         nct = 148
+    elif which == "c3":  # dense phiv operator of BASELINE config 3 (general instance, tensor-map tiles)
+        n3 = 16384
+        g3 = torch.Generator(device="cuda").manual_seed(2)
+        A3 = torch.randn(n3, n3, dtype=torch.float64, device="cuda", generator=g3) / 128
+        b3 = torch.randn(n3, dtype=torch.float64, device="cuda", generator=g3)
+        op = eu.operator(A3)
+        del A3
+        Ks3 = eu.KrylovSubspace(n3, m)
+        f = lambda: eu.arnoldi_(Ks3, op, b3, m=m, ishermitian=False)
+        nct = 148
     else:
         A = laplacian2d(250, 400)
         op = eu.operator(A)
