@@ -17,6 +17,7 @@
 #include "aux_kernels.cuh"
 #include "krylov_kernel.cuh"
 #include "krylov_kernel_tma.cuh"
+#include "krylov_kernel_mv.cuh"
 #include "krylov_kernel_z.cuh"
 #include "smallexp_kernel.cuh"
 #include "smallmat.hpp"
@@ -90,6 +91,8 @@ struct b200k_context {
     int host_smallexp = 0;  // B200K_SMALLEXP=host: one-shot / batched expv do the small exponential on the host
     DevBuf tdev, errdev;
     HostBuf errh;
+    int no_mv = 0;     // B200K_FLAG_NO_MV / B200K_MV: 2 = batched Lanczos uses the lock-step multi-vector kernel whenever it
+                       // is possible; 0 (default) and 1 = per-problem teams (the kernel is opt-in, see b200k_expv_batched)
     int no_xl = 0;     // B200K_FLAG_NO_XL / B200K_XL=0: never use the short-window (XL) instance
     int last_xl = 0;   // the last persistent launch used the XL instance
     DevBuf llpkt;      // packet all-reduce inboxes of the XL instance [2][LLQ][CPAD dest][CPAD src] x 16 B, zeroed at allocation
@@ -534,6 +537,113 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
     return B200K_OK;
 }
 
+// ---- lock-step multi-vector Lanczos for batches (krylov_kernel_mv.cuh) ---------------------------------------------
+// Cost model (cycles per step of one team, measured on the XL instance): a fixed part for the two packet all-reduces
+// plus a per-row part; the multi-vector step does four problems for ~5 cycles per row instead of 3 for one.
+struct BatchPlan {
+    Geom g;
+    double cost = -1.0;  // cycles per Krylov step for the whole batch, < 0: not possible
+    int nslot = 0;
+};
+
+BatchPlan plan_batch(b200k_context *h, long long n, int nb, int per_group, double fixed, double per_row, int bytes_per_row) {
+    BatchPlan best;
+    const int ngroups = (nb + per_group - 1) / per_group;
+    for (int C = 1; C <= h->max_ctas; ++C) {
+        const int nteams = std::min(h->max_ctas / C, ngroups);
+        if (nteams < 1) break;
+        Geom g = make_geom(n, C, nteams);
+        if ((long long)g.slice * (C - 1) >= n && C > 1) continue;  // empty trailing CTAs
+        const size_t bufs = 2 * (size_t)round_up((long long)g.slice * bytes_per_row, 128);
+        if (sizeof(SmemTma) + bufs + 2 * (size_t)SLOT_BYTES > SMEM_LIMIT) continue;
+        const int rounds = (ngroups + nteams - 1) / nteams;
+        const double cost = (double)rounds * (fixed + 40.0 * C + per_row * g.slice);
+        if (best.cost < 0 || cost < best.cost) {
+            best.cost = cost;
+            best.g = g;
+            best.nslot = (int)std::min<size_t>((SMEM_LIMIT - sizeof(SmemTma) - bufs) / SLOT_BYTES, MAXSLOT);
+        }
+    }
+    return best;
+}
+
+int launch_krylov_mv(b200k_context *h, const KrylovCall &c, const BatchPlan &plan) {
+    b200k_operator *op = c.op;
+    const long long n = op->n;
+    KrylovParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = (int)n;
+    P.rowptr = op->rowptr.as<int>();
+    P.colind = op->colind.as<int>();
+    P.val = op->val.as<double>();
+    P.op_kind = OP_CSR_STREAM;
+    const int mrn = std::max(op->max_row_nnz, 1);
+    int ch_rows = (int)((SLOT_BYTES - 12 * 8 - 16) / (12LL * mrn + 4));
+    ch_rows = std::min(ch_rows, NTC) / 32 * 32;
+    if (ch_rows < 64) return fail(h, B200K_EUNSUPPORTED, "multi-vector kernel needs short rows");
+    P.ch_rows = ch_rows;
+    P.nnz_cap = (int)round_up((long long)ch_rows * mrn + 8, 4);
+    P.team_size = plan.g.C;
+    P.nteams = plan.g.nteams;
+    P.nprob = c.nprob;
+    P.slice = plan.g.slice;
+    P.b = c.b;
+    P.b_stride = c.b_stride;
+    P.V = c.V;
+    P.ldv = c.ldv;
+    P.V_stride = c.V_stride;
+    P.m = c.m;
+    P.lanczos = 1;
+    P.tol = c.tol;
+    P.w_in_smem = 1;
+    P.nslot = plan.nslot;
+    P.tile_rows = 16;
+    const int ldhd = c.m + 1;
+    P.ldh = ldhd;
+    P.H_stride = (long long)ldhd * (c.m + 1);
+    P.xlen = round_up(n, 16);
+    P.nranks = 1;
+    P.cpad = CPAD;
+    const int nt = plan.g.nteams;
+    CK(h, h->xbuf.ensure((size_t)nt * 2 * P.xlen * KV * 8));
+    CK(h, h->Hd.ensure((size_t)c.nprob * P.H_stride * 8));
+    CK(h, h->scal.ensure((size_t)c.nprob * 4 * 8));
+    CK(h, h->stat.ensure((size_t)c.nprob * 4 * 4));
+    P.peer_xbuf[0] = h->xbuf.as<double>();
+    P.Hd = h->Hd.as<double>();
+    P.scal = h->scal.as<double>();
+    P.stat = h->stat.as<int>();
+    CK(h, cudaMemsetAsync(P.Hd, 0, (size_t)c.nprob * P.H_stride * 8, h->stream));
+    CK(h, cudaMemsetAsync(P.scal, 0, (size_t)c.nprob * 4 * 8, h->stream));
+    const size_t pbytes = (size_t)2 * LLQ * CPAD * CPAD * sizeof(uint4);
+    if (pbytes > h->llpkt.cap) {
+        CK(h, h->llpkt.ensure(pbytes));
+        CK(h, cudaMemsetAsync(h->llpkt.p, 0, h->llpkt.cap, h->stream));
+        h->ll_seq = 0;
+    }
+    const int ngroups = (c.nprob + KV - 1) / KV;
+    const unsigned rounds = (unsigned)((ngroups + nt - 1) / nt);
+    const unsigned need = rounds * (2u * (unsigned)c.m + 4u) + 8u;
+    if (h->ll_seq > 0xffffffffu - need - 16u) {
+        CK(h, cudaMemsetAsync(h->llpkt.p, 0, h->llpkt.cap, h->stream));
+        h->ll_seq = 0;
+    }
+    P.llpkt = h->llpkt.as<uint4>();
+    P.seq_base = h->ll_seq;
+    h->ll_seq += need;
+    const size_t smem = sizeof(SmemTma) + 2 * (size_t)round_up((long long)P.slice * KV * 8, 128) + (size_t)P.nslot * SLOT_BYTES;
+    const void *kern = mrn <= 5 ? (const void *)krylov_mv_kernel<5> : (const void *)krylov_mv_kernel<8>;
+    if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
+    void *args[] = {(void *)&P};
+    CK(h, cudaLaunchCooperativeKernel(kern, dim3(plan.g.C * plan.g.nteams), dim3(NT2), args, smem, h->stream));
+    if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
+    if (h->timing) { h->ev_k = true; h->ev_p = false; }
+    h->launches += 1;
+    h->last_kernel = 5;
+    h->last_xl = 0;
+    return B200K_OK;
+}
+
 // Row-sharded launches never reset the barrier counter / sequence number of the communicator: account for what the
 // launch consumed.  Steps js..je ran; every step passes two reductions (sequence numbers), but the XL instance
 // replaces the counter barrier by packet all-reduces for the norm and for inner-product windows of <= LLQ columns.
@@ -923,6 +1033,8 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
                                  (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5>,
                                  (const void *)krylov_tma_kernel<OP_CSR_WARP, false, false>, (const void *)krylov_tma_kernel<OP_CSR_WARP, true, false>,
                                  (const void *)krylov_tma_kernel<OP_DENSE, false, false>, (const void *)krylov_tma_kernel<OP_DENSE, true, false>};
+    cudaFuncSetAttribute((const void *)krylov_mv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    cudaFuncSetAttribute((const void *)krylov_mv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     bool attr_ok = true;
     for (const void *k : tma_kernels)
         attr_ok = attr_ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) == cudaSuccess;
@@ -945,6 +1057,7 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
                          6 * SE_MAXM * SE_MAXM * 8);
     cudaFuncSetAttribute((const void *)small_exp_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          6 * SE_MAXM * SE_MAXM * 8);
+    if (const char *env = std::getenv("B200K_MV")) h->no_mv = std::strcmp(env, "0") == 0 ? 1 : (std::strcmp(env, "2") == 0 ? 2 : 0);
     if (const char *env = std::getenv("B200K_XL")) h->no_xl = std::strcmp(env, "0") == 0 ? 1 : 0;
     if (const char *env = std::getenv("B200K_KERNEL")) h->force_ldg = std::strcmp(env, "ldg") == 0 ? 1 : 0;
     h->max_ctas = std::min(h->sm_count, CPAD);  // one CTA per SM
@@ -1005,6 +1118,7 @@ int b200k_set_flag(b200k_handle_t h, int flag, int value) {
     if (flag == B200K_FLAG_FORCE_LDG) h->force_ldg = value ? 1 : 0;
     else if (flag == B200K_FLAG_HOST_SMALLEXP) h->host_smallexp = value ? 1 : 0;
     else if (flag == B200K_FLAG_NO_XL) h->no_xl = value ? 1 : 0;
+    else if (flag == B200K_FLAG_NO_MV) h->no_mv = value == 2 ? 2 : (value ? 1 : 0);
     else if (flag == B200K_FLAG_L2HINT) h->l2hint = value < 0 ? -1 : (value ? 1 : 0);
     else return fail(h, B200K_EARG, "unknown flag");
     return B200K_OK;
@@ -1414,8 +1528,28 @@ int b200k_expv_batched(b200k_handle_t h, b200k_op_t op, int nb, const double *t,
     c.ldb = 0;
     c.btail_host = nullptr;
     c.g = batch_geom(h, n, nb, op->kind == 0 && (c.lanczos || c.iop > 0));
-    int st = launch_krylov(h, c);
-    if (st) return st;
+    int st = B200K_OK;
+    bool mv = false;
+    if (c.lanczos && op->kind == 0 && !op->comm && h->no_mv != 1 && !h->no_xl && !h->force_ldg && nb >= 2 &&
+        op->max_row_nnz > 0 && (SLOT_BYTES - 12 * 8 - 16) / (12LL * op->max_row_nnz + 4) >= 64 &&
+        !std::getenv("B200K_BATCH_TEAM")) {
+        // Four problems per team in lock step.  Measured at C5 (profiles/r1_s2_phase_c5_mv.json): a team-step costs
+        // 30.6 k cycles for four problems (mat-vec 10.0 k = 4.9 cycles per row as modelled, but 20.6 k of fixed cost:
+        // update with strided gather-buffer stores 4.6 k, release fence behind 64 KB of stores 3.9 k, four fp64
+        // divisions + square roots per thread 1.9 k, reductions 7.3 k) against 32.9 k for one problem on the
+        // per-problem teams with four times as many teams: 20.9 k vs 22.4 k expv/s/GPU end to end.  Until that fixed
+        // part is trimmed the kernel is opt-in (B200K_FLAG_NO_MV = 2 / B200K_MV=2); it is parity-tested either way.
+        const BatchPlan pm = plan_batch(h, n, nb, KV, 18000.0, 5.0, KV * 8);
+        if (pm.cost > 0 && h->no_mv == 2) {
+            st = launch_krylov_mv(h, c, pm);
+            if (st) return st;
+            mv = true;
+        }
+    }
+    if (!mv) {
+        st = launch_krylov(h, c);
+        if (st) return st;
+    }
     if (!h->host_smallexp && m <= SE_MAXM) {
         // nb exponentials on nb SMs + one batched projection, all on the device
         st = launch_smallexp_project(h, nb, m, c.lanczos, t, h->V.as<double>(), ldv, vstride, n, W, ldw, ldw);

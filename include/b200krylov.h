@@ -265,7 +265,8 @@ int b200k_last_timing(b200k_handle_t h, float *krylov_ms, float *project_ms);
 int b200k_set_timing(b200k_handle_t h, int enabled);
 /* Which Krylov kernel the last factorisation used: 1 = LDG kernel (krylov_persistent_kernel, any layout),
  * 2 = TMA-ring kernel (krylov_tma_kernel; needs even n / ldv and 16-byte aligned bases), 3 = complex kernel,
- * 4 = the short-window (Lanczos / IOP) instance of the TMA-ring kernel (resident basis vector).  The environment
+ * 4 = the short-window (Lanczos / IOP) instance of the TMA-ring kernel (resident basis vector), 5 = the lock-step
+ * multi-vector Lanczos kernel of batched expv.  The environment
  * variable B200K_KERNEL=ldg, read at b200k_create, forces 1 (A/B measurements). */
 int b200k_last_kernel(b200k_handle_t h, int *which);
 /* Runtime switches (A/B measurements and tests): B200K_FLAG_FORCE_LDG = 1 uses krylov_persistent_kernel even
@@ -277,6 +278,8 @@ int b200k_last_kernel(b200k_handle_t h, int *which);
                                whose working set exceeds the L2), 0 never, 1 always */
 #define B200K_FLAG_NO_XL 4  /* 1: never use the short-window (Lanczos / IOP) instance of the TMA-ring kernel that keeps
                                the current basis vector in shared memory and reduces with packet all-reduces */
+#define B200K_FLAG_NO_MV 5 /* batched Lanczos and the lock-step multi-vector kernel (four problems per team): 2 = use it
+                              whenever possible; 0 (default) / 1 = per-problem teams.  Opt-in: parity-tested, not yet faster */
 int b200k_set_flag(b200k_handle_t h, int flag, int value);
 
 #ifdef __cplusplus

@@ -68,12 +68,15 @@ def main(which):
     torch.cuda.synchronize()
     buf = np.zeros(CT * ST * MK, dtype=np.int64)
     assert lib.b200k_debug_phase_ts(buf.ctypes.data, buf.size) == 0
-    full = buf.reshape(CT, ST, MK)[:nct, 1:m + 1, :].astype(np.float64)
+    allc = buf.reshape(CT, ST, MK)
+    used = np.nonzero(allc[:, 5, 0] > 0)[0]  # CTAs that ran (geometry-dependent for batches)
+    full = allc[used][:, 1:m + 1, :].astype(np.float64)
+    out_n = int(used.size)
     ts_ = full[:, :, :7]
     names = ["matvec", "dots", "reduce1", "update", "reduce2", "normalise"]
     d = np.diff(ts_, axis=2)                       # [cta, step, phase]
     step_total = ts_[:, 1:, 0] - ts_[:, :-1, 0]    # start-to-start
-    out = {"which": which, "cycles_per_step_mean": float(step_total[:, 3:].mean()), "phases": {}}
+    out = {"which": which, "ctas": out_n, "cycles_per_step_mean": float(step_total[:, 3:].mean()), "phases": {}}
     for k, nm in enumerate(names):
         x = d[:, 3:, k]
         out["phases"][nm] = {"mean": float(x.mean()), "min_cta_mean": float(x.mean(1).min()),

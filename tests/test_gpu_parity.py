@@ -334,6 +334,55 @@ def test_short_window_instance_xl(gpu, oracle):
     assert relerr(L @ V[:, :30], V @ H) < 1e-12
 
 
+def test_batched_multivector_lanczos(gpu, oracle):
+    """The lock-step multi-vector Lanczos kernel of batched expv (four problems per team, krylov_kernel_mv.cuh) against
+    per-problem teams and the oracle: group padding (nb = 9), a zero start vector, mixed times, different m."""
+    eng = gpu.get_engine()
+    L = laplacian2d(90, 70)
+    n, nb = 6300, 9
+    rng = np.random.default_rng(31)
+    B = rng.standard_normal((n, nb))
+    B[:, 5] = 0.0
+    ts = rng.uniform(0.1, 1.0, nb)
+    op = gpu.operator(L)
+    out = {}
+    try:
+        for no_mv in (False, True):
+            eng.set_flag("no_mv", 1 if no_mv else 2)  # 2: always (the cost model prefers per-problem teams for 9 problems)
+            for m in (30, 7):
+                out[(no_mv, m)] = gpu.expv_batched(ts, op, B, m=m)
+                assert eng.last_kernel() == ("tma_xl" if no_mv else "tma_mv")
+    finally:
+        eng.set_flag("no_mv", 0)
+    # problems of one group that break down at different steps (Krylov dimensions 3, 2, 0, 3, 1) while others run on
+    import scipy.sparse as sp
+    nd = 6000
+    d = np.array([1.0, 2.0, 3.0])[np.arange(nd) % 3]
+    Dg = sp.diags(d).tocsr()
+    Bd = rng.standard_normal((nd, 6))
+    Bd[d == 3.0, 1] = 0.0
+    Bd[:, 2] = 0.0
+    Bd[d != 2.0, 4] = 0.0
+    td = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6]
+    try:
+        eng.set_flag("no_mv", 2)
+        Wd = gpu.expv_batched(td, Dg, Bd, m=30)
+        assert eng.last_kernel() == "tma_mv"
+    finally:
+        eng.set_flag("no_mv", 0)
+    for i, t in enumerate(td):
+        ref = np.exp(t * d) * Bd[:, i]
+        assert np.linalg.norm(Wd[:, i] - ref) <= 1e-9 * max(np.linalg.norm(ref), 1e-300), i
+    for m in (30, 7):
+        W, G = out[(False, m)], out[(True, m)]
+        assert np.linalg.norm(W[:, 5]) == 0.0
+        for i in range(nb):
+            if i != 5:
+                assert relerr(W[:, i], G[:, i]) < 1e-11, (m, i)
+        for i in (0, 4, 8):
+            assert relerr(W[:, i], oracle.expv(ts[i], L, B[:, i], m=m)) < RTOL
+
+
 def test_device_small_exp_branches(gpu, oracle):
     """Fused expv (device Pade) across the Pade orders: scale t so that ||tH|| hits C3..C13 and several squarings."""
     A = convdiff2d(60, 50)
