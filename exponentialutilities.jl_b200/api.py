@@ -429,8 +429,31 @@ def arnoldi(A, b, *, m=None, ishermitian=None, **kw):
 # ------------------------------------------------------------------------------------------
 # expv / phiv (src/krylov_phiv.jl)
 # ------------------------------------------------------------------------------------------
+class ExpvCache:
+    """ExpvCache{T}(maxiter) -- src/krylov_phiv.jl:45-77.  The reference preallocates the m x m working copy of H and
+    the exponential! workspaces here; the engine keeps the equivalent scratch in the handle (grown lazily, never on
+    the steady-state path), so this mirror only carries the size and exists so that callers written against the
+    reference (``expv!(w, t, Ks; cache = ExpvCache{T}(m))``) run unchanged -- including the error for a wrong type."""
+
+    def __init__(self, maxiter: int):
+        self.maxiter = int(maxiter)
+
+    def resize(self, maxiter: int):
+        self.maxiter = int(maxiter)
+        return self
+
+
+class PhivCache:
+    """PhivCache(w, maxiter, p) -- src/krylov_phiv.jl:404-428 (see ExpvCache: a size-carrying mirror)."""
+
+    def __init__(self, w, maxiter: int, p: int):
+        self.maxiter, self.p = int(maxiter), int(p)
+
+
 def expv_(w, t, Ks: KrylovSubspace, *, cache=None):
     """expv!(w, t, Ks) -- src/krylov_phiv.jl:200-247.  ``w``: float64 CUDA tensor of length size(V,1)."""
+    if cache is not None and not isinstance(cache, ExpvCache):
+        raise ArgumentError("Cache must be an ExpvCache")  # krylov_phiv.jl:221
     eng = Ks.engine
     t_c = isinstance(t, (complex, np.complexfloating))
     if w.numel() != Ks.nrows:
@@ -475,11 +498,13 @@ def expv(t, A, b=None, *, mode="happy_breakdown", m=None, tol=1.0e-7, ishermitia
          cache=None, expmethod=None, rtol=None, return_m=False):
     """expv(t, A, b; m, tol, ishermitian, iop, ...) or expv(t, Ks) -- src/krylov_phiv.jl:125-168."""
     t_c = isinstance(t, (complex, np.complexfloating))
+    if cache is not None and not isinstance(cache, ExpvCache):
+        raise ArgumentError("Cache must be an ExpvCache")  # expv forwards `cache` to expv! (krylov_phiv.jl:135-144, 221)
     if isinstance(A, KrylovSubspace):
         Ks = A
         wdt = torch.complex128 if (Ks.is_complex or t_c) else torch.float64
         w = torch.empty(Ks.nrows, dtype=wdt, device=Ks.engine.device)
-        return expv_(w, t, Ks)
+        return expv_(w, t, Ks, cache=cache)
     if mode not in ("happy_breakdown", "error_estimate"):
         raise ArgumentError(f"Unknown Krylov iteration termination mode, {mode}")
     op = operator(A)
@@ -551,6 +576,8 @@ def phiv_(w, t, Ks: KrylovSubspace, k, *, cache=None, correct=False, errest=Fals
     """phiv!(w, t, Ks, k; correct, errest) -- src/krylov_phiv.jl:607-653.
 
     ``w``: float64 CUDA tensor holding the column-major nrows x (k+1) result, i.e. of shape (k+1, nrows)."""
+    if cache is not None and not isinstance(cache, PhivCache):
+        raise ArgumentError("Cache must be a PhivCache")  # krylov_phiv.jl:630
     eng = Ks.engine
     if w.dim() != 2 or w.shape[1] != Ks.nrows or w.shape[0] != k + 1:
         raise DimensionMismatch("Dimension mismatch")
@@ -577,7 +604,7 @@ def phiv(t, A, b=None, k=None, *, cache=None, correct=False, errest=False, m=Non
         was_np = not (torch is not None and isinstance(b, torch.Tensor))
         Ks = arnoldi(op, b, m=m, tol=tol, ishermitian=ishermitian, iop=iop)
     w = torch.empty((k + 1, Ks.nrows), dtype=torch.float64, device=Ks.engine.device)
-    res = phiv_(w, t, Ks, k, correct=correct, errest=errest)
+    res = phiv_(w, t, Ks, k, cache=cache, correct=correct, errest=errest)
     wt = (res[0] if errest else res).t()
     out = wt.cpu().numpy() if was_np else wt
     return (out, res[1]) if errest else out

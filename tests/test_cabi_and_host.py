@@ -113,6 +113,17 @@ def test_error_mapping(eu):
     assert L.load().b200k_status_string(3).decode().startswith("singular")
 
 
+def test_cache_mirrors_and_their_error(eu):
+    """expv!/phiv! reject a cache of the wrong type with ArgumentError (src/krylov_phiv.jl:221, 630); the check comes
+    before anything touches the device."""
+    assert eu.ExpvCache(30).resize(40).maxiter == 40
+    assert eu.PhivCache(None, 30, 4).p == 4
+    with pytest.raises(eu.ArgumentError):
+        eu.expv_(None, 1.0, None, cache=eu.PhivCache(None, 30, 4))
+    with pytest.raises(eu.ArgumentError):
+        eu.phiv_(None, 1.0, None, 2, cache=object())
+
+
 def test_runtime_flags_match_header(eu):
     """The B200K_FLAG_* constants of include/b200krylov.h are the ones the host mirror passes to b200k_set_flag."""
     import inspect
