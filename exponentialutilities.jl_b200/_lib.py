@@ -43,6 +43,7 @@ class TimestepOpts(C.Structure):
 # Every symbol include/b200krylov.h declares: (restype, argtypes)
 PROTOTYPES = {
     "b200k_version": (C.c_int, []),
+    "b200k_sizeof": (C.c_int, [C.c_int]),
     "b200k_status_string": (C.c_char_p, [C.c_int]),
     "b200k_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "b200k_destroy": (C.c_int, [C.c_void_p]),
@@ -87,6 +88,8 @@ PROTOTYPES = {
                                   C.c_int64, C.c_int, C.c_void_p, C.c_int, c_double_p, c_int_p, c_int_p]),
     "b200k_expv_ks_z": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                   C.c_int, C.c_int, C.c_double, C.c_void_p]),
+    "b200k_phiv_ks_z": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                  C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_int64, c_double_p]),
     "b200k_expv_z": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.POINTER(KrylovOpts),
                                C.c_void_p, c_int_p, c_int_p]),
     "b200k_expv_small_z": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, c_int_p]),
@@ -138,6 +141,11 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI drifted
         fn.restype = res
         fn.argtypes = args
+    if hasattr(lib, "b200k_sizeof"):  # the binding's struct definitions must match the library's (ABI guard)
+        for which, cls in ((1, KrylovOpts), (2, KiopsOpts), (3, TimestepOpts)):
+            if lib.b200k_sizeof(which) != C.sizeof(cls):
+                raise RuntimeError(f"ABI mismatch: {cls.__name__} is {C.sizeof(cls)} bytes here, "
+                                   f"{lib.b200k_sizeof(which)} in {path}")
     _lib = lib
     return lib
 

@@ -486,6 +486,13 @@ def expv_(w, t, Ks: KrylovSubspace, *, cache=None):
                                         Y.ctypes.data_as(_lib.c_double_p), m, 2, C.c_void_p(Wt.data_ptr()), ld))
         w.copy_(torch.complex(Wt[0, : Ks.nrows], Wt[1, : Ks.nrows]))
         return w
+    if w.is_complex():  # real subspace and real t with a ComplexF64 output vector: promote the real result
+        wr = torch.empty(Ks.nrows, dtype=torch.float64, device=eng.device)
+        expv_(wr, t, Ks)
+        w.copy_(wr.to(torch.complex128))
+        return w
+    if w.dtype != torch.float64:
+        raise ArgumentError("expv! needs a Float64 (or ComplexF64) output vector")
     eng.bind_stream()
     st = eng.lib.b200k_expv_ks(eng.handle, float(t), C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.nrows,
                                Ks.H.ctypes.data_as(_lib.c_double_p), Ks.H.shape[0], Ks.m, Ks.beta,
@@ -581,11 +588,31 @@ def phiv_(w, t, Ks: KrylovSubspace, k, *, cache=None, correct=False, errest=Fals
     eng = Ks.engine
     if w.dim() != 2 or w.shape[1] != Ks.nrows or w.shape[0] != k + 1:
         raise DimensionMismatch("Dimension mismatch")
+    if Ks.is_complex or isinstance(t, (complex, np.complexfloating)):
+        return _phiv_z(w, t, Ks, k, correct=correct, errest=errest)
+    if w.dtype != torch.float64 or not w.is_cuda or w.stride(1) != 1:
+        raise ArgumentError("phiv! on a real Krylov subspace needs a float64 CUDA output of shape (k+1, nrows)")
     err = C.c_double()
     eng.bind_stream()
     st = eng.lib.b200k_phiv_ks(eng.handle, float(t), C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.nrows,
                                Ks.H.ctypes.data_as(_lib.c_double_p), Ks.H.shape[0], Ks.m, Ks.beta, int(k),
                                1 if correct else 0, C.c_void_p(w.data_ptr()), w.stride(0), C.byref(err))
+    eng.check(st)
+    return (w, err.value) if errest else w
+
+
+def _phiv_z(w, t, Ks, k, *, correct, errest):
+    """_phiv! on a ComplexF64 subspace (b200k_phiv_ks_z); a real subspace with complex t is not offered."""
+    eng = Ks.engine
+    if not Ks.is_complex:
+        raise _lib.UnsupportedError("phiv! with complex t on a real Krylov subspace: build the subspace with a complex b")
+    if not w.is_complex() or not w.is_cuda or w.stride(1) != 1:
+        raise ArgumentError("a complex Krylov subspace needs a ComplexF64 CUDA output of shape (k+1, nrows)")
+    err = C.c_double()
+    eng.bind_stream()
+    st = eng.lib.b200k_phiv_ks_z(eng.handle, float(np.real(t)), float(np.imag(t)), C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv,
+                                 Ks.nrows, C.c_void_p(Ks.H.ctypes.data), Ks.H.shape[0], Ks.m, Ks.beta, int(k),
+                                 1 if correct else 0, C.c_void_p(w.data_ptr()), w.stride(0), C.byref(err))
     eng.check(st)
     return (w, err.value) if errest else w
 
@@ -603,7 +630,8 @@ def phiv(t, A, b=None, k=None, *, cache=None, correct=False, errest=False, m=Non
         op = operator(A)
         was_np = not (torch is not None and isinstance(b, torch.Tensor))
         Ks = arnoldi(op, b, m=m, tol=tol, ishermitian=ishermitian, iop=iop)
-    w = torch.empty((k + 1, Ks.nrows), dtype=torch.float64, device=Ks.engine.device)
+    cplx = Ks.is_complex or isinstance(t, (complex, np.complexfloating))
+    w = torch.empty((k + 1, Ks.nrows), dtype=torch.complex128 if cplx else torch.float64, device=Ks.engine.device)
     res = phiv_(w, t, Ks, k, cache=cache, correct=correct, errest=errest)
     wt = (res[0] if errest else res).t()
     out = wt.cpu().numpy() if was_np else wt

@@ -104,7 +104,14 @@ struct b200k_context {
     // scratch (device)
     DevBuf xbuf, part, partn, bar, wglob, Hd, scal, stat, btail, Y, corr, mvec, betavec, tmp;
     // scratch (host, pinned)
-    HostBuf Hh, scalh, stath, Yh;
+    HostBuf Hh, scalh, stath;
+    // pinned staging for host -> device coefficient copies: a ring of slots, each guarded by an event recorded after
+    // its copy was queued, so a slot is never rewritten while an earlier cudaMemcpyAsync may still read it
+    static constexpr int NSTAGE = 8;
+    HostBuf stage[NSTAGE];
+    cudaEvent_t stage_ev[NSTAGE] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool stage_busy[NSTAGE] = {false, false, false, false, false, false, false, false};
+    int stage_next = 0, stage_cur = 0;
     // internal Krylov storage for the one-shot calls
     DevBuf V, bdev, wdev;
     DevBuf tsV, tsW, tsP, tsu;  // phiv_timestep workspace (basis, W, P, u)
@@ -179,6 +186,30 @@ int fail(b200k_context *h, int code, const std::string &msg) {
         if (e__ != cudaSuccess)                                                                            \
             return fail((h), B200K_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));            \
     } while (0)
+
+// Pinned staging slot of at least `bytes` bytes that no queued copy still reads (nullptr on failure); after queueing
+// the copies out of it on h->stream call stage_commit.
+void *stage_acquire(b200k_context *h, size_t bytes) {
+    const int s = h->stage_next;
+    h->stage_next = (s + 1) % b200k_context::NSTAGE;
+    if (h->stage_busy[s]) {
+        if (cudaEventSynchronize(h->stage_ev[s]) != cudaSuccess) return nullptr;
+        h->stage_busy[s] = false;
+    }
+    if (h->stage[s].ensure(bytes) != cudaSuccess) return nullptr;
+    h->stage_cur = s;
+    return h->stage[s].p;
+}
+cudaError_t stage_commit(b200k_context *h) {
+    const int s = h->stage_cur;
+    if (!h->stage_ev[s]) {
+        cudaError_t e = cudaEventCreateWithFlags(&h->stage_ev[s], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(h->stage_ev[s], h->stream);
+    if (e == cudaSuccess) h->stage_busy[s] = true;
+    return e;
+}
 
 struct Geom {
     int C = 1, nteams = 1, slice = 16, w_in_smem = 1;
@@ -702,9 +733,9 @@ int expv_small(b200k_context *h, double t, const double *H, int ldh, int m, doub
 int launch_project(b200k_context *h, const double *V, long long ldv, long long nrows, int m, double beta,
                    const double *Yhost, int ldy, int nc, double *W, long long ldw, const double *corr_host) {
     if (m > PROJ_MAXM) return fail(h, B200K_EUNSUPPORTED, "projection supports m <= 256");
-    CK(h, h->Yh.ensure((size_t)m * nc * 8 + (size_t)nc * 8));
     CK(h, h->Y.ensure((size_t)m * nc * 8));
-    double *yh = h->Yh.as<double>();
+    double *yh = reinterpret_cast<double *>(stage_acquire(h, (size_t)m * nc * 8 + (size_t)nc * 8));
+    if (!yh) return fail(h, B200K_ENOMEM, "pinned staging buffer");
     for (int c = 0; c < nc; ++c)
         for (int i = 0; i < m; ++i) yh[(size_t)c * m + i] = Yhost[(size_t)c * ldy + i];
     CK(h, cudaMemcpyAsync(h->Y.p, yh, (size_t)m * nc * 8, cudaMemcpyHostToDevice, h->stream));
@@ -717,6 +748,7 @@ int launch_project(b200k_context *h, const double *V, long long ldv, long long n
         CK(h, cudaMemcpyAsync(h->corr.p, ch, (size_t)nc * 8, cudaMemcpyHostToDevice, h->stream));
         P.corr = h->corr.as<double>();
     }
+    CK(h, stage_commit(h));
     P.V = V;
     P.ldv = ldv;
     P.nrows = nrows;
@@ -958,6 +990,15 @@ extern "C" {
 
 int b200k_version(void) { return B200K_VERSION; }
 
+int b200k_sizeof(int which) {
+    switch (which) {
+        case B200K_STRUCT_KRYLOV_OPTS: return (int)sizeof(b200k_krylov_opts);
+        case B200K_STRUCT_KIOPS_OPTS: return (int)sizeof(b200k_kiops_opts);
+        case B200K_STRUCT_TIMESTEP_OPTS: return (int)sizeof(b200k_timestep_opts);
+        default: return -1;
+    }
+}
+
 const char *b200k_status_string(int s) {
     switch (s) {
         case B200K_OK: return "ok";
@@ -1073,8 +1114,12 @@ int b200k_destroy(b200k_handle_t h) {
     DevBuf *bufs[] = {&h->zV, &h->zH, &h->zpart, &h->zxbuf, &h->zw, &h->zy, &h->tsV, &h->tsW, &h->tsP, &h->tsu, &h->tdev, &h->errdev, &h->llpkt, &h->kV, &h->kB, &h->xbuf, &h->part, &h->partn, &h->bar, &h->wglob, &h->Hd, &h->scal, &h->stat, &h->btail,
                       &h->Y, &h->corr, &h->mvec, &h->betavec, &h->tmp, &h->V, &h->bdev, &h->wdev};
     for (DevBuf *b : bufs) b->release();
-    HostBuf *hb[] = {&h->zHh, &h->errh, &h->Hh, &h->scalh, &h->stath, &h->Yh};
+    HostBuf *hb[] = {&h->zHh, &h->errh, &h->Hh, &h->scalh, &h->stath};
     for (HostBuf *b : hb) b->release();
+    for (int i = 0; i < b200k_context::NSTAGE; ++i) {
+        h->stage[i].release();
+        if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
+    }
     for (int i = 0; i < 4; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -1571,8 +1616,8 @@ int b200k_expv_batched(b200k_handle_t h, b200k_op_t op, int nb, const double *t,
     // small dense phase per problem on the host, then one batched projection launch
     const int ldhd = m + 1;
     const size_t hstride = (size_t)ldhd * (m + 1);
-    CK(h, h->Yh.ensure((size_t)nb * m * 8 + (size_t)nb * 16));
-    double *Yh = h->Yh.as<double>();
+    double *Yh = reinterpret_cast<double *>(stage_acquire(h, (size_t)nb * m * 8 + (size_t)nb * 16));
+    if (!Yh) return fail(h, B200K_ENOMEM, "pinned staging buffer");
     double *betah = Yh + (size_t)nb * m;
     int *mh = reinterpret_cast<int *>(betah + nb);
     // the nb independent m x m exponentials are spread over host threads (they are ~50 us each)
@@ -1615,6 +1660,7 @@ int b200k_expv_batched(b200k_handle_t h, b200k_op_t op, int nb, const double *t,
     CK(h, cudaMemcpyAsync(h->Y.p, Yh, (size_t)nb * m * 8, cudaMemcpyHostToDevice, h->stream));
     CK(h, cudaMemcpyAsync(h->betavec.p, betah, (size_t)nb * 8, cudaMemcpyHostToDevice, h->stream));
     CK(h, cudaMemcpyAsync(h->mvec.p, mh, (size_t)nb * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(h, stage_commit(h));
     ProjectParams P;
     std::memset(&P, 0, sizeof(P));
     P.V = h->V.as<double>();
@@ -1871,6 +1917,11 @@ int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out
             for (int k = l; k <= numSteps; ++k)
                 if (std::fabs(tau_out[k - 1]) < std::fabs(nextT)) blownTs += 1;
             if (blownTs != 0) {
+                if (l + blownTs > numSteps) {  // w[:, l + blownTs] is a BoundsError in the reference (kiops.jl:303)
+                    status = fail(h, B200K_EDIM, "BoundsError: kiops output time inside a step but w has no column for it "
+                                                 "(pass several output times as a 1 x k row, as in the reference)");
+                    break;
+                }
                 cudaMemcpyAsync(W + (size_t)(l + blownTs - 1) * ldw, W + (size_t)(l - 1) * ldw, (size_t)n * 8,
                                 cudaMemcpyDeviceToDevice, h->stream);
                 for (int k = 0; k < blownTs; ++k) {
@@ -2071,8 +2122,8 @@ int expv_ks_z_core(b200k_context *h, cplx t, const double *V, long long ldv, lon
     if (st == 1) return fail(h, B200K_ESINGULAR, "symmetric tridiagonal eigensolver did not converge");
     if (st == 2) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
     CK(h, h->zy.ensure((size_t)m * 16));
+    // (pageable source: the runtime stages it before returning, so the vector may go out of scope)
     CK(h, cudaMemcpyAsync(h->zy.p, y.data(), (size_t)m * 16, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));  // y is a stack vector
     const int blocks = (int)std::min<long long>((nrows + 255) / 256, (long long)h->sm_count * 8);
     project_z_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const double2 *>(V), ldv, nrows, m, beta,
                                                      h->zy.as<double2>(), reinterpret_cast<double2 *>(w));
@@ -2206,6 +2257,52 @@ int b200k_expv_ks_z(b200k_handle_t h, double t_re, double t_im, const double *V,
     if (!h || !V || !H || !w) return B200K_EARG;
     CK(h, cudaSetDevice(h->device));
     return expv_ks_z_core(h, cplx(t_re, t_im), V, ldv, nrows, reinterpret_cast<const cplx *>(H), ldh, m, beta, w);
+}
+
+int b200k_phiv_ks_z(b200k_handle_t h, double t_re, double t_im, const double *V, int64_t ldv, int64_t nrows,
+                    const double *H, int ldh, int m, double beta, int k, int correct, double *W, int64_t ldw,
+                    double *errest) {
+    if (!h || !V || !H || !W) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    if (m < 1 || k < 1) return fail(h, B200K_EARG, "m >= 1 and k >= 1 required");
+    if (m + 1 > MAXCOL) return fail(h, B200K_EUNSUPPORTED, "m must be < 256");
+    if (ldv < nrows || ldw < nrows) return fail(h, B200K_EDIM, "Dimension mismatch");
+    const cplx t(t_re, t_im);
+    const cplx *Hz = reinterpret_cast<const cplx *>(H);
+    std::vector<cplx> Hc((size_t)m * m), e(m, cplx(0.0, 0.0)), C2((size_t)m * (k + 1));
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) Hc[(size_t)j * m + i] = t * Hz[(size_t)j * ldh + i];
+    e[0] = cplx(1.0, 0.0);
+    smallmat::ExpWorkT<cplx> work;
+    if (smallmat::phiv_dense(m, Hc.data(), m, e.data(), k, C2.data(), m, work))
+        return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
+    const cplx hlast = Hz[(size_t)(m - 1) * ldh + m];
+    if (errest) *errest = std::abs(beta * hlast * t * C2[(size_t)k * m + (m - 1)]);
+    if (beta == 0.0) {
+        for (int c = 0; c <= k; ++c) CK(h, cudaMemsetAsync(W + (size_t)c * ldw * 2, 0, (size_t)nrows * 16, h->stream));
+        return B200K_OK;
+    }
+    // column c: beta * V[:, 1:m] * C2[:, c] (+ betah * C2[m, c+1] * v_{m+1} for c < k when `correct`): the correction is
+    // one more basis column with coefficient betah * C2[m, c+1] / beta
+    const int mm = correct ? m + 1 : m;
+    cplx *stage = reinterpret_cast<cplx *>(stage_acquire(h, (size_t)mm * (k + 1) * 16));
+    if (!stage) return fail(h, B200K_ENOMEM, "pinned staging buffer");
+    for (int c = 0; c <= k; ++c) {
+        for (int i = 0; i < m; ++i) stage[(size_t)c * mm + i] = C2[(size_t)c * m + i];
+        if (correct) stage[(size_t)c * mm + m] = c < k ? hlast * t * C2[(size_t)(c + 1) * m + (m - 1)] : cplx(0.0, 0.0);
+    }
+    CK(h, h->zy.ensure((size_t)mm * (k + 1) * 16));
+    CK(h, cudaMemcpyAsync(h->zy.p, stage, (size_t)mm * (k + 1) * 16, cudaMemcpyHostToDevice, h->stream));
+    CK(h, stage_commit(h));
+    const int blocks = (int)std::min<long long>((nrows + 255) / 256, (long long)h->sm_count * 8);
+    for (int c = 0; c <= k; ++c) {
+        project_z_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const double2 *>(V), ldv, nrows, mm, beta,
+                                                         h->zy.as<double2>() + (size_t)c * mm,
+                                                         reinterpret_cast<double2 *>(W) + (size_t)c * ldw);
+        h->launches += 1;
+    }
+    CK(h, cudaGetLastError());
+    return B200K_OK;
 }
 
 int b200k_expv_z(b200k_handle_t h, b200k_op_t op, double t_re, double t_im, const double *b,

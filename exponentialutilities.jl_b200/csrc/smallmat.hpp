@@ -466,18 +466,18 @@ inline bool is_exactly_symmetric(int m, const double *H, int ldh) {
 }
 
 // phiv_dense!(w, A, v, k): w (m x (k+1), ld ldw) = [phi_0(A) v, ..., phi_k(A) v]  (phi.jl:84-115).
-inline int phiv_dense(int m, const double *A, int lda, const double *v, int k, double *w, int ldw,
-                      ExpWork &work) {
+template <typename S>
+inline int phiv_dense(int m, const S *A, int lda, const S *v, int k, S *w, int ldw, ExpWorkT<S> &work) {
     const int N = m + k;
-    std::vector<double> C((size_t)N * N, 0.0);
+    std::vector<S> C((size_t)N * N, S(0.0));
     for (int j = 0; j < m; ++j)
         for (int i = 0; i < m; ++i) C[(size_t)j * N + i] = A[(size_t)j * lda + i];
     for (int i = 0; i < m; ++i) C[(size_t)m * N + i] = v[i];
-    for (int i = m; i < m + k - 1; ++i) C[(size_t)(i + 1) * N + i] = 1.0;
+    for (int i = m; i < m + k - 1; ++i) C[(size_t)(i + 1) * N + i] = S(1.0);
     const int st = expm_higham2005base(N, C.data(), work);
     if (st) return st;
     for (int i = 0; i < m; ++i) {
-        double s = 0.0;
+        S s = S(0.0);
         for (int j = 0; j < m; ++j) s += C[(size_t)j * N + i] * v[j];
         w[i] = s;
     }

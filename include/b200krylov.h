@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B200K_VERSION 100 /* 0.1.0 */
+#define B200K_VERSION 200 /* 0.2.0 */
 
 typedef enum {
     B200K_OK = 0,
@@ -44,6 +44,13 @@ typedef struct b200k_operator *b200k_op_t;
 
 /* ---- library / handle ------------------------------------------------------------------- */
 int b200k_version(void);
+/* sizeof() of the option structs as THIS library was compiled, so that a foreign-language binding can verify its own
+ * struct definitions once at load time (a Julia `struct` that lacks a trailing field would otherwise make the library
+ * read past it).  which: B200K_STRUCT_*; returns -1 for an unknown id. */
+#define B200K_STRUCT_KRYLOV_OPTS 1
+#define B200K_STRUCT_KIOPS_OPTS 2
+#define B200K_STRUCT_TIMESTEP_OPTS 3
+int b200k_sizeof(int which);
 /* Static description of an error code (never NULL). */
 const char *b200k_status_string(int status);
 /* device: CUDA ordinal; stream: a cudaStream_t (CUstream) or NULL for the legacy default stream. */
@@ -182,6 +189,11 @@ int b200k_arnoldi_z(b200k_handle_t h, b200k_op_t op, const double *b, const b200
 /* expv!(w, t, Ks) with complex w and real or complex t = t_re + i t_im (krylov_phiv.jl:200-280). */
 int b200k_expv_ks_z(b200k_handle_t h, double t_re, double t_im, const double *V, int64_t ldv, int64_t nrows,
                     const double *H, int ldh, int m, double beta, double *w);
+/* _phiv!(w, t, Ks, k, cache, correct) on a ComplexF64 subspace (src/krylov_phiv.jl:620-653): W device, complex,
+ * nrows x (k+1), leading dimension ldw (complex elements); errest may be NULL. */
+int b200k_phiv_ks_z(b200k_handle_t h, double t_re, double t_im, const double *V, int64_t ldv, int64_t nrows,
+                    const double *H, int ldh, int m, double beta, int k, int correct, double *W, int64_t ldw,
+                    double *errest);
 /* expv(t, A, b) one-shot on a complex operator. */
 int b200k_expv_z(b200k_handle_t h, b200k_op_t op, double t_re, double t_im, const double *b,
                  const b200k_krylov_opts *opts, double *w, int *m_out, int *breakdown);

@@ -32,6 +32,28 @@ def test_library_exports_every_declared_symbol(eu):
     assert set(protos) == set(syms), set(protos) ^ set(syms)
 
 
+def test_plain_c_consumer_compiles_links_and_runs(eu, tmp_path):
+    """include/b200krylov.h is C (not just ctypes-) clean: a C99 translation unit compiled with gcc -pedantic links
+    against the shared library and calls the host-side entry points; struct sizes agree with b200k_sizeof."""
+    lib = eu.load()
+    exe = str(tmp_path / "consumer")
+    src = os.path.join(ROOT, "tests", "cconsumer", "consumer.c")
+    libdir = os.path.dirname(eu.lib_path())
+    cc = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src,
+                         "-o", exe, "-L", libdir, "-l:libb200krylov.so", "-lm", f"-Wl,-rpath,{libdir}"],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "consumer ok" in run.stdout
+    import ctypes as C
+    from importlib import import_module
+    L = import_module("eu_b200._lib")
+    assert lib.b200k_sizeof(1) == C.sizeof(L.KrylovOpts)
+    assert lib.b200k_sizeof(2) == C.sizeof(L.KiopsOpts)
+    assert lib.b200k_sizeof(3) == C.sizeof(L.TimestepOpts)
+
+
 def test_no_cpu_fallback(eu):
     import torch
     if torch.cuda.is_available():
