@@ -638,26 +638,40 @@ def phiv(t, A, b=None, k=None, *, cache=None, correct=False, errest=False, m=Non
     return (out, res[1]) if errest else out
 
 
-def expv_batched(ts, A, B, *, m=30, tol=1.0e-7, ishermitian=None, iop=0):
-    """nb independent expv(t_i, A, B[:, i]) on a shared operator in one launch.  B: n x nb."""
+def expv_batched(ts, A, B, *, m=30, tol=1.0e-7, ishermitian=None, iop=0, out=None):
+    """nb independent expv(t_i, A, B[:, i]) on a shared operator in one launch.  B: n x nb.
+    ``out``: optional (nb, round_up(n, 2)) float64 CUDA tensor that receives the results (row i = w_i)."""
     op = operator(A)
     eng = op.engine
     ts = np.ascontiguousarray(np.asarray(ts, dtype=np.float64).reshape(-1))
-    Bd, was_np = _to_device(B, eng)
+    if (torch is not None and isinstance(B, torch.Tensor) and B.is_cuda and B.dtype == torch.float64 and B.dim() == 2
+            and B.stride(0) == 1):
+        Bd, was_np = B, False  # column-major view: keep the layout (no .contiguous())
+    else:
+        Bd, was_np = _to_device(B, eng)
     if Bd.dim() != 2 or Bd.shape[0] != op.n or Bd.shape[1] != ts.size:
         raise DimensionMismatch("B must be n x nb with nb == length(ts)")
     nb = ts.size
-    ld = _round_up(op.n, 2)
-    Bt = torch.zeros((nb, ld), dtype=torch.float64, device=eng.device)
-    Bt[:, : op.n] = Bd.t()
-    Wt = torch.empty((nb, ld), dtype=torch.float64, device=eng.device)
+    if (not was_np and Bd.stride(0) == 1 and (nb == 1 or (Bd.stride(1) >= op.n and Bd.stride(1) % 2 == 0))
+            and Bd.data_ptr() % 16 == 0):
+        # already column-major with an even leading dimension (Julia's layout, e.g. `Bt.t()` of an (nb, ld) tensor):
+        # handed to the library as it is
+        Bt, ld = Bd, (Bd.stride(1) if nb > 1 else _round_up(op.n, 2))
+    else:
+        ld = _round_up(op.n, 2)
+        Bt = torch.zeros((nb, ld), dtype=torch.float64, device=eng.device)
+        Bt[:, : op.n] = Bd.t()
+    ldw = _round_up(op.n, 2)
+    Wt = torch.empty((nb, ldw), dtype=torch.float64, device=eng.device) if out is None else out
+    if Wt.shape != (nb, ldw) or Wt.dtype != torch.float64 or not Wt.is_contiguous():
+        raise DimensionMismatch("out must be a contiguous float64 (nb, round_up(n, 2)) CUDA tensor")
     opts = KrylovOpts()
     eng.lib.b200k_krylov_opts_default(C.byref(opts))
     opts.m, opts.tol, opts.iop = int(min(m, op.n)), float(tol), int(iop)
     opts.hermitian = -1 if ishermitian is None else int(bool(ishermitian))
     eng.bind_stream()
     st = eng.lib.b200k_expv_batched(eng.handle, op.ptr, nb, ts.ctypes.data_as(_lib.c_double_p),
-                                    C.c_void_p(Bt.data_ptr()), ld, C.byref(opts), C.c_void_p(Wt.data_ptr()), ld,
+                                    C.c_void_p(Bt.data_ptr()), ld, C.byref(opts), C.c_void_p(Wt.data_ptr()), ldw,
                                     None, None)
     eng.check(st)
     W = Wt[:, : op.n].t()

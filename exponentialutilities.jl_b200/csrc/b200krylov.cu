@@ -678,9 +678,11 @@ int launch_krylov_mv(b200k_context *h, const KrylovCall &c, const BatchPlan &pla
 // Row-sharded launches never reset the barrier counter / sequence number of the communicator: account for what the
 // launch consumed.  Steps js..je ran; every step passes two reductions (sequence numbers), but the XL instance
 // replaces the counter barrier by packet all-reduces for the norm and for inner-product windows of <= LLQ columns.
-void account_sharded(b200k_context *h, b200k_comm *cm, const KrylovCall &c, bool ran, int js, int je) {
+void account_sharded(b200k_context *h, b200k_comm *cm, const KrylovCall &c, bool ran, int js, int je, int nreorth) {
     unsigned nseq = 1, nbar = 1;  // firststep! (or the halo staging barrier of a resumed factorisation)
     if (ran) {
+        nseq += 2u * (unsigned)nreorth;  // a re-orthogonalised step passes two more counter-barrier reductions
+        nbar += 2u * (unsigned)nreorth;
         const int iopw = c.iop > 0 ? c.iop : c.m;
         for (int j = js; j <= je; ++j) {
             nseq += 2u;
@@ -843,7 +845,7 @@ int arnoldi_core(b200k_context *h, b200k_operator *op, const double *b, const b2
     if (op->comm) {  // the multi-GPU barrier counters are never reset: account for this launch's arrivals
         const double b0 = o->init == 0 ? h->scalh.as<double>()[0] : *beta;
         const int js = c.j0 == 0 ? 1 : c.j0;
-        account_sharded(h, op->comm, c, b0 != 0.0, js, h->stath.as<int>()[0]);
+        account_sharded(h, op->comm, c, b0 != 0.0, js, h->stath.as<int>()[0], h->stath.as<int>()[2]);
     }
     const double *Hh = h->Hh.as<double>();
     const int ldhd = m + 1;
@@ -1435,7 +1437,7 @@ int b200k_expv(b200k_handle_t h, b200k_op_t op, double t, const double *b, const
             mo = beta == 0.0 ? o.m : h->stath.as<int>()[0];
             bd = beta == 0.0 ? 0 : h->stath.as<int>()[1];
             if (op->comm) {
-                account_sharded(h, op->comm, c, beta != 0.0, 1, mo);
+                account_sharded(h, op->comm, c, beta != 0.0, 1, mo, h->stath.as<int>()[2]);
             }
             if (*h->errh.as<int>()) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
             if (m_out) *m_out = mo;
@@ -1866,6 +1868,10 @@ int b200k_kiops(b200k_handle_t h, b200k_op_t op, int ntau, const double *tau_out
             const double err = std::fabs(beta * nrm * F[(size_t)j * N + (j - 1)]);
             const double oldomega = omega;
             omega = tau_end * err / (tau * ko->tol);
+            if (!(omega == omega)) {  // NaN (non-finite input): `ceil(Int, NaN)` is an InexactError in the reference
+                status = fail(h, B200K_EARG, "InexactError: the kiops error estimate is NaN (non-finite operator or input?)");
+                break;
+            }
             if (m == oldm && tau != oldtau && ireject >= 1) {
                 order = std::max(1.0, std::log(omega / oldomega) / std::log(tau / oldtau));
                 orderold = false;

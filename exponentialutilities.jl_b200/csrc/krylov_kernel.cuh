@@ -638,25 +638,53 @@ __device__ void krylov_body(const KrylovParams &P, SmemFixed *S, double *ws_smem
             const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
             const int hi = jc;
             dots_phase<VEC>(P, cx, tm, V, lo, hi, part);
-            team_barrier(tm);
-
             const int nc = hi - lo + 1;
             const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
-            for (int ci = cx.warp; ci < nc; ci += NW) {
+            // Arnoldi / IOP: ||w_before||^2 travels with the inner products as quantity nc (DGKS re-orthogonalisation
+            // test, see krylov_kernel_tma.cuh)
+            const bool dgks = !P.lanczos;
+            if (dgks) {
+                double sq = 0.0;
+                for (int i = tid; i < cx.nrows; i += NT) sq = fma(cx.ws[i], cx.ws[i], sq);
+                if (p > 0 && tm.rank == 0 && tid < p) sq = fma(S->wtail[tid], S->wtail[tid], sq);
+                __syncthreads();
+                block_sum_to(cx, sq, part + (long long)nc * CPAD + tm.rank);
+            }
+            team_barrier(tm);
+
+            for (int ci = cx.warp; ci < (dgks ? nc + 1 : nc); ci += NW) {
                 const double s = team_sum(part + (long long)ci * CPAD, tm.C, cx.lane);
                 if (cx.lane == 0) {
                     S->hs[lo + ci - ulo] = s;
-                    if (tm.rank == 0) Hd[(long long)jc * ldh + lo + ci] = s;
+                    if (tm.rank == 0 && ci < nc) Hd[(long long)jc * ldh + lo + ci] = s;
                 }
             }
             if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = beta_prev;
             __syncthreads();
 
-            const double nrm = update_phase<VEC>(P, cx, tm, V, ulo, hi, xout);
+            double nrm = update_phase<VEC>(P, cx, tm, V, ulo, hi, xout);
             block_sum_to(cx, nrm, partn + tm.rank);
             team_barrier(tm);
 
-            const double beta = sqrt(team_sum(partn, tm.C, cx.lane));
+            double beta2 = team_sum(partn, tm.C, cx.lane);
+            if (dgks && beta2 < 0.0625 * S->hs[nc]) {  // second classical Gram-Schmidt pass (eta = 1/4)
+                __syncthreads();
+                dots_phase<VEC>(P, cx, tm, V, lo, hi, part);
+                team_barrier(tm);
+                for (int ci = cx.warp; ci < nc; ci += NW) {
+                    const double s = team_sum(part + (long long)ci * CPAD, tm.C, cx.lane);
+                    if (cx.lane == 0) {
+                        if (tm.rank == 0) Hd[(long long)jc * ldh + lo + ci] = S->hs[ci] + s;
+                        S->hs[ci] = s;
+                    }
+                }
+                __syncthreads();
+                nrm = update_phase<VEC>(P, cx, tm, V, lo, hi, xout);
+                block_sum_to(cx, nrm, partn + tm.rank);
+                team_barrier(tm);
+                beta2 = team_sum(partn, tm.C, cx.lane);
+            }
+            const double beta = sqrt(beta2);
             if (tm.rank == 0 && tid == 0) Hd[(long long)jc * ldh + jc + 1] = beta;
             {  // y /= beta (arnoldi.jl:306): v_{j+1}
                 double *vn = V + (long long)(jc + 1) * ldv;

@@ -898,6 +898,120 @@ __device__ double update_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom 
     return nrm;
 }
 
+
+// ---- DGKS re-orthogonalisation ("twice is enough") -------------------------------------------------------------------
+// Classical Gram-Schmidt loses orthogonality like eps * (||A v_j|| / ||w||)^2 where the reference's modified
+// Gram-Schmidt (arnoldi.jl:301-304) loses eps * ||A v_j|| / ||w||.  Whenever the update removed most of the vector,
+// ||w_after|| < REORTH_ETA * ||w_before||, the step runs a second classical pass on the updated w and adds its
+// coefficients to H -- after which the basis is orthogonal to rounding (Daniel, Gragg, Kaufman, Stewart 1976; Giraud,
+// Langou, Rozloznik 2005).  Well-conditioned Krylov sequences (every BASELINE config) never trigger it, so the hot
+// path pays one extra block reduction per step for ||w_before||^2 and nothing else; the second pass itself is rare, so
+// it reads the basis slice with direct loads instead of going through the producer's tile schedule, and lives in
+// out-of-line functions to keep the hot loop's code size and register allocation unchanged.
+constexpr double REORTH_ETA2 = 0.0625;  // eta = 1/4 (squared norms are compared)
+
+// Per-CTA partial of ||w||^2 for the current w slice -> quantity `col` of the step's partial table.
+// (All three take plain values, not the Cons / TmaGeom / Team structs of the caller: an address that escapes into an
+// out-of-line call would pin those structs in local memory for the whole hot loop.)
+__device__ __noinline__ void sqnorm_partial_c(const KrylovParams &P, SmemTma *S, const double *ws, int nrows, int rank,
+                                              long long part_off, int col, bool with_tail) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double2 *ws2 = reinterpret_cast<const double2 *>(ws);
+    const int units = nrows >> 1;
+    double sq = 0.0;
+    for (int i = tid; i < units; i += NTC) {
+        const double2 w2 = ws2[i];
+        sq = fma(w2.x, w2.x, fma(w2.y, w2.y, sq));
+    }
+    if (with_tail && rank == 0 && P.myrank == 0 && tid < P.p) sq = fma(S->wtail[tid], S->wtail[tid], sq);
+    sq = warp_sum(sq);
+    if (lane == 0) S->redn[warp] = sq;
+    consumer_sync();
+    if (tid == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += S->redn[w];
+        P.peer_part[P.myrank][part_off + (long long)col * P.cpad + rank] = s;
+    }
+    consumer_sync();  // redn is reused by the next block reduction
+}
+
+// Second-pass inner products <v_c, w> for c = lo..hi with direct loads of the CTA's basis slice.
+__device__ __noinline__ void reorth_dots_c(const KrylovParams &P, SmemTma *S, const double *ws, int r0, int nrows, int rank,
+                                           const double *V, int lo, int hi, long long part_off, bool aug) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double2 *ws2 = reinterpret_cast<const double2 *>(ws);
+    const int units = nrows >> 1;
+    int batch = 0;
+    for (int cb = lo; cb <= hi; cb += CB, ++batch) {
+        const int nb = min(CB, hi - cb + 1);
+        double acc[CB];
+#pragma unroll
+        for (int u = 0; u < CB; ++u) acc[u] = 0.0;
+        const double *vb = V + (long long)cb * P.ldv + r0;
+        for (int i = tid; i < units; i += NTC) {
+            const double2 w2 = ws2[i];
+#pragma unroll
+            for (int u = 0; u < CB; ++u)
+                if (u < nb) {
+                    const double2 v2 = *reinterpret_cast<const double2 *>(vb + (long long)u * P.ldv + 2 * i);
+                    acc[u] = fma(v2.x, w2.x, fma(v2.y, w2.y, acc[u]));
+                }
+        }
+        if (aug && P.p > 0 && rank == 0 && P.myrank == 0 && tid == 0) {
+#pragma unroll
+            for (int u = 0; u < CB; ++u)
+                if (u < nb)
+                    for (int kk = 0; kk < P.p; ++kk)
+                        acc[u] = fma(V[(long long)(cb + u) * P.ldv + P.n + kk], S->wtail[kk], acc[u]);
+        }
+        const double r = warp_reduce8(acc, lane);
+        const int buf = batch & 1;
+        if ((lane & 3) == 0) S->red[buf][warp][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = r;
+        consumer_sync();
+        if (tid < nb) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += S->red[buf][w][tid];
+            P.peer_part[P.myrank][part_off + (long long)(cb - lo + tid) * P.cpad + rank] = s;
+        }
+    }
+}
+
+// Second-pass update w -= sum_c h2[c - lo] v_c (direct loads); rewrites the w slice and the gather-buffer copy and
+// returns this thread's partial ||w||^2.
+__device__ __noinline__ double reorth_update_c(const KrylovParams &P, SmemTma *S, double *ws, int r0, int nrows, int rank,
+                                               const double *V, int lo, int hi, const double *h2, double *xout, bool aug) {
+    const int tid = threadIdx.x;
+    double2 *ws2 = reinterpret_cast<double2 *>(ws);
+    double2 *xo2 = reinterpret_cast<double2 *>(xout + r0);
+    const int units = nrows >> 1;
+    double nrm = 0.0;
+    for (int i = tid; i < units; i += NTC) {
+        double2 w2 = ws2[i];
+        const double *vrow = V + r0 + 2 * i;
+        for (int c = hi; c >= lo; --c) {
+            const double hc = h2[c - lo];
+            const double2 v2 = *reinterpret_cast<const double2 *>(vrow + (long long)c * P.ldv);
+            w2.x = fma(-hc, v2.x, w2.x);
+            w2.y = fma(-hc, v2.y, w2.y);
+        }
+        ws2[i] = w2;
+        xo2[i] = w2;
+        nrm = fma(w2.x, w2.x, fma(w2.y, w2.y, nrm));
+    }
+    if (aug && P.p > 0 && tid < P.p) {
+        double wt = S->wtail[tid];
+        for (int c = hi; c >= lo; --c) wt = fma(-h2[c - lo], V[(long long)c * P.ldv + P.n + tid], wt);
+        S->wtail[tid] = wt;
+        if (rank == 0) {
+            xout[P.n + P.nhalo + tid] = wt;
+            if (P.myrank == 0) nrm = fma(wt, wt, nrm);
+        }
+    }
+    return nrm;
+}
+
 // One problem on the consumer side.  Mirrors krylov_body<2> of krylov_kernel.cuh.
 template <int OPK, bool AUG>
 __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom &G, Team &tm, int prob, int nlocal,
@@ -915,7 +1029,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
     const double *xsrc;
     double xscale;
     int jstart;
-    int m_out = P.m, breakdown = 0;
+    int m_out = P.m, breakdown = 0, nreorth = 0;
     const bool sharded = P.nranks > 1;
     const bool via_xb0 = p > 0 || sharded;            // first gather source must carry tail / halo entries
     const double *lpart = P.peer_part[P.myrank];      // this GPU's inboxes
@@ -945,6 +1059,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
             if (tm.rank == 0 && tid == 0) {
                 P.stat[prob * 4 + 0] = P.m;
                 P.stat[prob * 4 + 1] = 0;
+                P.stat[prob * 4 + 2] = 0;
             }
             return;
         }
@@ -1012,7 +1127,10 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         PT_MARK(blockIdx.x, j, 2);
         const int nc = hi - lo + 1;
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
-        team_reduce_c(P, cx, tm, lpart + part, nc, S->hs + (lo - ulo), false);
+        // Arnoldi / IOP: ||w_before||^2 travels with the inner products as quantity nc (re-orthogonalisation test)
+        const bool dgks = !P.lanczos;
+        if (dgks) sqnorm_partial_c(P, S, cx.ws, G.nrows, tm.rank, part, nc, AUG);
+        team_reduce_c(P, cx, tm, lpart + part, dgks ? nc + 1 : nc, S->hs + (lo - ulo), false);
         PT_MARK(blockIdx.x, j, 3);
         if (tm.rank == 0)
             for (int ci = tid; ci < nc; ci += NTC) Hd[(long long)jc * ldh + lo + ci] = S->hs[lo + ci - ulo];
@@ -1026,6 +1144,21 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, sharded);
         PT_MARK(blockIdx.x, j, 5);
 
+        if (dgks && S->bc[0] < REORTH_ETA2 * S->hs[nc]) {
+            // second classical Gram-Schmidt pass (every CTA of every rank takes the same decision: the reduced values
+            // are bitwise identical everywhere).  NaN never triggers it.
+            double *h2 = &S->llv[0][0];  // (packet scratch of the XL instance: unused here)
+            consumer_sync();
+            reorth_dots_c(P, S, cx.ws, G.r0, G.nrows, tm.rank, V, lo, hi, part, AUG);
+            team_reduce_c(P, cx, tm, lpart + part, nc, h2, false);
+            if (tm.rank == 0)
+                for (int ci = tid; ci < nc; ci += NTC) Hd[(long long)jc * ldh + lo + ci] = S->hs[ci] + h2[ci];
+            const double nrm2 = reorth_update_c(P, S, cx.ws, G.r0, G.nrows, tm.rank, V, lo, hi, h2, xout, AUG);
+            block_sum_to_c(P, cx, nrm2, partn + tm.rank);
+            push_halo(P, cx, G, tm, xoff);
+            team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, sharded);
+            ++nreorth;
+        }
         const double beta = sqrt(S->bc[0]);
         if (tm.rank == 0 && tid == 0) Hd[(long long)jc * ldh + jc + 1] = beta;
         {
@@ -1054,6 +1187,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
     if (tm.rank == 0 && tid == 0) {
         P.stat[prob * 4 + 0] = m_out;
         P.stat[prob * 4 + 1] = breakdown;
+        P.stat[prob * 4 + 2] = nreorth;  // steps that took the second Gram-Schmidt pass (host: barrier accounting)
     }
 }
 
@@ -1263,6 +1397,7 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
             if (tm.rank == 0 && tid == 0) {
                 P.stat[prob * 4 + 0] = P.m;
                 P.stat[prob * 4 + 1] = 0;
+                P.stat[prob * 4 + 2] = 0;
             }
             return;
         }
@@ -1429,6 +1564,7 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
     if (tm.rank == 0 && tid == 0) {
         P.stat[prob * 4 + 0] = m_out;
         P.stat[prob * 4 + 1] = breakdown;
+        P.stat[prob * 4 + 2] = 0;
     }
 }
 

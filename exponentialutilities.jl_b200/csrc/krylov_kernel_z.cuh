@@ -222,74 +222,103 @@ __global__ void __launch_bounds__(NT, 1) krylov_z_kernel(const __grid_constant__
         }
         __syncthreads();
 
-        // ---- inner products h_i = <v_i, w> = sum conj(v_i) w over the window ----
+        // ---- inner products h_i = <v_i, w> = sum conj(v_i) w over the window, update, norm -- at most twice:
+        // the second classical Gram-Schmidt pass runs when ||w_after|| < ||w_before|| / 4 (DGKS re-orthogonalisation,
+        // see krylov_kernel_tma.cuh) and adds its coefficients to H ----
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
         const int hi = jc;
-        int batch = 0;
-        for (int cb = lo; cb <= hi; cb += CB, ++batch) {
-            const int nb = min(CB, hi - cb + 1);
-            double are[CB], aim[CB];
-#pragma unroll
-            for (int u = 0; u < CB; ++u) are[u] = aim[u] = 0.0;
-            const double2 *vb = V + (long long)cb * ldv + r0;
-            for (int i = tid; i < nrows; i += NT) {
-                const double2 w1 = ws[i];
-#pragma unroll
-                for (int u = 0; u < CB; ++u)
-                    if (u < nb) {
-                        const double2 v1 = ldz(vb + (long long)u * ldv + i);
-                        are[u] = fma(v1.x, w1.x, fma(v1.y, w1.y, are[u]));
-                        aim[u] = fma(v1.x, w1.y, fma(-v1.y, w1.x, aim[u]));
-                    }
-            }
-            const double rr = warp_reduce8(are, lane);
-            const double ri = warp_reduce8(aim, lane);
-            const int buf = batch & 1;
-            if ((lane & 3) == 0)
-                S->red[buf][warp][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = make_double2(rr, ri);
-            __syncthreads();
-            if (tid < nb) {
-                double2 s = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    s.x += S->red[buf][w][tid].x;
-                    s.y += S->red[buf][w][tid].y;
-                }
-                part[(long long)(cb - lo + tid) * CPAD + tm.rank] = s;
-            }
-        }
-        team_barrier(tm);
-
         const int nc = hi - lo + 1;
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
-        for (int ci = warp; ci < nc; ci += NW) {
-            double2 s = team_sum_z(part + (long long)ci * CPAD, tm.C, lane);
-            if (P.lanczos) s.y = 0.0;  // coeff(U <: Real, alpha) = real(alpha)
-            if (lane == 0) {
-                S->hs[lo + ci - ulo] = s;
-                if (tm.rank == 0) P.Hd[(long long)jc * P.ldh + lo + ci] = s;
+        const bool dgks = !P.lanczos;
+        double beta2 = 0.0, wsq_before = 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            int batch = 0;
+            for (int cb = lo; cb <= hi; cb += CB, ++batch) {
+                const int nb = min(CB, hi - cb + 1);
+                double are[CB], aim[CB];
+#pragma unroll
+                for (int u = 0; u < CB; ++u) are[u] = aim[u] = 0.0;
+                const double2 *vb = V + (long long)cb * ldv + r0;
+                for (int i = tid; i < nrows; i += NT) {
+                    const double2 w1 = ws[i];
+#pragma unroll
+                    for (int u = 0; u < CB; ++u)
+                        if (u < nb) {
+                            const double2 v1 = ldz(vb + (long long)u * ldv + i);
+                            are[u] = fma(v1.x, w1.x, fma(v1.y, w1.y, are[u]));
+                            aim[u] = fma(v1.x, w1.y, fma(-v1.y, w1.x, aim[u]));
+                        }
+                }
+                const double rr = warp_reduce8(are, lane);
+                const double ri = warp_reduce8(aim, lane);
+                const int buf = batch & 1;
+                if ((lane & 3) == 0)
+                    S->red[buf][warp][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = make_double2(rr, ri);
+                __syncthreads();
+                if (tid < nb) {
+                    double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        s.x += S->red[buf][w][tid].x;
+                        s.y += S->red[buf][w][tid].y;
+                    }
+                    part[(long long)(cb - lo + tid) * CPAD + tm.rank] = s;
+                }
             }
-        }
-        if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = make_double2(beta_prev, 0.0);
-        __syncthreads();
-
-        // ---- update w -= sum_c h_c v_c (reverse order), partial ||w||^2, publish the unnormalised w ----
-        double nrm = 0.0;
-        for (int i = tid; i < nrows; i += NT) {
-            double2 w1 = ws[i];
-            for (int c = hi; c >= ulo; --c) {
-                const double2 hc = S->hs[c - ulo];
-                const double2 v1 = ldz(V + (long long)c * ldv + r0 + i);
-                w1 = zfma(make_double2(-hc.x, -hc.y), v1, w1);
+            if (dgks && pass == 0) {  // ||w_before||^2 travels with the inner products as quantity nc
+                double sq = 0.0;
+                for (int i = tid; i < nrows; i += NT) {
+                    const double2 w1 = ws[i];
+                    sq = fma(w1.x, w1.x, fma(w1.y, w1.y, sq));
+                }
+                __syncthreads();
+                block_sum_to_z(S, tid, lane, warp, sq, &part[(long long)nc * CPAD + tm.rank].x);
             }
-            ws[i] = w1;
-            xout[r0 + i] = w1;
-            nrm = fma(w1.x, w1.x, fma(w1.y, w1.y, nrm));
-        }
-        block_sum_to_z(S, tid, lane, warp, nrm, partn + tm.rank);
-        team_barrier(tm);
+            team_barrier(tm);
 
-        const double beta = sqrt(team_sum(partn, tm.C, lane));
+            for (int ci = warp; ci < ((dgks && pass == 0) ? nc + 1 : nc); ci += NW) {
+                double2 s = team_sum_z(part + (long long)ci * CPAD, tm.C, lane);
+                if (P.lanczos) s.y = 0.0;  // coeff(U <: Real, alpha) = real(alpha)
+                if (lane == 0) {
+                    if (ci == nc) {
+                        S->hs[MAXCOL - 1].x = s.x;  // (m < MAXCOL: the last slot is never a window column)
+                    } else if (pass == 0) {
+                        S->hs[lo + ci - ulo] = s;
+                        if (tm.rank == 0) P.Hd[(long long)jc * P.ldh + lo + ci] = s;
+                    } else {
+                        if (tm.rank == 0) {
+                            const double2 h1 = S->hs[ci];
+                            P.Hd[(long long)jc * P.ldh + lo + ci] = make_double2(h1.x + s.x, h1.y + s.y);
+                        }
+                        S->hs[ci] = s;
+                    }
+                }
+            }
+            if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = make_double2(beta_prev, 0.0);
+            __syncthreads();
+            if (dgks && pass == 0) wsq_before = S->hs[MAXCOL - 1].x;
+
+            // ---- update w -= sum_c h_c v_c (reverse order), partial ||w||^2, publish the unnormalised w ----
+            double nrm = 0.0;
+            for (int i = tid; i < nrows; i += NT) {
+                double2 w1 = ws[i];
+                for (int c = hi; c >= ulo; --c) {
+                    const double2 hc = S->hs[c - ulo];
+                    const double2 v1 = ldz(V + (long long)c * ldv + r0 + i);
+                    w1 = zfma(make_double2(-hc.x, -hc.y), v1, w1);
+                }
+                ws[i] = w1;
+                xout[r0 + i] = w1;
+                nrm = fma(w1.x, w1.x, fma(w1.y, w1.y, nrm));
+            }
+            block_sum_to_z(S, tid, lane, warp, nrm, partn + tm.rank);
+            team_barrier(tm);
+            beta2 = team_sum(partn, tm.C, lane);
+            if (!(dgks && pass == 0 && beta2 < 0.0625 * wsq_before)) break;
+            __syncthreads();
+        }
+
+        const double beta = sqrt(beta2);
         if (tm.rank == 0 && tid == 0) P.Hd[(long long)jc * P.ldh + jc + 1] = make_double2(beta, 0.0);
         {
             double2 *vn = V + (long long)(jc + 1) * ldv;

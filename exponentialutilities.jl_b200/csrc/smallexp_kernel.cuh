@@ -186,7 +186,7 @@ __device__ double *se_expm_core(int n, double *sm, double *sc, double *colsum, b
             off = 28;
             N_ = 14;
             const double s2 = log2(best / 5.4);
-            if (s2 > 0) si_ = (int)ceil(s2);
+            if (s2 > 0) si_ = (int)ceil(fmin(s2, 1100.0));  // (Inf norm: bounded squaring loop, the result is NaN anyway)
         }
         s_cfg[0] = off;
         s_cfg[1] = N_;

@@ -304,7 +304,7 @@ inline int expm_higham2005base(int n, S *A, ExpWorkT<S> &w) {
         int si = 0;
         const size_t sz = (size_t)n * n;
         if (s > 0) {
-            si = (int)std::ceil(s);
+            si = (int)std::ceil(std::min(s, 1100.0));  // (Inf norm: bounded loop, the result is NaN anyway)
             const double f = std::ldexp(1.0, si);
             for (size_t i = 0; i < sz; ++i) A[i] /= f;
         }

@@ -375,6 +375,15 @@ def exponential_higham2005base(A):
 # --------------------------------------------------------------------------------------
 # expv / phiv  (src/krylov_phiv.jl, src/phi.jl)
 # --------------------------------------------------------------------------------------
+def expv_small(t, Hcopy):
+    """The small dense phase of expv! (src/krylov_phiv.jl:223-244): exp(t*H) e1 for the m x m block Hcopy."""
+    if np.array_equal(Hcopy, Hcopy.conj().T):
+        lam, Z = sla.eigh_tridiagonal(np.real(np.diag(Hcopy)).copy(),
+                                      np.real(np.diag(Hcopy, -1)).copy(), lapack_driver="stemr")
+        return Z @ (np.exp(t * lam) * Z[0, :])
+    return exponential_higham2005base(t * Hcopy)[:, 0]
+
+
 def expv_ks(t, Ks):
     """expv!(w, t, Ks) -- src/krylov_phiv.jl:200-280 (real and complex t)."""
     m, beta, V, H = Ks.m, Ks.beta, Ks.getV(), Ks.getH()
@@ -384,12 +393,7 @@ def expv_ks(t, Ks):
         return np.zeros(n, dtype=wtype)
     Hcopy = np.array(H[:m, :m], copy=True)
     Vm = V[:, :m]
-    if np.array_equal(Hcopy, Hcopy.conj().T):
-        lam, Z = sla.eigh_tridiagonal(np.real(np.diag(Hcopy)).copy(),
-                                      np.real(np.diag(Hcopy, -1)).copy(), lapack_driver="stemr")
-        expHe = Z @ (np.exp(t * lam) * Z[0, :])
-    else:
-        expHe = exponential_higham2005base(t * Hcopy)[:, 0]
+    expHe = expv_small(t, Hcopy)
     return beta * (Vm @ expHe)
 
 

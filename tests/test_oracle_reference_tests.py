@@ -188,3 +188,28 @@ def test_gpu_testset_inputs_on_the_oracle(oracle):
     Ks = oracle.arnoldi(A4, v0, tol=1e-7, ishermitian_=False)
     assert relerr(oracle.expv_ks(0.01j, Ks), sla.expm(0.01j * A4) @ v0) < SQRT_EPS
 
+
+
+# ---- the C/OpenMP restatement (oracle/cpu_krylov.c, the "best-effort CPU" baseline) against the NumPy port ----------
+def test_c_openmp_restatement_matches_numpy_port():
+    from conftest import convdiff2d, laplacian2d, relerr
+    from oracle import cpu_fast as F
+    from oracle import oracle as O
+    rng = np.random.default_rng(21)
+    for A, herm, iop in ((laplacian2d(60, 45), True, 0), (laplacian2d(60, 45), False, 0), (convdiff2d(50, 40), False, 0),
+                         (convdiff2d(50, 40), False, 2)):
+        b = rng.standard_normal(A.shape[0])
+        V, H, beta, mo, bd = F.arnoldi(A, b, m=25, iop=iop, ishermitian_=herm)
+        Ko = O.arnoldi(A, b, m=25, iop=iop, ishermitian_=herm)
+        assert mo == Ko.m and bd == Ko.wasbreakdown and abs(beta - Ko.beta) <= 1e-14 * Ko.beta
+        assert np.abs(H[:26, :25] - Ko.getH()).max() < 1e-12
+        assert relerr(V[:26].T, Ko.getV()) < 1e-10
+        assert relerr(F.expv(0.7, A, b, m=25, iop=iop, ishermitian_=herm), O.expv(0.7, A, b, m=25, iop=iop, ishermitian_=herm)) < 1e-12
+    # happy breakdown and the zero vector
+    import scipy.sparse as sp
+    v = rng.standard_normal(30)
+    v /= np.linalg.norm(v)
+    Pm = sp.csr_matrix(np.outer(v, v))
+    V, H, beta, mo, bd = F.arnoldi(Pm, rng.standard_normal(30), m=10)
+    assert mo == 2 and bd
+    assert np.all(F.expv(1.0, Pm, np.zeros(30), m=10) == 0.0)
