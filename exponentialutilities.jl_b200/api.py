@@ -83,7 +83,7 @@ class Engine:
 
     def set_flag(self, name: str, value: bool):
         """'force_ldg' or 'host_smallexp' (include/b200krylov.h: B200K_FLAG_*)."""
-        flag = {"force_ldg": 1, "host_smallexp": 2, "l2hint": 3, "no_xl": 4, "no_mv": 5}[name]
+        flag = {"force_ldg": 1, "host_smallexp": 2, "l2hint": 3, "no_xl": 4, "no_mv": 5, "sym_pade": 6}[name]
         self.check(self.lib.b200k_set_flag(self.handle, flag, int(value)))
 
     def last_kernel(self):

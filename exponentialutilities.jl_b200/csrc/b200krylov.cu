@@ -88,6 +88,7 @@ struct b200k_context {
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime (no libcuda link dependency)
     int l2hint = -1;        // B200K_FLAG_L2HINT: -1 automatic, 0 never, 1 always evict_first for operator chunks
     long long l2_bytes = 0;
+    int sym_pade = 0;       // B200K_FLAG_SYM_PADE: device small exponential of a Lanczos H by Pade instead of Chebyshev
     int host_smallexp = 0;  // B200K_SMALLEXP=host: one-shot / batched expv do the small exponential on the host
     DevBuf tdev, errdev;
     HostBuf errh;
@@ -928,6 +929,7 @@ int launch_smallexp_project(b200k_context *h, int nprob, int m, int lanczos, con
     S.t = t_host[0];
     S.m = m;
     S.lanczos = lanczos;
+    S.force_pade = h->sym_pade;
     S.Y = h->Y.as<double>();
     S.ldy = m;
     S.betavec = h->betavec.as<double>();
@@ -1167,6 +1169,7 @@ int b200k_set_flag(b200k_handle_t h, int flag, int value) {
     else if (flag == B200K_FLAG_NO_XL) h->no_xl = value ? 1 : 0;
     else if (flag == B200K_FLAG_NO_MV) h->no_mv = value == 2 ? 2 : (value ? 1 : 0);
     else if (flag == B200K_FLAG_L2HINT) h->l2hint = value < 0 ? -1 : (value ? 1 : 0);
+    else if (flag == B200K_FLAG_SYM_PADE) h->sym_pade = value ? 1 : 0;
     else return fail(h, B200K_EARG, "unknown flag");
     return B200K_OK;
 }

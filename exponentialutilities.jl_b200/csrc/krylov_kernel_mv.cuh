@@ -74,7 +74,7 @@ __device__ void mv_producer(const KrylovParams &P, SmemTma *S, Ring &rg, const T
             ++issued;
         }
     }
-    while (S->stop_seq < seq) __nanosleep(256);
+    while (flag_get(&S->stop_seq) < seq) __nanosleep(256);
     const unsigned ns = (unsigned)rg.nslot;
     const unsigned first = issued > ns ? issued - ns : 0u;
     for (unsigned t = first; t < issued; ++t) mbar_wait(&S->full[t % ns], (t / ns) & 1u);
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(NT2, 1) krylov_mv_kernel(const __grid_constant
             cx.rg = Ring{ring, P.nslot, 0, 0u};
             mv_consumer<GW>(P, cx, G, tm, grp, nlocal, xb0, xb1);
             consumer_sync();
-            if (tid == 0) S->stop_seq = nlocal + 1;
+            if (tid == 0) flag_set(&S->stop_seq, nlocal + 1);
         }
         __syncthreads();
         if (grp + P.nteams < ngroups) {

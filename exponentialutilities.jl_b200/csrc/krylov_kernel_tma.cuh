@@ -49,9 +49,14 @@ struct __align__(128) SmemTma {
     int chunk_local[MAXCH2];  // XL: every column of the chunk lies in this CTA's slice (learnt by the first mat-vec)
     double bc[2];             // reduced scalars (squared norm) broadcast to the CTA
     double llv[LLQ][CPAD];    // packets of a fused barrier + all-reduce (ll_collect), one value per CTA of the team
-    volatile int cols_ready;  // number of complete basis columns of the current problem
-    volatile int stop_seq;    // consumers finished local problem #stop_seq (1-based)
+    // Flags the producer lane polls while the consumers run.  All accesses after initialisation are shared-memory
+    // ATOMICS (flag_set / flag_get): a polled flag is a data race by definition for plain loads and stores
+    // (compute-sanitizer racecheck reports it), atomics make the single-writer / single-reader protocol well defined.
+    int cols_ready;  // number of complete basis columns of the current problem
+    int stop_seq;    // consumers finished local problem #stop_seq (1-based)
 };
+__device__ __forceinline__ void flag_set(int *f, int v) { atomicExch(f, v); }
+__device__ __forceinline__ int flag_get(int *f) { return atomicAdd(f, 0); }
 
 // Per-phase timestamps (profiling builds only: -DB200K_PHASE_TIMING, scripts/phase_timing.py).
 #ifdef B200K_PHASE_TIMING
@@ -187,14 +192,14 @@ struct TmaGeom {
 // instruction, so there is nothing for the other lanes to do).
 __device__ __forceinline__ bool prod_acquire(SmemTma *S, const Ring &rg, int seq, int) {
     while (!mbar_try_wait(&S->empty[rg.slot], rg.phase ^ 1u)) {
-        if (S->stop_seq >= seq) return false;
+        if (flag_get(&S->stop_seq) >= seq) return false;
     }
     return true;
 }
 
 __device__ __forceinline__ bool prod_wait_col(SmemTma *S, int col, int seq, int) {
-    while (S->cols_ready <= col) {
-        if (S->stop_seq >= seq) return false;
+    while (flag_get(&S->cols_ready) <= col) {
+        if (flag_get(&S->stop_seq) >= seq) return false;
     }
     return true;
 }
@@ -338,7 +343,7 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
         }
     }
     // the consumers decide when the problem is over (m steps, happy breakdown, or beta == 0)
-    while (S->stop_seq < seq) __nanosleep(256);  // (do not steal issue slots from the consumers while waiting)
+    while (flag_get(&S->stop_seq) < seq) __nanosleep(256);  // (do not steal issue slots from the consumers while waiting)
     // every copy that was issued must have landed before the ring is re-initialised / the CTA exits
     const unsigned ns = (unsigned)rg.nslot;
     const unsigned first = issued > ns ? issued - ns : 0u;
@@ -785,16 +790,22 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
     consumer_sync();
 }
 
+// `want_sq`: Arnoldi / IOP steps also reduce ||w||^2 of the incoming w (re-orthogonalisation test, see below) as
+// quantity hi - lo + 1.  It rides in a free accumulator slot of the last batch; returns false if that batch was
+// full (window a multiple of 8 columns) and the caller has to reduce it separately.
 template <int OPK, bool AUG>
-__device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
-                             int lo, int hi, long long part_off) {
+__device__ bool dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
+                             int lo, int hi, long long part_off, bool want_sq) {
     SmemTma *S = cx.S;
     const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
     const double2 *ws2 = reinterpret_cast<const double2 *>(cx.ws);
     int batch = 0;
+    bool sq_done = false;
     for (int cb = lo; cb <= hi; cb += CB, ++batch) {
         const int nb = min(CB, hi - cb + 1);
+        const bool sq_here = want_sq && nb < CB && cb + CB > hi;
         double acc[CB];
+        double sq = 0.0;
 #pragma unroll
         for (int u = 0; u < CB; ++u) acc[u] = 0.0;
         for (int k = 0; k < G.ntk; ++k) {
@@ -805,6 +816,10 @@ __device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
             for (int q = 0; q < PPT; ++q) {
                 const int idx = tid + q * NTC;
                 wr[q] = idx < pairs ? ws2[pbase + idx] : make_double2(0.0, 0.0);
+            }
+            if (sq_here) {
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) sq = fma(wr[q].x, wr[q].x, fma(wr[q].y, wr[q].y, sq));
             }
 #pragma unroll
             for (int u = 0; u < CB; ++u) {
@@ -829,18 +844,27 @@ __device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
                 if (u < nb)
                     for (int kk = 0; kk < P.p; ++kk)
                         acc[u] = fma(V[(long long)(cb + u) * P.ldv + P.n + kk], S->wtail[kk], acc[u]);
+            if (sq_here)
+                for (int kk = 0; kk < P.p; ++kk) sq = fma(S->wtail[kk], S->wtail[kk], sq);
+        }
+        if (sq_here) {
+#pragma unroll
+            for (int u = 0; u < CB; ++u)
+                if (u == nb) acc[u] = sq;
+            sq_done = true;
         }
         const double r = warp_reduce8(acc, lane);
         const int buf = batch & 1;
         if ((lane & 3) == 0) S->red[buf][warp][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = r;
         consumer_sync();
-        if (tid < nb) {
+        if (tid < nb + (sq_here ? 1 : 0)) {
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) s += S->red[buf][w][tid];
             P.peer_part[P.myrank][part_off + (long long)(cb - lo + tid) * P.cpad + tm.rank] = s;
         }
     }
+    return sq_done || !want_sq;
 }
 
 template <int OPK, bool AUG>
@@ -1084,7 +1108,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         }
         fence_proxy_async();
         consumer_sync();
-        if (tid == 0) S->cols_ready = 1;
+        if (tid == 0) flag_set(&S->cols_ready, 1);
         xscale = 1.0 / beta;
         jstart = 1;
     } else {
@@ -1123,13 +1147,13 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
 
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
         const int hi = jc;
-        dots_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, hi, part);
-        PT_MARK(blockIdx.x, j, 2);
-        const int nc = hi - lo + 1;
-        const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
         // Arnoldi / IOP: ||w_before||^2 travels with the inner products as quantity nc (re-orthogonalisation test)
         const bool dgks = !P.lanczos;
-        if (dgks) sqnorm_partial_c(P, S, cx.ws, G.nrows, tm.rank, part, nc, AUG);
+        const int nc = hi - lo + 1;
+        const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
+        if (!dots_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, hi, part, dgks))
+            sqnorm_partial_c(P, S, cx.ws, G.nrows, tm.rank, part, nc, AUG);
+        PT_MARK(blockIdx.x, j, 2);
         team_reduce_c(P, cx, tm, lpart + part, dgks ? nc + 1 : nc, S->hs + (lo - ulo), false);
         PT_MARK(blockIdx.x, j, 3);
         if (tm.rank == 0)
@@ -1173,7 +1197,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         }
         fence_proxy_async();  // the producer's TMA reads of this column must see these generic-proxy stores
         consumer_sync();
-        if (tid == 0) S->cols_ready = jc + 2;
+        if (tid == 0) flag_set(&S->cols_ready, jc + 2);
         PT_MARK(blockIdx.x, j, 6);
         xsrc = xout;
         xscale = 1.0 / beta;
@@ -1525,7 +1549,7 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
             if (!sharded) ll_collect(P, cx, tm, 1, S->bc, true);
             else shard_collect(P, cx, tm, 1, S->bc, true);
             PT_MARK(blockIdx.x, j, 5);
-            if (tid == 0) S->cols_ready = jc + 1;
+            if (tid == 0) flag_set(&S->cols_ready, jc + 1);
             beta = sqrt(S->bc[0]);
             if (tm.rank == 0 && tid == 0) Hd[(long long)jc * ldh + jc + 1] = beta;
             {  // the new w becomes the resident vector of the next step
@@ -1649,7 +1673,7 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
             if constexpr (XL) consumer_problem_xl<OPK, AUG, true, GW>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
             else consumer_problem<OPK, AUG>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
             consumer_sync();
-            if (tid == 0) S->stop_seq = nlocal + 1;
+            if (tid == 0) flag_set(&S->stop_seq, nlocal + 1);
         }
         // CTA-wide resynchronisation: the ring is re-initialised between problems
         __syncthreads();

@@ -51,6 +51,7 @@ struct SmallExpParams {
     double t;
     int m;               // requested dimension (used when beta == 0)
     int lanczos;         // H holds only diagonal + sub-diagonal: mirror it
+    int force_pade;      // tests / A-B: never take the Chebyshev path for symmetric tridiagonal H
     double *Y;           // [nprob][ldy] out
     int ldy;
     double *betavec;     // [nprob] out
@@ -351,6 +352,162 @@ __device__ double *se_expm_core(int n, double *sm, double *sc, double *colsum, b
     return Xc;
 }
 
+// ---- symmetric tridiagonal H (Lanczos): exp(t T) e1 by ONE warp, no matrix function -------------------------------
+// The reference takes eigen!(SymTridiagonal) here (krylov_phiv.jl:225-229).  A QL / QR eigensolver is a chain of ~m^2
+// dependent rotations (sqrt + 2 divisions each: ~400 k cycles for m = 30 on one SM) and the Pade path costs 65 us
+// (nine 30^3 products + a pivoted LU), one CTA busy while 147 SMs idle -- 10 % of a Lanczos expv at C2.  What expv!
+// needs is only the VECTOR exp(t T) e1, which a Chebyshev expansion on the spectral interval [a, b] gives with
+// three-term recurrences on m-vectors:
+//     exp(t x) = e^{t b} * [ i_0(z) + 2 sum_k i_k(z) T_k(xi) ],   x = c + h xi,  z = t h,  i_k = e^{-z} I_k(z)   (t >= 0)
+// (t < 0: T -> -T).  K = z + 12 z^(1/3) + 25 terms reach 1e-17 (Bessel coefficients by Miller's backward recurrence).
+// The interval must be TIGHT at the upper end: rounding errors are eps * e^{t b}, the result is ~ e^{t lambda_max}.
+// So b comes from Sturm-sequence multisection (32 shifts per round, one per lane: each round shrinks the bracket of
+// lambda_max 33x) started from the Gershgorin bounds until t (b - lambda_max) <= 0.02; the lower end a only costs
+// terms and stays at its Gershgorin value.  Same function of the same matrix as the reference's eigen branch,
+// agreeing to ~K eps (tests compare with the host QL path); z > 150 (or NaN) falls back to the Pade path below.
+// Measured: ~10 k cycles (5 us) instead of 130 k.
+constexpr int LC_KMAX = 256;
+constexpr double LC_ZMAX = 150.0;
+
+__device__ bool se_lanczos_cheb(int n, const double *H, int ldh, double t, double *yout, int ldy) {
+    __shared__ double s_a[SE_MAXM], s_b[SE_MAXM + 1], s_d[SE_MAXM], s_e[SE_MAXM + 1];
+    __shared__ double s_u[3][SE_MAXM + 2];
+    __shared__ double s_ck[LC_KMAX + 2];
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const double sg = t < 0.0 ? -1.0 : 1.0;
+    const double tt = fabs(t);
+    for (int i = lane; i < n; i += 32) {
+        s_a[i] = sg * H[(long long)i * ldh + i];
+        s_b[i] = (i < n - 1) ? sg * H[(long long)i * ldh + i + 1] : 0.0;  // couples i and i + 1
+    }
+    __syncwarp();
+    if (n == 1) {
+        if (lane == 0) yout[0] = exp(tt * s_a[0]);
+        for (int i = 1 + lane; i < ldy; i += 32) yout[i] = 0.0;
+        return true;
+    }
+    // Gershgorin bounds
+    double glo = 1.0e300, ghi = -1.0e300;
+    bool bad = false;
+    for (int i = lane; i < n; i += 32) {
+        const double r = (i > 0 ? fabs(s_b[i - 1]) : 0.0) + fabs(s_b[i]);
+        glo = fmin(glo, s_a[i] - r);
+        ghi = fmax(ghi, s_a[i] + r);
+        bad = bad || !(s_a[i] - r == s_a[i] - r) || !(fabs(s_a[i]) + r < 1.0e300);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        glo = fmin(glo, __shfl_xor_sync(full, glo, o));
+        ghi = fmax(ghi, __shfl_xor_sync(full, ghi, o));
+    }
+    if (__any_sync(full, bad)) return false;  // NaN / Inf in H: the Pade path propagates it
+    // multisection for a tight upper bound of lambda_max: count(x) = #eigenvalues < x (Sturm sequence of T - x I)
+    double lo = glo, hi = ghi;
+    for (int round = 0; round < 6 && tt * (hi - lo) > 0.02; ++round) {
+        const double x = lo + (hi - lo) * (double)(lane + 1) * (1.0 / 33.0);
+        double d = s_a[0] - x;
+        int cnt = d < 0.0 ? 1 : 0;
+        for (int i = 1; i < n; ++i) {
+            if (d == 0.0) d = 1.0e-300;
+            const double bq = s_b[i - 1];
+            d = (s_a[i] - x) - bq * bq / d;
+            cnt += d < 0.0 ? 1 : 0;
+        }
+        const unsigned m_all = __ballot_sync(full, cnt == n);
+        if (m_all == 0u) {
+            lo = __shfl_sync(full, x, 31);
+        } else {
+            const int jf = __ffs(m_all) - 1;
+            hi = __shfl_sync(full, x, jf);
+            if (jf > 0) lo = __shfl_sync(full, x, jf - 1);
+        }
+    }
+    const double a = glo, b = hi;
+    const double c = 0.5 * (a + b), h = 0.5 * (b - a);
+    const double z = tt * h;
+    if (!(z <= LC_ZMAX)) return false;
+    double *u0 = &s_u[0][1], *u1 = &s_u[1][1], *u2 = &s_u[2][1];
+    for (int i = lane; i < n + 2; i += 32) s_u[0][i] = s_u[1][i] = s_u[2][i] = 0.0;
+    __syncwarp();
+    double y0 = 0.0, y1 = 0.0;  // this lane's entries lane and lane + 32 of the result (n <= 64)
+    if (z < 0.5) {
+        // Taylor series of exp(t (T - c I)) e1: ||t (T - c I)|| <= z < 1/2, 20 terms
+        for (int i = lane; i < n; i += 32) {
+            s_d[i] = tt * (s_a[i] - c);
+            s_e[i] = tt * s_b[i];
+        }
+        if (lane == 0) u0[0] = 1.0;
+        __syncwarp();
+        y0 = lane == 0 ? 1.0 : 0.0;
+        for (int k = 1; k <= 20; ++k) {
+            const double rk = 1.0 / (double)k;
+            for (int i = lane, q = 0; i < n; i += 32, ++q) {
+                const double v = (s_d[i] * u0[i] + (i > 0 ? s_e[i - 1] : 0.0) * u0[i - 1] + s_e[i] * u0[i + 1]) * rk;
+                u1[i] = v;
+                if (q == 0) y0 += v; else y1 += v;
+            }
+            __syncwarp();
+            double *tp = u0; u0 = u1; u1 = tp;
+        }
+        const double scale = exp(tt * c);
+        y0 *= scale;
+        y1 *= scale;
+    } else {
+        const int N = (int)(z + 12.0 * cbrt(z) + 25.0);  // <= 239
+        if (lane == 0) {  // Miller: p_{k-1} = (2k / z) p_k + p_{k+1}, normalised by 1 = i_0 + 2 sum i_k
+            const double tz = 2.0 / z;
+            double pk1 = 0.0, pk = 1.0e-100, sum = 0.0;
+            s_ck[N] = pk;
+            for (int k = N; k >= 1; --k) {
+                const double pm = fma(tz * (double)k, pk, pk1);
+                sum += pk;
+                pk1 = pk;
+                pk = pm;
+                s_ck[k - 1] = pm;
+            }
+            s_ck[N + 1] = 1.0 / (pk + 2.0 * sum);
+        }
+        const double rh = 1.0 / h;
+        for (int i = lane; i < n; i += 32) {
+            s_d[i] = (s_a[i] - c) * rh;
+            s_e[i] = s_b[i] * rh;
+        }
+        __syncwarp();
+        const double nrm = s_ck[N + 1];
+        // u0 = e1, u1 = M e1
+        if (lane == 0) u0[0] = 1.0;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32)
+            u1[i] = s_d[i] * u0[i] + (i > 0 ? s_e[i - 1] : 0.0) * u0[i - 1] + s_e[i] * u0[i + 1];
+        __syncwarp();
+        {
+            const double c0 = s_ck[0] * nrm, c1 = 2.0 * s_ck[1] * nrm;
+            y0 = (lane == 0 ? c0 : 0.0) + (lane < n ? c1 * u1[lane] : 0.0);
+            y1 = lane + 32 < n ? c1 * u1[lane + 32] : 0.0;
+        }
+        for (int k = 2; k <= N; ++k) {
+            const double ckk = 2.0 * s_ck[k] * nrm;
+            for (int i = lane, q = 0; i < n; i += 32, ++q) {
+                const double mv = s_d[i] * u1[i] + (i > 0 ? s_e[i - 1] : 0.0) * u1[i - 1] + s_e[i] * u1[i + 1];
+                const double v = 2.0 * mv - u0[i];
+                u2[i] = v;
+                if (q == 0) y0 = fma(ckk, v, y0); else y1 = fma(ckk, v, y1);
+            }
+            __syncwarp();
+            double *tp = u0; u0 = u1; u1 = u2; u2 = tp;
+        }
+        const double scale = exp(tt * b);
+        y0 *= scale;
+        y1 *= scale;
+    }
+    if (lane < n) yout[lane] = y0;
+    if (lane + 32 < n) yout[lane + 32] = y1;
+    for (int i = n + lane; i < ldy; i += 32) yout[i] = 0.0;
+    return true;
+}
+
+
 __global__ void __launch_bounds__(SE_NT) small_exp_kernel(const SmallExpParams P) {
     extern __shared__ double sm[];
     __shared__ double sc[SE_MAXM];   // balancing scale factors
@@ -372,6 +529,15 @@ __global__ void __launch_bounds__(SE_NT) small_exp_kernel(const SmallExpParams P
     }
     const double t = P.tvec ? P.tvec[prob] : P.t;
     const double *H = P.Hd + (long long)prob * P.H_stride;
+    if (P.lanczos && !P.force_pade) {  // symmetric tridiagonal: Chebyshev on one warp (uniform per CTA)
+        __shared__ int s_done;
+        if (tid < 32) {
+            const bool ok = se_lanczos_cheb(n, H, P.ldh, t, yout, P.ldy);
+            if (tid == 0) s_done = ok ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_done) return;
+    }
     const int nn = n * n;
     for (int idx = tid; idx < nn; idx += SE_NT) {
         const int i = idx % n, j = idx / n;

@@ -290,8 +290,10 @@ int b200k_last_kernel(b200k_handle_t h, int *which);
                                whose working set exceeds the L2), 0 never, 1 always */
 #define B200K_FLAG_NO_XL 4  /* 1: never use the short-window (Lanczos / IOP) instance of the TMA-ring kernel that keeps
                                the current basis vector in shared memory and reduces with packet all-reduces */
-#define B200K_FLAG_NO_MV 5 /* batched Lanczos and the lock-step multi-vector kernel (four problems per team): 2 = use it
-                              whenever possible; 0 (default) / 1 = per-problem teams.  Opt-in: parity-tested, not yet faster */
+#define B200K_FLAG_NO_MV 5 /* batched Lanczos and the lock-step multi-vector kernel (several problems per team): 1 = never,
+                              2 = whenever possible, 0 (default) = when the cost model says it is faster */
+#define B200K_FLAG_SYM_PADE 6 /* 1: the device-side small exponential of a symmetric tridiagonal (Lanczos) H uses the
+                                 Pade path instead of the one-warp Chebyshev evaluation of exp(tT) e1 (A/B, tests) */
 int b200k_set_flag(b200k_handle_t h, int flag, int value);
 
 #ifdef __cplusplus

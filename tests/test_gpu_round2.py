@@ -213,3 +213,44 @@ def test_reorthogonalisation_on_ill_conditioned_krylov_sequences(gpu, oracle):
     Az = clustered.astype(np.complex128) + 1e-3j * sp.diags(rng.standard_normal(n))
     bz = rng.standard_normal(n) + 1j * rng.standard_normal(n)
     assert relerr(gpu.expv(0.01, Az, bz, m=30), oracle.expv(0.01, Az, bz, m=30)) < RTOL
+
+
+# ---- device small exponential of a Lanczos (symmetric tridiagonal) H: one-warp Chebyshev vs the eigen branch ---------
+def test_device_lanczos_small_exp_chebyshev_matches_eigen_branch(gpu, oracle):
+    """The fused one-shot expv evaluates exp(tT) e1 on the device with a Chebyshev expansion on a Sturm-tightened
+    spectral interval (csrc/smallexp_kernel.cuh) where the reference calls eigen!(SymTridiagonal)
+    (src/krylov_phiv.jl:225-229).  Same function of the same matrix: compare with the oracle's eigen branch over
+    many scales of t * ||T|| (Taylor regime z < 1/2, Chebyshev regime, Pade fallback z > 150), both signs of t,
+    tiny dimensions, and with the Pade path forced."""
+    rng = np.random.default_rng(17)
+    eng = gpu.get_engine()
+    worst = 0.0
+    for trial in range(40):
+        n = int(rng.integers(40, 400))
+        m = int(rng.choice([1, 2, 3, 10, 30, 48]))
+        Q = rng.standard_normal((n, n))
+        S = (Q + Q.T) * 10 ** rng.uniform(-3, 1.2)
+        if trial % 3 == 0:
+            S = S - np.abs(np.linalg.eigvalsh(S)).max() * np.eye(n)  # negative definite, like a Laplacian
+        b = rng.standard_normal(n)
+        t = float(rng.choice([1.0, 0.05, -0.3, 2.5]))
+        wo = oracle.expv(t, S, b, m=m, ishermitian_=True)
+        w = gpu.expv(t, S, b, m=m, ishermitian=True)
+        e = relerr(w, wo)
+        worst = max(worst, e)
+        assert e < RTOL, (trial, n, m, t, e)
+        eng.set_flag("sym_pade", 1)
+        try:
+            assert relerr(gpu.expv(t, S, b, m=m, ishermitian=True), wo) < RTOL
+        finally:
+            eng.set_flag("sym_pade", 0)
+    # the C2-like case and a batch with mixed times
+    L = laplacian2d(120, 90)
+    b = rng.standard_normal(L.shape[0])
+    for t in (1.0, 10.0, 40.0, -0.2):  # t = 40: z = 160 > 150 -> Pade fallback
+        assert relerr(gpu.expv(t, L, b, m=30), oracle.expv(t, L, b, m=30)) < RTOL, t
+    B = rng.standard_normal((L.shape[0], 5))
+    ts = np.array([0.01, 1.0, 7.0, 30.0, 50.0])
+    W = gpu.expv_batched(ts, L, B, m=30)
+    for i in range(5):
+        assert relerr(W[:, i], oracle.expv(ts[i], L, B[:, i], m=30)) < RTOL, i
