@@ -430,24 +430,108 @@ def arnoldi(A, b, *, m=None, ishermitian=None, **kw):
 # expv / phiv (src/krylov_phiv.jl)
 # ------------------------------------------------------------------------------------------
 class ExpvCache:
-    """ExpvCache{T}(maxiter) -- src/krylov_phiv.jl:45-77.  The reference preallocates the m x m working copy of H and
-    the exponential! workspaces here; the engine keeps the equivalent scratch in the handle (grown lazily, never on
-    the steady-state path), so this mirror only carries the size and exists so that callers written against the
-    reference (``expv!(w, t, Ks; cache = ExpvCache{T}(m))``) run unchanged -- including the error for a wrong type."""
+    """ExpvCache{T}(maxiter) -- src/krylov_phiv.jl:45-77.  Same state and growth rules as the reference: a flat ``mem``
+    of maxiter^2 elements that ``get_cache(m)`` views as the m x m working copy of H (``resize`` doubles it on demand,
+    :69-77), ``expcol`` for the first column of the reduced exponential, and the size-keyed store of exponential!
+    workspaces (``expcache``: at most 64 entries, oldest evicted first, :447-470) -- here an entry records that the
+    library's own workspace for that size is warm (the Pade scratch itself lives in the handle).  ``expv_`` runs the
+    small dense phase IN this memory when a cache is passed."""
 
-    def __init__(self, maxiter: int):
-        self.maxiter = int(maxiter)
+    def __init__(self, maxiter: int, dtype=np.float64):
+        self.dtype = np.dtype(dtype)
+        self.mem = np.empty(int(maxiter) ** 2, dtype=self.dtype)
+        self.expcol = np.empty(int(maxiter), dtype=self.dtype)
+        self.expcache = []  # [(n, workspace token)]
+
+    @property
+    def maxiter(self):
+        return int(math.isqrt(self.mem.size))
 
     def resize(self, maxiter: int):
-        self.maxiter = int(maxiter)
+        """Base.resize!(C::ExpvCache, maxiter) -- krylov_phiv.jl:69-73 (note the factor 2)."""
+        self.mem = np.empty(int(maxiter) ** 2 * 2, dtype=self.dtype)
+        if self.expcol.size < maxiter:
+            self.expcol = np.empty(int(maxiter), dtype=self.dtype)
         return self
+
+    def get_cache(self, m: int):
+        """get_cache(C, m) -- krylov_phiv.jl:74-77: the m x m (column-major) view, grown on demand."""
+        if m * m > self.mem.size:
+            self.resize(m)
+        return self.mem[: m * m].reshape((m, m), order="F")
+
+    def get_expcache(self, n: int):
+        """get_expcache!(C, A, ExpMethodHigham2005Base()) -- krylov_phiv.jl:447-470: FIFO store bounded at 64 sizes."""
+        for nc, work in self.expcache:
+            if nc == n:
+                return work
+        if len(self.expcache) >= 64:
+            self.expcache.pop(0)
+        work = {"n": n, "uses": 0}
+        self.expcache.append((n, work))
+        return work
 
 
 class PhivCache:
-    """PhivCache(w, maxiter, p) -- src/krylov_phiv.jl:404-428 (see ExpvCache: a size-carrying mirror)."""
+    """PhivCache(w, maxiter, p) -- src/krylov_phiv.jl:404-428, 471-504: one flat buffer of
+    maxiter + maxiter^2 + (maxiter + p)^2 + maxiter (p + 1) elements that ``get_caches(m, p)`` splits into
+    (e, Hcopy, C1, C2) and doubles on demand; ``coeffs`` and ``ts1`` scratch of phiv_timestep!.  ``phiv_`` evaluates
+    phiv_dense! in this memory when a cache is passed."""
 
     def __init__(self, w, maxiter: int, p: int):
-        self.maxiter, self.p = int(maxiter), int(p)
+        dt = np.complex128 if (_is_complex_value(w) if w is not None else False) else np.float64
+        self.dtype = np.dtype(dt)
+        maxiter, p = int(maxiter), int(p)
+        self.mem = np.empty(self._numelems(maxiter, p), dtype=self.dtype)
+        self.expcache = []
+        self.coeffs = np.ones(max(p, 1), dtype=self.dtype)
+        self.ts1 = np.empty(1)
+        self.useview = not (torch is not None and isinstance(w, torch.Tensor) and w.is_cuda)  # krylov_phiv.jl:420
+
+    @staticmethod
+    def _numelems(m, p):
+        return m + m * m + (m + p) ** 2 + m * (p + 1)
+
+    def resize(self, maxiter: int, p: int):
+        self.mem = np.empty(self._numelems(int(maxiter), int(p)) * 2, dtype=self.dtype)
+        return self
+
+    def get_caches(self, m: int, p: int):
+        """get_caches(C, m, p) -- krylov_phiv.jl:479-504."""
+        if self._numelems(m, p) > self.mem.size:
+            self.resize(m, p)
+        e = self.mem[:m]
+        off = m
+        Hcopy = self.mem[off: off + m * m].reshape((m, m), order="F")
+        off += m * m
+        C1 = self.mem[off: off + (m + p) ** 2].reshape((m + p, m + p), order="F")
+        off += (m + p) ** 2
+        C2 = self.mem[off: off + m * (p + 1)].reshape((m, p + 1), order="F")
+        return e, Hcopy, C1, C2
+
+    get_expcache = ExpvCache.get_expcache
+
+
+def _expv_with_cache(w, t, Ks, cache):
+    """expv!(w, t, Ks; cache) for a real subspace and real t with the small dense phase in the cache's memory
+    (krylov_phiv.jl:214-244): Hcopy = get_cache(cache, m) <- H[1:m, 1:m]; expcol <- exp(t Hcopy) e1; w = beta V expcol."""
+    eng = Ks.engine
+    m = Ks.m
+    if Ks.beta == 0.0:
+        w.zero_()
+        return w
+    Hcopy = cache.get_cache(m)
+    Hcopy[:, :] = Ks.H[:m, :m]
+    cache.get_expcache(m)["uses"] += 1
+    if cache.expcol.size < m:
+        cache.expcol = np.empty(m, dtype=cache.dtype)
+    y = cache.expcol[:m]
+    _lib.check(eng.lib.b200k_expv_small(m, Hcopy.ctypes.data_as(_lib.c_double_p), m, float(t),
+                                        y.ctypes.data_as(_lib.c_double_p), None))
+    eng.bind_stream()
+    eng.check(eng.lib.b200k_project(eng.handle, C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.nrows, m, Ks.beta,
+                                    y.ctypes.data_as(_lib.c_double_p), m, 1, C.c_void_p(w.data_ptr()), Ks.nrows))
+    return w
 
 
 def expv_(w, t, Ks: KrylovSubspace, *, cache=None):
@@ -493,6 +577,8 @@ def expv_(w, t, Ks: KrylovSubspace, *, cache=None):
         return w
     if w.dtype != torch.float64:
         raise ArgumentError("expv! needs a Float64 (or ComplexF64) output vector")
+    if cache is not None and cache.dtype == np.float64:
+        return _expv_with_cache(w, t, Ks, cache)
     eng.bind_stream()
     st = eng.lib.b200k_expv_ks(eng.handle, float(t), C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.nrows,
                                Ks.H.ctypes.data_as(_lib.c_double_p), Ks.H.shape[0], Ks.m, Ks.beta,
@@ -592,6 +678,8 @@ def phiv_(w, t, Ks: KrylovSubspace, k, *, cache=None, correct=False, errest=Fals
         return _phiv_z(w, t, Ks, k, correct=correct, errest=errest)
     if w.dtype != torch.float64 or not w.is_cuda or w.stride(1) != 1:
         raise ArgumentError("phiv! on a real Krylov subspace needs a float64 CUDA output of shape (k+1, nrows)")
+    if cache is not None and cache.dtype == np.float64 and Ks.beta != 0.0:
+        return _phiv_with_cache(w, t, Ks, k, cache, correct, errest)
     err = C.c_double()
     eng.bind_stream()
     st = eng.lib.b200k_phiv_ks(eng.handle, float(t), C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.nrows,
@@ -599,6 +687,31 @@ def phiv_(w, t, Ks: KrylovSubspace, k, *, cache=None, correct=False, errest=Fals
                                1 if correct else 0, C.c_void_p(w.data_ptr()), w.stride(0), C.byref(err))
     eng.check(st)
     return (w, err.value) if errest else w
+
+
+def _phiv_with_cache(w, t, Ks, k, cache, correct, errest):
+    """_phiv! with the small dense phase in the PhivCache's memory (krylov_phiv.jl:632-652): (e, Hcopy, C1, C2) =
+    get_caches(cache, m, k); Hcopy <- t H[1:m, :]; C2 <- phiv_dense!(Hcopy, e, k); w = beta V C2 (+ correction)."""
+    eng = Ks.engine
+    m = Ks.m
+    e, Hcopy, C1, C2 = cache.get_caches(m, k)
+    Hcopy[:, :] = float(t) * Ks.H[:m, :m]
+    e[:] = 0.0
+    e[0] = 1.0
+    cache.get_expcache(m + k)["uses"] += 1
+    _lib.check(eng.lib.b200k_phiv_dense(m, Hcopy.ctypes.data_as(_lib.c_double_p), m, e.ctypes.data_as(_lib.c_double_p),
+                                        int(k), C2.ctypes.data_as(_lib.c_double_p), m))
+    hlast = float(Ks.H[m, m - 1])  # H[end, end] of the (m+1) x m view
+    err = abs(Ks.beta * hlast * float(t) * C2[m - 1, k])
+    mm = m + 1 if correct else m
+    Y = np.zeros((mm, k + 1), order="F")
+    Y[:m, :] = C2
+    if correct:  # w[:, i] += beta h t C2[end, i+1] v_{m+1}: one more basis column with that coefficient / beta
+        Y[m, :k] = hlast * float(t) * C2[m - 1, 1:]
+    eng.bind_stream()
+    eng.check(eng.lib.b200k_project(eng.handle, C.c_void_p(Ks.Vt.data_ptr()), Ks.ldv, Ks.nrows, mm, Ks.beta,
+                                    Y.ctypes.data_as(_lib.c_double_p), mm, k + 1, C.c_void_p(w.data_ptr()), w.stride(0)))
+    return (w, err) if errest else w
 
 
 def _phiv_z(w, t, Ks, k, *, correct, errest):

@@ -138,8 +138,23 @@ def test_error_mapping(eu):
 def test_cache_mirrors_and_their_error(eu):
     """expv!/phiv! reject a cache of the wrong type with ArgumentError (src/krylov_phiv.jl:221, 630); the check comes
     before anything touches the device."""
-    assert eu.ExpvCache(30).resize(40).maxiter == 40
-    assert eu.PhivCache(None, 30, 4).p == 4
+    # ExpvCache: maxiter^2 elements, get_cache views m x m, resize! doubles (src/krylov_phiv.jl:45-77)
+    c = eu.ExpvCache(30)
+    assert c.mem.size == 900 and c.expcol.size == 30 and c.maxiter == 30
+    v = c.get_cache(20)
+    assert v.shape == (20, 20) and v.flags.f_contiguous and np.shares_memory(v, c.mem)
+    assert c.get_cache(40).shape == (40, 40) and c.mem.size == 40 * 40 * 2 and c.expcol.size == 40  # grown on demand
+    for n in range(70):  # size-keyed exponential! workspaces: FIFO store bounded at 64 (krylov_phiv.jl:447-470)
+        c.get_expcache(n)
+    assert len(c.expcache) == 64 and c.expcache[0][0] == 6 and c.get_expcache(69) is c.expcache[-1][1]
+    # PhivCache: m + m^2 + (m+p)^2 + m(p+1) elements split by get_caches (krylov_phiv.jl:404-428, 479-504)
+    pc = eu.PhivCache(None, 30, 4)
+    assert pc.mem.size == 30 + 900 + 34 * 34 + 30 * 5 and pc.coeffs.size == 4 and pc.useview
+    e, Hc, C1, C2 = pc.get_caches(10, 3)
+    assert e.shape == (10,) and Hc.shape == (10, 10) and C1.shape == (13, 13) and C2.shape == (10, 4)
+    assert all(np.shares_memory(x, pc.mem) for x in (e, Hc, C1, C2))
+    pc.get_caches(50, 4)
+    assert pc.mem.size == 2 * (50 + 2500 + 54 * 54 + 50 * 5)
     with pytest.raises(eu.ArgumentError):
         eu.expv_(None, 1.0, None, cache=eu.PhivCache(None, 30, 4))
     with pytest.raises(eu.ArgumentError):

@@ -254,3 +254,33 @@ def test_device_lanczos_small_exp_chebyshev_matches_eigen_branch(gpu, oracle):
     W = gpu.expv_batched(ts, L, B, m=30)
     for i in range(5):
         assert relerr(W[:, i], oracle.expv(ts[i], L, B[:, i], m=30)) < RTOL, i
+
+
+def test_expv_phiv_with_reference_style_caches(gpu, oracle):
+    """expv!(w, t, Ks; cache = ExpvCache{T}(m)) / phiv!(w, t, Ks, k; cache = PhivCache(w, m, k)): the small dense phase
+    runs in the caller's cache memory (src/krylov_phiv.jl:214-244, 632-652), caches grow on demand and are reusable
+    across subspace sizes; results equal the cache-less calls and the oracle."""
+    import torch
+    rng = np.random.default_rng(23)
+    A, L = convdiff2d(40, 30), laplacian2d(40, 30)
+    b = rng.standard_normal(1200)
+    ec = gpu.ExpvCache(5)           # deliberately too small: grows like the reference's
+    pc = gpu.PhivCache(None, 5, 2)
+    for op, herm, m in ((A, False, 20), (L, True, 25), (A, False, 8)):
+        Ks = gpu.arnoldi(op, b, m=m, ishermitian=herm)
+        Ko = oracle.arnoldi(op, b, m=m, ishermitian_=herm)
+        w0 = torch.empty(1200, dtype=torch.float64, device="cuda")
+        w1 = torch.empty(1200, dtype=torch.float64, device="cuda")
+        gpu.expv_(w0, 0.7, Ks)
+        gpu.expv_(w1, 0.7, Ks, cache=ec)
+        assert relerr(w1.cpu().numpy(), w0.cpu().numpy()) < 1e-13
+        assert relerr(w1.cpu().numpy(), oracle.expv_ks(0.7, Ko)) < RTOL
+        for correct in (False, True):
+            W0 = torch.empty((4, 1200), dtype=torch.float64, device="cuda")
+            W1 = torch.empty((4, 1200), dtype=torch.float64, device="cuda")
+            _, e0 = gpu.phiv_(W0, 0.7, Ks, 3, correct=correct, errest=True)
+            _, e1 = gpu.phiv_(W1, 0.7, Ks, 3, cache=pc, correct=correct, errest=True)
+            assert relerr(W1.cpu().numpy(), W0.cpu().numpy()) < 1e-13 and abs(e0 - e1) <= 1e-12 * abs(e0)
+            Wo, eo = oracle.phiv_ks(0.7, Ko, 3, correct=correct, errest=True)
+            assert relerr(W1.t().cpu().numpy(), Wo) < RTOL and abs(e1 - eo) <= 1e-8 * abs(eo)
+    assert ec.mem.size >= 25 * 25 and len(ec.expcache) == 3 and len(pc.expcache) == 3
