@@ -104,6 +104,8 @@ PROTOTYPES = {
     "b200k_op_csr_create_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200k_op_dense_create_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                                C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "b200k_exponential_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64]),
     "b200k_exponential": (C.c_int, [C.c_int, c_double_p, C.c_int]),
     "b200k_expv_small": (C.c_int, [C.c_int, c_double_p, C.c_int, C.c_double, c_double_p, c_int_p]),

@@ -167,6 +167,7 @@ struct b200k_operator {
     long long n = 0, nnz = 0;
     DevBuf rowptr, colind, val;  // owned, 0-based, padded
     const double *Ad = nullptr;  // dense: alias (device input) or owned copy
+    long long ncols = 0;         // dense row block of a row-sharded operator: global dimension (0: square)
     DevBuf Aown;
     long long lda = 0;
     int max_row_nnz = 0;
@@ -328,6 +329,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
         P.op_kind = OP_DENSE;
         P.Ad = op->Ad;
         P.lda = op->lda;
+        P.ncols = (int)(op->ncols ? op->ncols : n);
     }
     P.p = c.p;
     P.Bm = c.B;
@@ -477,7 +479,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
                                           const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                           CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                           CUtensorMapFloatOOBfill);
-            const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)n};
+            const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)(op->ncols ? op->ncols : n)};
             const cuuint64_t gstr[1] = {(cuuint64_t)op->lda * 8};
             const cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)cpt};
             const cuuint32_t estr[2] = {1, 1};
@@ -837,8 +839,8 @@ int arnoldi_core(b200k_context *h, b200k_operator *op, const double *b, const b2
     if (p > 0) make_btail(p, o->t, o->mu, btail);
     c.btail_host = btail;
     c.g = single_geom(h, n);
-    if (op->comm && c.g.C != h->max_ctas)
-        return fail(h, B200K_EUNSUPPORTED, "row-sharded operators need at least 16 rows per CTA on every rank");
+    if (op->comm && c.g.C < 2 * LLQ)  // (the owner CTAs of the packet all-reduce; every GPU may use its own team size)
+        return fail(h, B200K_EUNSUPPORTED, "row-sharded operators need at least 128 rows on every rank");
     int st = launch_krylov(h, c);
     if (st) return st;
     st = fetch_krylov(h, 1, m);
@@ -1356,6 +1358,7 @@ int b200k_op_info(b200k_op_t op, int64_t *n, int64_t *nnz, int *kind, int *is_he
 
 int b200k_op_apply(b200k_handle_t h, b200k_op_t op, const double *x, double *y) {
     if (!h || !op || !x || !y) return B200K_EARG;
+    if (op->comm) return fail(h, B200K_EUNSUPPORTED, "mul! on a row-sharded operator (the halo exchange lives in the Krylov kernel)");
     if (op->kind == 0) {
         const int blocks = (int)std::min<long long>((op->n + 7) / 8, (long long)h->sm_count * 16);
         csr_apply_kernel<<<blocks, 256, 0, h->stream>>>((int)op->n, op->rowptr.as<int>(), op->colind.as<int>(),
@@ -1427,8 +1430,8 @@ int b200k_expv(b200k_handle_t h, b200k_op_t op, double t, const double *b, const
         c.ldb = 0;
         c.btail_host = nullptr;
         c.g = single_geom(h, op->n);
-        if (op->comm && c.g.C != h->max_ctas)
-            return fail(h, B200K_EUNSUPPORTED, "row-sharded operators need at least 16 rows per CTA on every rank");
+        if (op->comm && c.g.C < 2 * LLQ)
+            return fail(h, B200K_EUNSUPPORTED, "row-sharded operators need at least 128 rows on every rank");
         st = launch_krylov(h, c);
         if (st) return st;
         st = launch_smallexp_project(h, 1, o.m, c.lanczos, &t, h->V.as<double>(), ldv, 0, op->n, w, op->n, 0);
@@ -2670,6 +2673,94 @@ int b200k_op_csr_create_sharded(b200k_handle_t h, b200k_comm_t cm, int64_t nloc,
         *out = nullptr;
         return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
     }
+    return B200K_OK;
+}
+
+// A row block of a DENSE operator (C3 beyond one GPU).  Every rank needs the whole of x each step: its
+// gather buffer holds the nloc own entries first, then all other rows in ascending global order ("halo" = n - nloc),
+// so the block's COLUMNS are permuted into that order while it is copied into library storage, and every own row is
+// pushed to every peer (send list built here from the row partition).  The persistent kernel is unchanged: the dense
+// mat-vec streams an nloc x n block instead of n x n and the halo push / all-reduces are those of the sparse case.
+int b200k_op_dense_create_sharded(b200k_handle_t h, b200k_comm_t cm, int64_t n_global, const int64_t *row_starts,
+                                  const double *A_block, int64_t lda, int location, int is_hermitian, b200k_op_t *out) {
+    if (!h || !cm || !out || !row_starts || !A_block) return B200K_EARG;
+    *out = nullptr;
+    const int R = cm->nranks, me = cm->rank;
+    if (row_starts[0] != 0 || row_starts[R] != n_global) return fail(h, B200K_EARG, "row_starts must run from 0 to n");
+    for (int r = 0; r < R; ++r)
+        if (row_starts[r + 1] <= row_starts[r]) return fail(h, B200K_EARG, "row_starts must be increasing");
+    const int64_t row0 = row_starts[me], nloc = row_starts[me + 1] - row0;
+    if (nloc % 2 != 0 || row0 % 2 != 0) return fail(h, B200K_EUNSUPPORTED, "row-sharded blocks need even row counts");
+    if (lda < nloc) return fail(h, B200K_EARG, "lda < number of local rows");
+    if (n_global > 2000000000LL) return fail(h, B200K_EUNSUPPORTED, "n too large");
+    if (n_global + MAXP > cm->xlen) return fail(h, B200K_EDIM, "communicator gather buffer (xlen) too small: need n + 16");
+    CK(h, cudaSetDevice(h->device));
+    b200k_operator *op = new b200k_operator();
+    op->ctx = h;
+    op->device = h->device;
+    op->kind = 1;
+    op->n = nloc;
+    op->ncols = n_global;
+    op->nnz = nloc * n_global;
+    op->comm = cm;
+    op->nhalo = n_global - nloc;
+    op->is_herm = is_hermitian ? 1 : 0;
+    const long long ld = round_up(nloc, 2);
+    cudaError_t e = op->Aown.ensure((size_t)ld * n_global * 8);
+    if (e != cudaSuccess) {
+        delete op;
+        return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+    }
+    const cudaMemcpyKind kind = location == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    double *dst = op->Aown.as<double>();
+    // own columns -> [0, nloc); columns left of the block -> [nloc, nloc + row0); columns right of it -> the rest
+    struct Piece { int64_t src_col, dst_col, ncol; } pieces[3] = {
+        {row0, 0, nloc}, {0, nloc, row0}, {row0 + nloc, nloc + row0, n_global - row0 - nloc}};
+    for (const Piece &pc : pieces) {
+        if (pc.ncol <= 0) continue;
+        e = cudaMemcpy2DAsync(dst + (size_t)pc.dst_col * ld, (size_t)ld * 8, A_block + (size_t)pc.src_col * lda,
+                              (size_t)lda * 8, (size_t)nloc * 8, (size_t)pc.ncol, kind, h->stream);
+        if (e != cudaSuccess) break;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+        delete op;
+        return fail(h, B200K_ECUDA, cudaGetErrorString(e));
+    }
+    op->Ad = dst;
+    op->lda = ld;
+    // opnorm(A, Inf) of the block (the caller combines the ranks with a max if it needs the global value)
+    op->opnorm_inf = 0.0;
+    // send list: own row i goes to every peer q at the position of global row row0 + i in q's gather buffer
+    const int64_t nsend = nloc * (R - 1);
+    std::vector<int> srow((size_t)nsend), speer((size_t)nsend), spos((size_t)nsend);
+    size_t k = 0;
+    for (int64_t i = 0; i < nloc; ++i) {
+        const int64_t g = row0 + i;
+        for (int q = 0; q < R; ++q) {
+            if (q == me) continue;
+            const int64_t q0 = row_starts[q], qn = row_starts[q + 1] - q0;
+            srow[k] = (int)i;
+            speer[k] = q;
+            spos[k] = (int)(g < q0 ? qn + g : g);  // (g >= q0 + qn: qn + (g - qn) = g)
+            ++k;
+        }
+    }
+    op->send_row_host = srow;
+    const size_t bytes = (size_t)std::max<int64_t>(nsend, 1) * 4;
+    e = op->send_row.ensure(bytes);
+    if (e == cudaSuccess) e = op->send_peer.ensure(bytes);
+    if (e == cudaSuccess) e = op->send_pos.ensure(bytes);
+    if (e == cudaSuccess && nsend > 0) {
+        cudaMemcpy(op->send_row.p, srow.data(), (size_t)nsend * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(op->send_peer.p, speer.data(), (size_t)nsend * 4, cudaMemcpyHostToDevice);
+        e = cudaMemcpy(op->send_pos.p, spos.data(), (size_t)nsend * 4, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        b200k_op_destroy(op);
+        return fail(h, B200K_ENOMEM, cudaGetErrorString(e));
+    }
+    *out = op;
     return B200K_OK;
 }
 

@@ -52,6 +52,7 @@ struct KrylovParams {
     int ch_rows;  // rows per TMA chunk (CSR stream)
     const double *Ad;
     long long lda;
+    int ncols;  // dense: number of columns (= n, or the GLOBAL dimension for a row block of a row-sharded dense operator)
     // augmentation (kiops)
     int p;
     const double *Bm;

@@ -285,7 +285,7 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
             // tensor-map boxes (rows past n are zero-filled by the TMA unit and still count as bytes)
             const int nrb = P.slice / P.dense_box_rows;
             const uint32_t tbytes = (uint32_t)P.slice * (uint32_t)P.dense_cpt * 8u;
-            for (int c0 = 0; c0 < P.n; c0 += P.dense_cpt) {
+            for (int c0 = 0; c0 < P.ncols; c0 += P.dense_cpt) {
                 if (!prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
                 if (lane == 0) {
                     mbar_arrive_expect_tx(&S->full[rg.slot], tbytes);
@@ -709,8 +709,8 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
             // operator tiles arrive through the TMA ring: [dense_cpt columns][nrows] per slot
             double a0 = 0.0, a1 = 0.0;
             if (G.nrows > 0) {
-                for (int c0 = 0; c0 < n; c0 += P.dense_cpt) {
-                    const int nc = min(P.dense_cpt, n - c0);
+                for (int c0 = 0; c0 < P.ncols; c0 += P.dense_cpt) {
+                    const int nc = min(P.dense_cpt, P.ncols - c0);
                     cx.wait_full();
                     if (ul < units) {
                         // smem tile: [row box][column][box rows]; this thread's row pair sits in box rb
@@ -757,7 +757,7 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
                 if (valid) {
                     const double *ap = P.Ad + G.r0 + 2LL * u;
 #pragma unroll 8
-                    for (int c = g; c < n; c += Gc) {
+                    for (int c = g; c < P.ncols; c += Gc) {
                         const double xc = xsrc[c];
                         const double2 a2 = ld_ro2(ap + (long long)c * P.lda);
                         a0 = fma(a2.x, xc, a0);
@@ -817,10 +817,9 @@ __device__ bool dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
                 const int idx = tid + q * NTC;
                 wr[q] = idx < pairs ? ws2[pbase + idx] : make_double2(0.0, 0.0);
             }
-            if (sq_here) {
+            // (unconditional: a loop-invariant branch here makes the compiler duplicate the unrolled tile loop)
 #pragma unroll
-                for (int q = 0; q < PPT; ++q) sq = fma(wr[q].x, wr[q].x, fma(wr[q].y, wr[q].y, sq));
-            }
+            for (int q = 0; q < PPT; ++q) sq = fma(wr[q].x, wr[q].x, fma(wr[q].y, wr[q].y, sq));
 #pragma unroll
             for (int u = 0; u < CB; ++u) {
                 if (u < nb) {
@@ -1036,6 +1035,46 @@ __device__ __noinline__ double reorth_update_c(const KrylovParams &P, SmemTma *S
     return nrm;
 }
 
+// The whole second pass: inner products, reduction, H += h2, update, norm reduction (result in S->bc[0]).  Passes two
+// team reductions: the caller advances its barrier target by 2 C and its sequence number by 2 afterwards.
+__device__ __noinline__ void reorth_step_c(const KrylovParams &P, SmemTma *S, double *ws, int r0, int nrows, int team,
+                                           int rank, int C, unsigned *bar, unsigned target, unsigned seq, const double *V,
+                                           int lo, int hi, long long part, long long partn, double *xout, long long xoff,
+                                           double *Hcol, bool aug) {
+    Cons cx;
+    cx.S = S;
+    cx.ws = ws;
+    cx.xin = nullptr;
+    cx.ws_a = cx.xin_a = 0;
+    cx.team = team;
+    cx.tid = threadIdx.x;
+    cx.lane = threadIdx.x & 31;
+    cx.warp = threadIdx.x >> 5;
+    cx.seq = seq;
+    Team tm;
+    tm.bar = bar;
+    tm.target = target;
+    tm.seq = seq;
+    tm.C = C;
+    tm.rank = rank;
+    TmaGeom G;
+    G.r0 = r0;
+    G.nrows = nrows;
+    G.nch = G.ntk = G.TR = 0;
+    const int nc = hi - lo + 1;
+    const bool sharded = P.nranks > 1;
+    double *h2 = &S->llv[0][0];  // (packet scratch of the XL instance: unused by this instance)
+    consumer_sync();
+    reorth_dots_c(P, S, ws, r0, nrows, rank, V, lo, hi, part, aug);
+    team_reduce_c(P, cx, tm, P.peer_part[P.myrank] + part, nc, h2, false);
+    if (rank == 0)
+        for (int ci = cx.tid; ci < nc; ci += NTC) Hcol[ci] = S->hs[ci] + h2[ci];
+    const double nrm2 = reorth_update_c(P, S, ws, r0, nrows, rank, V, lo, hi, h2, xout, aug);
+    block_sum_to_c(P, cx, nrm2, partn + rank);
+    push_halo(P, cx, G, tm, xoff);
+    team_reduce_c(P, cx, tm, P.peer_partn[P.myrank] + partn, 1, S->bc, sharded);
+}
+
 // One problem on the consumer side.  Mirrors krylov_body<2> of krylov_kernel.cuh.
 template <int OPK, bool AUG>
 __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom &G, Team &tm, int prob, int nlocal,
@@ -1148,7 +1187,11 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
         const int hi = jc;
         // Arnoldi / IOP: ||w_before||^2 travels with the inner products as quantity nc (re-orthogonalisation test)
+#ifdef B200K_NO_DGKS  // A/B builds only
+        const bool dgks = false;
+#else
         const bool dgks = !P.lanczos;
+#endif
         const int nc = hi - lo + 1;
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
         if (!dots_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, hi, part, dgks))
@@ -1170,17 +1213,13 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
 
         if (dgks && S->bc[0] < REORTH_ETA2 * S->hs[nc]) {
             // second classical Gram-Schmidt pass (every CTA of every rank takes the same decision: the reduced values
-            // are bitwise identical everywhere).  NaN never triggers it.
-            double *h2 = &S->llv[0][0];  // (packet scratch of the XL instance: unused here)
-            consumer_sync();
-            reorth_dots_c(P, S, cx.ws, G.r0, G.nrows, tm.rank, V, lo, hi, part, AUG);
-            team_reduce_c(P, cx, tm, lpart + part, nc, h2, false);
-            if (tm.rank == 0)
-                for (int ci = tid; ci < nc; ci += NTC) Hd[(long long)jc * ldh + lo + ci] = S->hs[ci] + h2[ci];
-            const double nrm2 = reorth_update_c(P, S, cx.ws, G.r0, G.nrows, tm.rank, V, lo, hi, h2, xout, AUG);
-            block_sum_to_c(P, cx, nrm2, partn + tm.rank);
-            push_halo(P, cx, G, tm, xoff);
-            team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, sharded);
+            // are bitwise identical everywhere; NaN never triggers it).  Out of line, two more team reductions.
+#ifndef B200K_DGKS_NOCALL  // A/B builds only
+            reorth_step_c(P, S, cx.ws, G.r0, G.nrows, cx.team, tm.rank, tm.C, tm.bar, tm.target, cx.seq, V, lo, hi, part,
+                          partn, xout, xoff, Hd + (long long)jc * ldh + lo, AUG);
+#endif
+            tm.target += 2u * (unsigned)tm.C;
+            cx.seq += 2u;
             ++nreorth;
         }
         const double beta = sqrt(S->bc[0]);

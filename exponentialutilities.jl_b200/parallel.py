@@ -128,6 +128,61 @@ class ShardedOperator:
             self.comm = None
 
 
+class ShardedDenseOperator:
+    """A dense operator whose rows are split across the ranks (BASELINE config 3 beyond one GPU).  ``A_block`` is this
+    rank's (nloc x n) row block (NumPy array or CUDA tensor, columns in global order); every rank passes the same
+    ``row_starts`` (length world + 1, even offsets, e.g. from ``row_partition``).  ``op`` is used like any operator
+    with this rank's row block of every vector; per Krylov step every rank pushes its block of the new vector to all
+    peers inside the persistent kernel (the all-gather of x) -- no collective call on the data path."""
+
+    def __init__(self, A_block, row_starts, *, ishermitian: bool, group=None, engine=None):
+        import torch
+        import torch.distributed as dist
+        from .api import Operator, get_engine
+
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        eng = engine or get_engine()
+        self.engine = eng
+        rs = np.ascontiguousarray(np.asarray(row_starts, dtype=np.int64))
+        n = int(rs[-1])
+        self.row0, self.nloc, self.n_global = int(rs[self.rank]), int(rs[self.rank + 1] - rs[self.rank]), n
+        lib = eng.lib
+        eng.bind_stream()
+        handle = (C.c_ubyte * 64)()
+        comm = C.c_void_p()
+        eng.check(lib.b200k_comm_create(eng.handle, self.rank, self.world, n + 32, handle, C.byref(comm)))
+        hs = [None] * self.world
+        dist.all_gather_object(hs, bytes(handle), group=group)
+        allh = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(hs))
+        eng.check(lib.b200k_comm_connect(comm, allh))
+        dist.barrier(group=group)
+        self.comm = comm
+        ptr = C.c_void_p()
+        if isinstance(A_block, torch.Tensor):
+            if A_block.shape != (self.nloc, n):
+                raise _lib.DimensionMismatch("A_block must be nloc x n")
+            At = A_block.to(device=eng.device, dtype=torch.float64).t().contiguous()  # row j = column j of the block
+            eng.check(lib.b200k_op_dense_create_sharded(eng.handle, comm, n, rs.ctypes.data, C.c_void_p(At.data_ptr()),
+                                                        self.nloc, 0, 1 if ishermitian else 0, C.byref(ptr)))
+            eng.synchronize()
+            del At
+        else:
+            Af = np.asfortranarray(np.asarray(A_block, dtype=np.float64))
+            if Af.shape != (self.nloc, n):
+                raise _lib.DimensionMismatch("A_block must be nloc x n")
+            eng.check(lib.b200k_op_dense_create_sharded(eng.handle, comm, n, rs.ctypes.data, Af.ctypes.data, self.nloc, 1,
+                                                        1 if ishermitian else 0, C.byref(ptr)))
+        self.op = Operator(eng, ptr, (comm,))
+
+    def close(self):
+        if self.comm:
+            self.op = None
+            self.engine.lib.b200k_comm_destroy(self.comm)
+            self.comm = None
+
+
 def kiops_sharded(tau_out, sop: ShardedOperator, u_local, **kw):
     """kiops on a row-sharded operator: u_local is this rank's row block of u (nloc x (p+1)); returns this rank's
     rows of w and the (replicated) stats."""

@@ -255,6 +255,15 @@ int b200k_op_csr_create_sharded(b200k_handle_t h, b200k_comm_t comm, int64_t nlo
                                 int location, int is_hermitian, int64_t nsend, const int32_t *send_row,
                                 const int32_t *send_peer, const int32_t *send_pos, b200k_op_t *op);
 
+/* This rank's row block of a DENSE operator (the dense analogue; BASELINE config 3 beyond one GPU, reference call site
+ * src/arnoldi.jl:185).  row_starts: HOST, nranks + 1 global row offsets (rank r owns rows [row_starts[r],
+ * row_starts[r+1]), all even); A_block: this rank's rows, (row_starts[rank+1] - row_starts[rank]) x n_global
+ * column-major with leading dimension lda, columns in GLOBAL order (the library copies it and permutes the columns
+ * into its gather order: own entries first).  The communicator's xlen must be >= n_global + 16.  Every step each rank
+ * pushes its block of the new vector to every peer (the "all-gather of x") inside the persistent kernel. */
+int b200k_op_dense_create_sharded(b200k_handle_t h, b200k_comm_t comm, int64_t n_global, const int64_t *row_starts,
+                                  const double *A_block, int64_t lda, int location, int is_hermitian, b200k_op_t *op);
+
 /* ---- small dense matrix functions (host, m <= ~130) ----------------------------------------- */
 /* exponential!(A, ExpMethodHigham2005Base()) in place (src/exp_baseexp.jl:112-161). */
 int b200k_exponential(int n, double *A, int lda);

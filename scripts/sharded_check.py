@@ -19,9 +19,12 @@ def log(*a):
 
 def gather_rows(x_local, ranges):
     """all ranks' row blocks -> full vector on every rank (test plumbing)"""
-    outs = [torch.empty(r[1], dtype=torch.float64, device="cuda") for r in ranges]
-    dist.all_gather(outs, x_local.contiguous())
-    return torch.cat(outs).cpu().numpy()
+    mx = max(r[1] for r in ranges)  # equal-size padded blocks (the last rank's block may be longer)
+    pad = torch.zeros(mx, dtype=torch.float64, device="cuda")
+    pad[: x_local.numel()] = x_local.reshape(-1)
+    outs = [torch.empty(mx, dtype=torch.float64, device="cuda") for _ in ranges]
+    dist.all_gather(outs, pad)
+    return torch.cat([o[: r[1]] for o, r in zip(outs, ranges)]).cpu().numpy()
 
 def make(A, herm):
     n = A.shape[0]
@@ -61,6 +64,40 @@ if "parity" in which:
                 print(f"[{name}] kiops herm={h} relerr {relerr(wf, wo[:, 0]):.3e} stats {st} vs {so}", flush=True)
         dist.barrier(); sop.close()
 
+if "dense" in which:
+    # dense operator, row blocks: x is all-gathered inside the kernel every step
+    from oracle import oracle as O
+    n = 2048
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((n, n)) / np.sqrt(n) * 4
+    Asym = (A + A.T) / 2
+    b = np.random.default_rng(3).standard_normal(n)
+    ranges = P.row_partition(n, world)
+    starts = [r[0] for r in ranges] + [n]
+    r0, nl = ranges[rank]
+    bl = torch.from_numpy(b[r0:r0 + nl]).cuda()
+    for name, M, herm in (("dense randn", A, False), ("dense symmetric", Asym, True)):
+        sop = P.ShardedDenseOperator(M[r0:r0 + nl], starts, ishermitian=herm)
+        for h in ([True, False] if herm else [False]):
+            w = eu.expv(1.0, sop.op, bl, m=30, ishermitian=h)
+            wf = gather_rows(w, ranges)
+            if rank == 0:
+                print(f"[{name} n={n}] expv herm={h} relerr {relerr(wf, O.expv(1.0, M, b, m=30, ishermitian_=h)):.3e} kernel {sop.engine.last_kernel()}", flush=True)
+        Ks = eu.KrylovSubspace(nl, 30, engine=sop.engine)
+        eu.arnoldi_(Ks, sop.op, bl, m=30, ishermitian=False)
+        Ko = O.arnoldi(M, b, m=30, ishermitian_=False)
+        Wl = eu.phiv(1.0, Ks, 4, correct=True)
+        Wf = np.stack([gather_rows(Wl[:, c].contiguous(), ranges) for c in range(5)], 1)
+        if rank == 0:
+            print(f"[{name}] H err {np.abs(Ks.getH() - Ko.getH()).max():.2e}  phiv relerr {relerr(Wf, O.phiv_ks(1.0, Ko, 4, correct=True)):.3e}", flush=True)
+        u = np.random.default_rng(4).standard_normal((n, 2))
+        wl, st = P.kiops_sharded(0.5, sop, torch.from_numpy(u[r0:r0 + nl]).cuda(), ishermitian=herm)
+        wf = gather_rows(torch.from_numpy(np.ascontiguousarray(wl[:, 0])).cuda(), ranges)
+        if rank == 0:
+            wo, so = O.kiops(0.5, M, u, ishermitian_=herm)
+            print(f"[{name}] kiops herm={herm} relerr {relerr(wf, wo[:, 0]):.3e} stats {st} vs {so}", flush=True)
+        dist.barrier(); sop.close()
+
 def timed(fn, reps, warm=3):
     for _ in range(warm): fn()
     dist.barrier(); torch.cuda.synchronize()
@@ -87,6 +124,39 @@ if "c2" in which:
         res[name] = {"ms_per_expv": ms, "expv_per_s": 1e3 / ms, "kernel_ms_rank0": float(np.mean(ks)),
                      "us_per_krylov_step": float(np.mean(ks)) * 1e3 / 30}
     log(json.dumps({"c2_row_sharded": res, "n_gpus": world}))
+    dist.barrier(); sop.close()
+
+if "c3" in which:
+    # BASELINE config 3 (phiv K = 4, dense n = 16384, m = 30) with the operator row-sharded over the ranks
+    n = 16384
+    ranges = P.row_partition(n, world)
+    starts = [r[0] for r in ranges] + [n]
+    r0, nl = ranges[rank]
+    g = torch.Generator(device="cuda").manual_seed(2)   # every rank generates the same matrix and keeps its rows
+    Afull = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g) / 128
+    bfull = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    sop = P.ShardedDenseOperator(Afull[r0:r0 + nl], starts, ishermitian=False)
+    bl = bfull[r0:r0 + nl].contiguous()
+    Ks = eu.KrylovSubspace(nl, 30, engine=sop.engine)
+    W = torch.empty((5, nl), dtype=torch.float64, device="cuda")
+    def f3():
+        eu.arnoldi_(Ks, sop.op, bl, m=30, ishermitian=False)
+        eu.phiv_(W, 1.0, Ks, 4)
+    ms = timed(f3, 5, 2)
+    sop.engine.set_timing(True); ks = []
+    for _ in range(3):
+        f3(); torch.cuda.synchronize(); ks.append(sop.engine.last_timing()["krylov_ms"])
+    sop.engine.set_timing(False)
+    res = {"ms_per_phiv": ms, "phiv_per_s": 1e3 / ms, "kernel_ms_rank0": float(np.mean(ks)), "kernel": sop.engine.last_kernel()}
+    if world <= 2:  # parity at full size against one GPU holding the whole matrix (rank 0 only has room for it at small world)
+        pass
+    wf = gather_rows(W[0].contiguous(), ranges)
+    if rank == 0:
+        op1 = eu.operator(Afull)
+        W1 = eu.phiv(1.0, op1, bfull, 4, m=30)
+        res["relerr_vs_one_gpu"] = relerr(wf, W1[:, 0].cpu().numpy())
+    log(json.dumps({"c3_dense_row_sharded": res, "n_gpus": world}))
+    del Afull
     dist.barrier(); sop.close()
 
 if "c4" in which:

@@ -229,16 +229,25 @@ def test_device_lanczos_small_exp_chebyshev_matches_eigen_branch(gpu, oracle):
         n = int(rng.integers(40, 400))
         m = int(rng.choice([1, 2, 3, 10, 30, 48]))
         Q = rng.standard_normal((n, n))
-        S = (Q + Q.T) * 10 ** rng.uniform(-3, 1.2)
-        if trial % 3 == 0:
-            S = S - np.abs(np.linalg.eigvalsh(S)).max() * np.eye(n)  # negative definite, like a Laplacian
-        b = rng.standard_normal(n)
+        S = Q + Q.T
         t = float(rng.choice([1.0, 0.05, -0.3, 2.5]))
+        # |t| * spectral radius: Taylor regime, Chebyshev regime, Pade fallback (the interval half-width z is about this)
+        target = float(rng.choice([1e-3, 0.3, 2.0, 10.0, 60.0, 140.0, 250.0]))
+        S *= target / (abs(t) * np.abs(np.linalg.eigvalsh(S)).max())
+        if trial % 3 == 0:
+            S = S - np.abs(np.linalg.eigvalsh(S)).max() * np.eye(n)  # negative semi-definite, like a Laplacian
+        if t < 0:
+            S = -S  # keep t * S bounded above (exp(t S) must not overflow in either implementation)
+        lam = np.linalg.eigvalsh(S)
+        shift = max(0.0, (t * lam).max() - 50.0)  # cap t * lambda_max at 50
+        S = S - (shift / t) * np.eye(n)
+        b = rng.standard_normal(n)
         wo = oracle.expv(t, S, b, m=m, ishermitian_=True)
+        assert np.isfinite(wo).all()
         w = gpu.expv(t, S, b, m=m, ishermitian=True)
         e = relerr(w, wo)
         worst = max(worst, e)
-        assert e < RTOL, (trial, n, m, t, e)
+        assert e < RTOL, (trial, n, m, t, target, e)
         eng.set_flag("sym_pade", 1)
         try:
             assert relerr(gpu.expv(t, S, b, m=m, ishermitian=True), wo) < RTOL
