@@ -368,6 +368,33 @@ def main():
     ms_total = timed(step_resident, args.steps, args.warmup)
     launches = nonlocal_l[1] - nonlocal_l[0]
     ms_e2e_total = timed(step_e2e, args.steps, args.warmup)
+
+    # e2e with two requests in flight: two handles on two streams, so the PCIe copies of one request overlap the
+    # kernels of the other (b200k_expv_host_async).  Every step still does its own H2D(b) and D2H(w).
+    eng2 = [eng, eu.Engine(local_rank)]
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    w_pins = [w_pin, torch.empty(n, dtype=torch.float64).pin_memory()]
+    b_pins = [b_pin, torch.from_numpy(b_host_np).pin_memory()]
+
+    def run_pipelined(steps):
+        for i in range(steps):
+            k = i & 1
+            with torch.cuda.stream(streams[k]):
+                if i >= 2:
+                    eng2[k].synchronize()  # the result of request i - 2 has landed: its buffers are free again
+                eu.expv_host_async(t_rank, op, b_pins[k], w_pins[k], m=M, ishermitian=herm, engine=eng2[k])
+        for k in (0, 1):
+            with torch.cuda.stream(streams[k]):
+                eng2[k].synchronize()
+
+    run_pipelined(max(args.warmup, 4))
+    barrier()
+    t0 = time.perf_counter()
+    run_pipelined(args.steps)
+    torch.cuda.synchronize()
+    ms_e2e_pipe_total = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
+    pipe_check = relerr(w_pins[1].numpy(), w_pins[0].numpy())  # both requests computed the same expv
     clocks = sampler.stop() if rank == 0 else None
 
     # kernel-only duration of the persistent Krylov kernel (events on the launching stream, in the library)
@@ -376,7 +403,8 @@ def main():
 
     ms_per_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
-    e2e_value = world * args.steps / (ms_e2e_total * 1e-3)
+    e2e_sync_value = world * args.steps / (ms_e2e_total * 1e-3)
+    e2e_value = world * args.steps / (ms_e2e_pipe_total * 1e-3)
     fact_bytes, proj_bytes = algorithmic_bytes(n, nnz, M, args.path)
     achieved = fact_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
@@ -393,8 +421,15 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "e2e": {"value": e2e_value, "unit": "expv/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
-                "ms_per_step": ms_e2e_total / args.steps,
-                "note": "b200k_expv_host through the C ABI; operator resident (uploaded once at ingestion)"},
+                "ms_per_step": ms_e2e_pipe_total / args.steps,
+                "mode": "two requests in flight (b200k_expv_host_async on two handles / streams): every step copies its "
+                        "own 8 MB b from pinned host memory and its own 8 MB w back; the copies of one request overlap "
+                        "the kernels of the other; host wall clock around the whole loop incl. the final synchronise",
+                "one_call_at_a_time": {"value": e2e_sync_value, "ms_per_step": ms_e2e_total / args.steps,
+                                       "note": "synchronous b200k_expv_host: H2D -> kernels -> D2H serialised per call "
+                                               "(CUDA events)"},
+                "pipelined_results_agree": pipe_check,
+                "note": "through the C ABI with HOST buffers; operator resident (uploaded once at ingestion)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": kname.get(headline_kernel, "?"), "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

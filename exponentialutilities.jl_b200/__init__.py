@@ -14,10 +14,10 @@ from . import _lib, build, parallel  # noqa: F401
 from ._lib import (ArgumentError, DimensionMismatch, SingularException, UnsupportedError,  # noqa: F401
                    lib_path, load)
 from .api import (Engine, ExpvCache, KrylovSubspace, Operator, PhivCache, arnoldi, arnoldi_, expv, expv_, expv_batched,  # noqa: F401
-                  expv_host, expv_small, expv_timestep, exponential_, exponential_batched_, get_engine, kiops, lanczos_, operator, phiv, phiv_, phiv_dense, phiv_timestep)
+                  expv_host, expv_host_async, expv_small, expv_timestep, exponential_, exponential_batched_, get_engine, kiops, lanczos_, operator, phiv, phiv_, phiv_dense, phiv_timestep)
 
 __all__ = [
     "Engine", "KrylovSubspace", "Operator", "ExpvCache", "PhivCache", "arnoldi", "arnoldi_", "lanczos_", "expv", "expv_", "expv_batched",
-    "expv_host", "expv_small", "expv_timestep", "phiv_timestep", "phiv", "phiv_", "kiops", "exponential_", "exponential_batched_", "phiv_dense", "operator", "get_engine",
+    "expv_host", "expv_host_async", "expv_small", "expv_timestep", "phiv_timestep", "phiv", "phiv_", "kiops", "exponential_", "exponential_batched_", "phiv_dense", "operator", "get_engine",
     "DimensionMismatch", "ArgumentError", "SingularException", "UnsupportedError", "load", "lib_path",
 ]

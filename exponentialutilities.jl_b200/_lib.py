@@ -73,6 +73,8 @@ PROTOTYPES = {
                                 C.c_void_p, c_int_p]),
     "b200k_expv_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.POINTER(KrylovOpts),
                                   C.c_void_p, c_int_p, c_int_p]),
+    "b200k_expv_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.POINTER(KrylovOpts),
+                                        C.c_void_p]),
     "b200k_phiv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
                              C.POINTER(KrylovOpts), C.c_int, C.c_void_p, C.c_int64, c_double_p, c_int_p,
                              c_int_p]),

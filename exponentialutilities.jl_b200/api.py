@@ -665,6 +665,21 @@ def expv_host(t, op: Operator, b_host, w_host, *, m=30, tol=1.0e-7, ishermitian=
     return w_host
 
 
+def expv_host_async(t, op: Operator, b_host, w_host, *, m=30, tol=1.0e-7, ishermitian=None, iop=0, engine=None):
+    """expv_host without the final synchronisation, on ``engine`` (default: the operator's) and torch's current
+    stream: H2D(b), the kernels and D2H(w) are queued and the call returns; ``engine.synchronize()`` completes it.
+    Two engines on two streams keep two requests in flight so that copies overlap kernels."""
+    eng = engine or op.engine
+    opts = KrylovOpts()
+    eng.lib.b200k_krylov_opts_default(C.byref(opts))
+    opts.m, opts.tol, opts.iop = int(min(m, op.n)), float(tol), int(iop)
+    opts.hermitian = -1 if ishermitian is None else int(bool(ishermitian))
+    eng.bind_stream()
+    eng.check(eng.lib.b200k_expv_host_async(eng.handle, op.ptr, float(t), C.c_void_p(b_host.data_ptr()), C.byref(opts),
+                                            C.c_void_p(w_host.data_ptr())))
+    return w_host
+
+
 def phiv_(w, t, Ks: KrylovSubspace, k, *, cache=None, correct=False, errest=False):
     """phiv!(w, t, Ks, k; correct, errest) -- src/krylov_phiv.jl:607-653.
 

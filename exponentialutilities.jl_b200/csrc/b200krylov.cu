@@ -1512,6 +1512,20 @@ int b200k_expv_ee(b200k_handle_t h, b200k_op_t op, double t, const double *b, in
     return launch_project(h, h->V.as<double>(), ldv, op->n, jstop, beta, y.data(), jstop, 1, w, op->n, nullptr);
 }
 
+int b200k_expv_host_async(b200k_handle_t h, b200k_op_t op, double t, const double *b_host,
+                          const b200k_krylov_opts *opts, double *w_host) {
+    if (!h || !op || !b_host || !opts || !w_host) return B200K_EARG;
+    CK(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)op->n * 8;
+    CK(h, h->bdev.ensure(bytes));
+    CK(h, h->wdev.ensure(bytes));
+    CK(h, cudaMemcpyAsync(h->bdev.p, b_host, bytes, cudaMemcpyHostToDevice, h->stream));
+    const int st = b200k_expv(h, op, t, h->bdev.as<double>(), opts, h->wdev.as<double>(), nullptr, nullptr, nullptr);
+    if (st) return st;
+    CK(h, cudaMemcpyAsync(w_host, h->wdev.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return B200K_OK;
+}
+
 int b200k_expv_host(b200k_handle_t h, b200k_op_t op, double t, const double *b_host,
                     const b200k_krylov_opts *opts, double *w_host, int *m_out, int *breakdown) {
     if (!h || !op || !b_host || !opts || !w_host) return B200K_EARG;

@@ -191,8 +191,11 @@ struct TmaGeom {
 // The producer is ONE lane of the producer warp (every copy, including the 2-D tensor-map boxes, is a single
 // instruction, so there is nothing for the other lanes to do).
 __device__ __forceinline__ bool prod_acquire(SmemTma *S, const Ring &rg, int seq, int) {
+    // (the stop flag is only looked at every 8th failed wait: it matters once per problem, the wait latency matters
+    // every slot, and the flag read is an atomic)
+    unsigned spins = 0;
     while (!mbar_try_wait(&S->empty[rg.slot], rg.phase ^ 1u)) {
-        if (flag_get(&S->stop_seq) >= seq) return false;
+        if ((++spins & 7u) == 0u && flag_get(&S->stop_seq) >= seq) return false;
     }
     return true;
 }
@@ -635,8 +638,10 @@ __device__ double matvec_xl(const KrylovParams &P, Cons &cx, const TmaGeom &G, c
     return selfacc;  // (no trailing barrier: the block reduction of the fused inner product is the barrier)
 }
 
+// Returns this thread's partial of ||w||^2 over the rows it produced (re-orthogonalisation test of Arnoldi / IOP steps).
 template <int OPK, bool AUG>
-__device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *xsrc, double xscale) {
+__device__ double matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *xsrc, double xscale) {
+    double wsq = 0.0;
     SmemTma *S = cx.S;
     const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
     const int n = P.n, p = AUG ? P.p : 0;
@@ -680,7 +685,9 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
                     const double *brow = P.Bm + (G.r0 + rl);
                     for (int k = 0; k < p; ++k) sum = fma(brow[(long long)k * P.ldb], S->xtail[k], sum);
                 }
-                ws[rl] = sum * xscale;
+                const double wv = sum * xscale;
+                ws[rl] = wv;
+                wsq = fma(wv, wv, wsq);
             }
             cx.release();
         }
@@ -694,7 +701,9 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
             if (lane == 0) {
                 if (p > 0)
                     for (int k = 0; k < p; ++k) sum = fma(P.Bm[row + (long long)k * P.ldb], S->xtail[k], sum);
-                ws[rl] = sum * xscale;
+                const double wv = sum * xscale;
+                ws[rl] = wv;
+                wsq = fma(wv, wv, wsq);
             }
         }
     } else {  // dense column-major
@@ -745,8 +754,11 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
                         s1 = fma(P.Bm[G.r0 + rl + 1 + (long long)k * P.ldb], S->xtail[k], s1);
                     }
                 }
-                ws[rl] = s0 * xscale;
-                ws[rl + 1] = s1 * xscale;
+                s0 *= xscale;
+                s1 *= xscale;
+                ws[rl] = s0;
+                ws[rl + 1] = s1;
+                wsq = fma(s0, s0, fma(s1, s1, wsq));
             }
         } else {
             // direct 16-byte loads (slices with more than 1024 rows per CTA)
@@ -780,14 +792,20 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
                             s1 = fma(P.Bm[G.r0 + rl + 1 + (long long)k * P.ldb], S->xtail[k], s1);
                         }
                     }
-                    ws[rl] = s0 * xscale;
-                    ws[rl + 1] = s1 * xscale;
+                    s0 *= xscale;
+                    s1 *= xscale;
+                    ws[rl] = s0;
+                    ws[rl + 1] = s1;
+                    wsq = fma(s0, s0, fma(s1, s1, wsq));
                 }
                 consumer_sync();
             }
         }
     }
+    if (AUG && p > 0 && tid < p && P.myrank == 0 && (int)(blockIdx.x % P.team_size) == 0)
+        wsq = fma(S->wtail[tid], S->wtail[tid], wsq);  // augmented tail rows count once (team rank 0 of GPU 0)
     consumer_sync();
+    return wsq;
 }
 
 // `want_sq`: Arnoldi / IOP steps also reduce ||w||^2 of the incoming w (re-orthogonalisation test, see below) as
@@ -795,7 +813,7 @@ __device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G
 // full (window a multiple of 8 columns) and the caller has to reduce it separately.
 template <int OPK, bool AUG>
 __device__ bool dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
-                             int lo, int hi, long long part_off, bool want_sq) {
+                             int lo, int hi, long long part_off, bool want_sq, double sq_in) {
     SmemTma *S = cx.S;
     const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
     const double2 *ws2 = reinterpret_cast<const double2 *>(cx.ws);
@@ -805,7 +823,6 @@ __device__ bool dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
         const int nb = min(CB, hi - cb + 1);
         const bool sq_here = want_sq && nb < CB && cb + CB > hi;
         double acc[CB];
-        double sq = 0.0;
 #pragma unroll
         for (int u = 0; u < CB; ++u) acc[u] = 0.0;
         for (int k = 0; k < G.ntk; ++k) {
@@ -817,9 +834,6 @@ __device__ bool dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
                 const int idx = tid + q * NTC;
                 wr[q] = idx < pairs ? ws2[pbase + idx] : make_double2(0.0, 0.0);
             }
-            // (unconditional: a loop-invariant branch here makes the compiler duplicate the unrolled tile loop)
-#pragma unroll
-            for (int q = 0; q < PPT; ++q) sq = fma(wr[q].x, wr[q].x, fma(wr[q].y, wr[q].y, sq));
 #pragma unroll
             for (int u = 0; u < CB; ++u) {
                 if (u < nb) {
@@ -843,13 +857,11 @@ __device__ bool dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
                 if (u < nb)
                     for (int kk = 0; kk < P.p; ++kk)
                         acc[u] = fma(V[(long long)(cb + u) * P.ldv + P.n + kk], S->wtail[kk], acc[u]);
-            if (sq_here)
-                for (int kk = 0; kk < P.p; ++kk) sq = fma(S->wtail[kk], S->wtail[kk], sq);
         }
-        if (sq_here) {
+        if (sq_here) {  // the mat-vec's per-thread partial of ||w||^2 rides in the free accumulator slot
 #pragma unroll
             for (int u = 0; u < CB; ++u)
-                if (u == nb) acc[u] = sq;
+                if (u == nb) acc[u] = sq_in;
             sq_done = true;
         }
         const double r = warp_reduce8(acc, lane);
@@ -933,20 +945,13 @@ __device__ double update_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom 
 // out-of-line functions to keep the hot loop's code size and register allocation unchanged.
 constexpr double REORTH_ETA2 = 0.0625;  // eta = 1/4 (squared norms are compared)
 
-// Per-CTA partial of ||w||^2 for the current w slice -> quantity `col` of the step's partial table.
-// (All three take plain values, not the Cons / TmaGeom / Team structs of the caller: an address that escapes into an
+// Per-CTA sum of the mat-vec's per-thread partials of ||w||^2 -> quantity `col` of the step's partial table (only
+// needed when the last inner-product batch has no free accumulator slot, i.e. the window is a multiple of 8 columns).
+// (All of these take plain values, not the Cons / TmaGeom / Team structs of the caller: an address that escapes into an
 // out-of-line call would pin those structs in local memory for the whole hot loop.)
-__device__ __noinline__ void sqnorm_partial_c(const KrylovParams &P, SmemTma *S, const double *ws, int nrows, int rank,
-                                              long long part_off, int col, bool with_tail) {
+__device__ __noinline__ void sqnorm_partial_c(const KrylovParams &P, SmemTma *S, double sq, int rank, long long part_off,
+                                              int col) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double2 *ws2 = reinterpret_cast<const double2 *>(ws);
-    const int units = nrows >> 1;
-    double sq = 0.0;
-    for (int i = tid; i < units; i += NTC) {
-        const double2 w2 = ws2[i];
-        sq = fma(w2.x, w2.x, fma(w2.y, w2.y, sq));
-    }
-    if (with_tail && rank == 0 && P.myrank == 0 && tid < P.p) sq = fma(S->wtail[tid], S->wtail[tid], sq);
     sq = warp_sum(sq);
     if (lane == 0) S->redn[warp] = sq;
     consumer_sync();
@@ -1036,14 +1041,14 @@ __device__ __noinline__ double reorth_update_c(const KrylovParams &P, SmemTma *S
 }
 
 // The whole second pass: inner products, reduction, H += h2, update, norm reduction (result in S->bc[0]).  Passes two
-// team reductions: the caller advances its barrier target by 2 C and its sequence number by 2 afterwards.
-__device__ __noinline__ void reorth_step_c(const KrylovParams &P, SmemTma *S, double *ws, int r0, int nrows, int team,
-                                           int rank, int C, unsigned *bar, unsigned target, unsigned seq, const double *V,
-                                           int lo, int hi, long long part, long long partn, double *xout, long long xoff,
-                                           double *Hcol, bool aug) {
+// team reductions: the caller advances its barrier target by 2 C and its sequence number by 2 afterwards.  Few scalar
+// arguments (everything else is re-derived from P and blockIdx exactly as the kernel does): they travel in registers.
+__device__ __noinline__ void reorth_step_c(const KrylovParams &P, unsigned target, unsigned seq, int prob, int jc, bool aug) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemTma *S = reinterpret_cast<SmemTma *>(smem_raw);
+    const int team = blockIdx.x / P.team_size;
     Cons cx;
     cx.S = S;
-    cx.ws = ws;
     cx.xin = nullptr;
     cx.ws_a = cx.xin_a = 0;
     cx.team = team;
@@ -1052,25 +1057,34 @@ __device__ __noinline__ void reorth_step_c(const KrylovParams &P, SmemTma *S, do
     cx.warp = threadIdx.x >> 5;
     cx.seq = seq;
     Team tm;
-    tm.bar = bar;
+    tm.rank = blockIdx.x % P.team_size;
+    tm.C = P.team_size;
+    tm.bar = P.peer_bar[P.myrank] + team;
     tm.target = target;
     tm.seq = seq;
-    tm.C = C;
-    tm.rank = rank;
     TmaGeom G;
-    G.r0 = r0;
-    G.nrows = nrows;
+    G.r0 = min(P.n, tm.rank * P.slice);
+    G.nrows = min(P.n, G.r0 + P.slice) - G.r0;
     G.nch = G.ntk = G.TR = 0;
-    const int nc = hi - lo + 1;
+    cx.ws = P.w_in_smem ? reinterpret_cast<double *>(smem_raw + sizeof(SmemTma)) : (P.wglob + (long long)team * P.n + G.r0);
+    const int j = jc + 1, par = j & 1;
+    const int iopw = P.iop > 0 ? P.iop : P.m;
+    const int lo = max(0, jc - iopw + 1), hi = jc, nc = hi - lo + 1;
+    const long long xoff = (long long)team * 2 * P.xlen + (par ? P.xlen : 0);
+    double *xout = P.peer_xbuf[P.myrank] + xoff;
+    const long long part = (long long)team * 2 * MAXCOL * P.cpad + (long long)par * MAXCOL * P.cpad;
+    const long long partn = (long long)team * 4 * P.cpad + (long long)par * P.cpad;
+    const double *V = P.V + (long long)prob * P.V_stride;
+    double *Hcol = P.Hd + (long long)prob * P.H_stride + (long long)jc * P.ldh + lo;
     const bool sharded = P.nranks > 1;
     double *h2 = &S->llv[0][0];  // (packet scratch of the XL instance: unused by this instance)
     consumer_sync();
-    reorth_dots_c(P, S, ws, r0, nrows, rank, V, lo, hi, part, aug);
+    reorth_dots_c(P, S, cx.ws, G.r0, G.nrows, tm.rank, V, lo, hi, part, aug);
     team_reduce_c(P, cx, tm, P.peer_part[P.myrank] + part, nc, h2, false);
-    if (rank == 0)
+    if (tm.rank == 0)
         for (int ci = cx.tid; ci < nc; ci += NTC) Hcol[ci] = S->hs[ci] + h2[ci];
-    const double nrm2 = reorth_update_c(P, S, ws, r0, nrows, rank, V, lo, hi, h2, xout, aug);
-    block_sum_to_c(P, cx, nrm2, partn + rank);
+    const double nrm2 = reorth_update_c(P, S, cx.ws, G.r0, G.nrows, tm.rank, V, lo, hi, h2, xout, aug);
+    block_sum_to_c(P, cx, nrm2, partn + tm.rank);
     push_halo(P, cx, G, tm, xoff);
     team_reduce_c(P, cx, tm, P.peer_partn[P.myrank] + partn, 1, S->bc, sharded);
 }
@@ -1181,7 +1195,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         const long long partn = partn0 + (long long)par * P.cpad;
 
         PT_MARK(blockIdx.x, j, 0);
-        matvec_phase_c<OPK, AUG>(P, cx, G, xsrc, xscale);
+        const double wsq_part = matvec_phase_c<OPK, AUG>(P, cx, G, xsrc, xscale);
         PT_MARK(blockIdx.x, j, 1);
 
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
@@ -1194,8 +1208,8 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
 #endif
         const int nc = hi - lo + 1;
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
-        if (!dots_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, hi, part, dgks))
-            sqnorm_partial_c(P, S, cx.ws, G.nrows, tm.rank, part, nc, AUG);
+        if (!dots_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, hi, part, dgks, wsq_part))
+            sqnorm_partial_c(P, S, wsq_part, tm.rank, part, nc);
         PT_MARK(blockIdx.x, j, 2);
         team_reduce_c(P, cx, tm, lpart + part, dgks ? nc + 1 : nc, S->hs + (lo - ulo), false);
         PT_MARK(blockIdx.x, j, 3);
@@ -1215,8 +1229,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
             // second classical Gram-Schmidt pass (every CTA of every rank takes the same decision: the reduced values
             // are bitwise identical everywhere; NaN never triggers it).  Out of line, two more team reductions.
 #ifndef B200K_DGKS_NOCALL  // A/B builds only
-            reorth_step_c(P, S, cx.ws, G.r0, G.nrows, cx.team, tm.rank, tm.C, tm.bar, tm.target, cx.seq, V, lo, hi, part,
-                          partn, xout, xoff, Hd + (long long)jc * ldh + lo, AUG);
+            reorth_step_c(P, tm.target, cx.seq, prob, jc, AUG);
 #endif
             tm.target += 2u * (unsigned)tm.C;
             cx.seq += 2u;

@@ -142,6 +142,13 @@ int b200k_expv_ee(b200k_handle_t h, b200k_op_t op, double t, const double *b, in
 /* Same call with HOST vectors: copies b in and w out on the handle's stream (end-to-end path). */
 int b200k_expv_host(b200k_handle_t h, b200k_op_t op, double t, const double *b_host,
                     const b200k_krylov_opts *opts, double *w_host, int *m_out, int *breakdown);
+/* The same without the final synchronisation: everything (H2D of b, the three kernels, D2H of w) is queued on the
+ * handle's stream and the call returns; w_host is valid after b200k_synchronize(h), which also reports a deferred
+ * SingularException.  b_host / w_host should be pinned and must stay untouched until then.  A server keeps two
+ * handles on two streams in flight so that the copies of one request overlap the kernels of the other (an operator
+ * may be used through any handle of its device, one call at a time). */
+int b200k_expv_host_async(b200k_handle_t h, b200k_op_t op, double t, const double *b_host,
+                          const b200k_krylov_opts *opts, double *w_host);
 /* phiv(t, A, b, k; correct, errest) one-shot (src/krylov_phiv.jl:563-570). */
 int b200k_phiv(b200k_handle_t h, b200k_op_t op, double t, const double *b, int k,
                const b200k_krylov_opts *opts, int correct, double *W, int64_t ldw, double *errest,
