@@ -305,6 +305,8 @@ struct KrylovCall {
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+void account_sharded(b200k_context *h, b200k_comm *cm, const KrylovCall &c, bool ran, int js, int je, int nreorth);
+
 // Launch the persistent kernel; results land in h->Hd / h->scal / h->stat (device), ldhd = m + 1.
 int launch_krylov(b200k_context *h, const KrylovCall &c) {
     b200k_operator *op = c.op;
@@ -440,6 +442,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
     CUtensorMap tmapA;
     std::memset(&tmapA, 0, sizeof(tmapA));
     const void *kern = (const void *)krylov_persistent_kernel;
+    const void *kern_safe = nullptr;
     int threads = NT;
     if (vec2 && !h->force_ldg) {
         const size_t fixed = sizeof(SmemTma);
@@ -545,6 +548,15 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
         P.wglob = h->wglob.as<double>();
         {
             const bool aug = c.p > 0;
+            // Arnoldi / IOP on the general instance: the fast kernel hands over to the SAFE instance (second
+            // Gram-Schmidt pass) at the first step whose re-orthogonalisation test fires
+            if (!xl && !c.lanczos) {
+                switch (P.op_kind) {
+                    case OP_CSR_STREAM: kern_safe = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, false, 8, true> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, false, 8, true>; break;
+                    case OP_CSR_WARP: kern_safe = aug ? (const void *)krylov_tma_kernel<OP_CSR_WARP, true, false, 8, true> : (const void *)krylov_tma_kernel<OP_CSR_WARP, false, false, 8, true>; break;
+                    default: kern_safe = aug ? (const void *)krylov_tma_kernel<OP_DENSE, true, false, 8, true> : (const void *)krylov_tma_kernel<OP_DENSE, false, false, 8, true>; break;
+                }
+            }
             switch (P.op_kind) {
                 case OP_CSR_STREAM:
                     if (xl && op->max_row_nnz <= 5) kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5>;
@@ -565,9 +577,47 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
     if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
     void *args[] = {(void *)&P, (void *)&tmapA};
     CK(h, cudaLaunchCooperativeKernel(kern, dim3(c.g.C * c.g.nteams), dim3(threads), args, smem, h->stream));
+    h->launches += 1;
+    if (cm) {
+        // Row-sharded: the barrier counters / packet sequence numbers of the communicator are never reset, so what the
+        // launch consumed (data dependent: breakdown, hand-over step) is read back before anything else is launched.
+        CK(h, h->stath.ensure(16));
+        CK(h, h->scalh.ensure(32));
+        CK(h, cudaMemcpyAsync(h->stath.p, h->stat.p, 16, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(h->scalh.p, h->scal.p, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        const int *st = h->stath.as<int>();
+        const bool ran = c.j0 != 0 || h->scalh.as<double>()[0] != 0.0;
+        const int js = c.j0 == 0 ? 1 : c.j0;
+        const int redo = (kern_safe && ran) ? st[3] : 0;
+        account_sharded(h, cm, c, ran, js, redo ? redo : st[0], 0);
+        if (redo) {
+            KrylovParams P2 = P;
+            P2.j0 = redo;
+            P2.j0_from_stat = 0;
+            P2.bar_base = cm->bar_base;
+            P2.seq_base = cm->seq_base;
+            void *args2[] = {(void *)&P2, (void *)&tmapA};
+            CK(h, cudaLaunchCooperativeKernel(kern_safe, dim3(c.g.C * c.g.nteams), dim3(threads), args2, smem, h->stream));
+            h->launches += 1;
+            CK(h, cudaMemcpyAsync(h->stath.p, h->stat.p, 16, cudaMemcpyDeviceToHost, h->stream));
+            CK(h, cudaStreamSynchronize(h->stream));
+            KrylovCall c2 = c;
+            c2.j0 = redo;
+            account_sharded(h, cm, c2, true, redo, st[0], st[2]);
+        }
+    } else if (kern_safe) {
+        // One GPU: the SAFE instance is always queued behind the fast one and reads per problem where to resume
+        // (nowhere, normally: 148 CTAs read one word and exit -- a few microseconds, no host round trip).
+        KrylovParams P2 = P;
+        P2.j0_from_stat = 1;
+        CK(h, cudaMemsetAsync(P.bar, 0, (size_t)nt * 4, h->stream));
+        void *args2[] = {(void *)&P2, (void *)&tmapA};
+        CK(h, cudaLaunchCooperativeKernel(kern_safe, dim3(c.g.C * c.g.nteams), dim3(threads), args2, smem, h->stream));
+        h->launches += 1;
+    }
     if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
     if (h->timing) { h->ev_k = true; h->ev_p = false; }
-    h->launches += 1;
     return B200K_OK;
 }
 
@@ -845,11 +895,6 @@ int arnoldi_core(b200k_context *h, b200k_operator *op, const double *b, const b2
     if (st) return st;
     st = fetch_krylov(h, 1, m);
     if (st) return st;
-    if (op->comm) {  // the multi-GPU barrier counters are never reset: account for this launch's arrivals
-        const double b0 = o->init == 0 ? h->scalh.as<double>()[0] : *beta;
-        const int js = c.j0 == 0 ? 1 : c.j0;
-        account_sharded(h, op->comm, c, b0 != 0.0, js, h->stath.as<int>()[0], h->stath.as<int>()[2]);
-    }
     const double *Hh = h->Hh.as<double>();
     const int ldhd = m + 1;
     if (o->init == 0) *beta = h->scalh.as<double>()[0];
@@ -1079,7 +1124,10 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
                                  (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 8>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 8>,
                                  (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5>,
                                  (const void *)krylov_tma_kernel<OP_CSR_WARP, false, false>, (const void *)krylov_tma_kernel<OP_CSR_WARP, true, false>,
-                                 (const void *)krylov_tma_kernel<OP_DENSE, false, false>, (const void *)krylov_tma_kernel<OP_DENSE, true, false>};
+                                 (const void *)krylov_tma_kernel<OP_DENSE, false, false>, (const void *)krylov_tma_kernel<OP_DENSE, true, false>,
+                                 (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, false, 8, true>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, false, 8, true>,
+                                 (const void *)krylov_tma_kernel<OP_CSR_WARP, false, false, 8, true>, (const void *)krylov_tma_kernel<OP_CSR_WARP, true, false, 8, true>,
+                                 (const void *)krylov_tma_kernel<OP_DENSE, false, false, 8, true>, (const void *)krylov_tma_kernel<OP_DENSE, true, false, 8, true>};
     cudaFuncSetAttribute((const void *)krylov_mv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     cudaFuncSetAttribute((const void *)krylov_mv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     bool attr_ok = true;
@@ -1442,9 +1490,6 @@ int b200k_expv(b200k_handle_t h, b200k_op_t op, double t, const double *b, const
             beta = h->scalh.as<double>()[0];
             mo = beta == 0.0 ? o.m : h->stath.as<int>()[0];
             bd = beta == 0.0 ? 0 : h->stath.as<int>()[1];
-            if (op->comm) {
-                account_sharded(h, op->comm, c, beta != 0.0, 1, mo, h->stath.as<int>()[2]);
-            }
             if (*h->errh.as<int>()) return fail(h, B200K_ESINGULAR, "SingularException(0): Pade denominator is singular");
             if (m_out) *m_out = mo;
             if (breakdown) *breakdown = bd;

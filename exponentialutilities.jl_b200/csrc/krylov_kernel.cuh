@@ -78,6 +78,7 @@ struct KrylovParams {
     // algorithm
     int m;
     int j0;  // 0: firststep!, else continue with step j0 (1-based)
+    int j0_from_stat;  // SAFE instance of krylov_tma_kernel: per problem, resume at stat[4 prob + 3] (0: skip the problem)
     int iop;
     int lanczos;
     double tol;
@@ -641,23 +642,15 @@ __device__ void krylov_body(const KrylovParams &P, SmemFixed *S, double *ws_smem
             dots_phase<VEC>(P, cx, tm, V, lo, hi, part);
             const int nc = hi - lo + 1;
             const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
-            // Arnoldi / IOP: ||w_before||^2 travels with the inner products as quantity nc (DGKS re-orthogonalisation
-            // test, see krylov_kernel_tma.cuh)
+            // DGKS re-orthogonalisation test (see krylov_kernel_tma.cuh): ||w_before||^2 = ||h||^2 + ||w_after||^2
             const bool dgks = !P.lanczos;
-            if (dgks) {
-                double sq = 0.0;
-                for (int i = tid; i < cx.nrows; i += NT) sq = fma(cx.ws[i], cx.ws[i], sq);
-                if (p > 0 && tm.rank == 0 && tid < p) sq = fma(S->wtail[tid], S->wtail[tid], sq);
-                __syncthreads();
-                block_sum_to(cx, sq, part + (long long)nc * CPAD + tm.rank);
-            }
             team_barrier(tm);
 
-            for (int ci = cx.warp; ci < (dgks ? nc + 1 : nc); ci += NW) {
+            for (int ci = cx.warp; ci < nc; ci += NW) {
                 const double s = team_sum(part + (long long)ci * CPAD, tm.C, cx.lane);
                 if (cx.lane == 0) {
                     S->hs[lo + ci - ulo] = s;
-                    if (tm.rank == 0 && ci < nc) Hd[(long long)jc * ldh + lo + ci] = s;
+                    if (tm.rank == 0) Hd[(long long)jc * ldh + lo + ci] = s;
                 }
             }
             if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = beta_prev;
@@ -668,7 +661,10 @@ __device__ void krylov_body(const KrylovParams &P, SmemFixed *S, double *ws_smem
             team_barrier(tm);
 
             double beta2 = team_sum(partn, tm.C, cx.lane);
-            if (dgks && beta2 < 0.0625 * S->hs[nc]) {  // second classical Gram-Schmidt pass (eta = 1/4)
+            double hsq = 0.0;
+            if (dgks)
+                for (int ci = 0; ci < nc; ++ci) hsq = fma(S->hs[ci], S->hs[ci], hsq);
+            if (dgks && beta2 < 0.0625 * (hsq + beta2)) {  // second classical Gram-Schmidt pass (eta = 1/4)
                 __syncthreads();
                 dots_phase<VEC>(P, cx, tm, V, lo, hi, part);
                 team_barrier(tm);

@@ -49,14 +49,19 @@ struct __align__(128) SmemTma {
     int chunk_local[MAXCH2];  // XL: every column of the chunk lies in this CTA's slice (learnt by the first mat-vec)
     double bc[2];             // reduced scalars (squared norm) broadcast to the CTA
     double llv[LLQ][CPAD];    // packets of a fused barrier + all-reduce (ll_collect), one value per CTA of the team
-    // Flags the producer lane polls while the consumers run.  All accesses after initialisation are shared-memory
-    // ATOMICS (flag_set / flag_get): a polled flag is a data race by definition for plain loads and stores
-    // (compute-sanitizer racecheck reports it), atomics make the single-writer / single-reader protocol well defined.
+    // Flags the producer lane polls while the consumers run (single writer, single reader).  flag_set / flag_get are
+    // volatile accesses in the product and shared-memory atomics in -DB200K_ATOMIC_FLAGS builds: a polled flag is a
+    // data race by definition for plain loads and stores, which compute-sanitizer racecheck reports.
     int cols_ready;  // number of complete basis columns of the current problem
     int stop_seq;    // consumers finished local problem #stop_seq (1-based)
 };
+#ifdef B200K_ATOMIC_FLAGS  // sanitizer builds: shared-memory atomics, so that racecheck sees a race-free protocol
 __device__ __forceinline__ void flag_set(int *f, int v) { atomicExch(f, v); }
 __device__ __forceinline__ int flag_get(int *f) { return atomicAdd(f, 0); }
+#else  // product: volatile accesses (measured: the atomics cost 1.1 % of the C2 Arnoldi kernel)
+__device__ __forceinline__ void flag_set(int *f, int v) { *reinterpret_cast<volatile int *>(f) = v; }
+__device__ __forceinline__ int flag_get(int *f) { return *reinterpret_cast<volatile int *>(f); }
+#endif
 
 // Per-phase timestamps (profiling builds only: -DB200K_PHASE_TIMING, scripts/phase_timing.py).
 #ifdef B200K_PHASE_TIMING
@@ -209,9 +214,9 @@ __device__ __forceinline__ bool prod_wait_col(SmemTma *S, int col, int seq, int)
 
 template <int OPK, bool AUG, bool XL>
 __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, SmemTma *S, Ring &rg,
-                                 const TmaGeom &G, const double *V, int seq, unsigned &issued, int lane) {
+                                 const TmaGeom &G, const double *V, int seq, unsigned &issued, int lane, int j0) {
     const long long ldv = P.ldv;
-    const int jstart = P.j0 == 0 ? 1 : P.j0;
+    const int jstart = j0 == 0 ? 1 : j0;
     const int iopw = P.iop > 0 ? P.iop : P.m;
     const int nnz_cap = P.nnz_cap;
     // L2 eviction priorities (P.l2hint): the operator is streamed once per step and would otherwise push the
@@ -638,10 +643,8 @@ __device__ double matvec_xl(const KrylovParams &P, Cons &cx, const TmaGeom &G, c
     return selfacc;  // (no trailing barrier: the block reduction of the fused inner product is the barrier)
 }
 
-// Returns this thread's partial of ||w||^2 over the rows it produced (re-orthogonalisation test of Arnoldi / IOP steps).
 template <int OPK, bool AUG>
-__device__ double matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *xsrc, double xscale) {
-    double wsq = 0.0;
+__device__ void matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *xsrc, double xscale) {
     SmemTma *S = cx.S;
     const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
     const int n = P.n, p = AUG ? P.p : 0;
@@ -685,9 +688,7 @@ __device__ double matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom 
                     const double *brow = P.Bm + (G.r0 + rl);
                     for (int k = 0; k < p; ++k) sum = fma(brow[(long long)k * P.ldb], S->xtail[k], sum);
                 }
-                const double wv = sum * xscale;
-                ws[rl] = wv;
-                wsq = fma(wv, wv, wsq);
+                ws[rl] = sum * xscale;
             }
             cx.release();
         }
@@ -701,9 +702,7 @@ __device__ double matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom 
             if (lane == 0) {
                 if (p > 0)
                     for (int k = 0; k < p; ++k) sum = fma(P.Bm[row + (long long)k * P.ldb], S->xtail[k], sum);
-                const double wv = sum * xscale;
-                ws[rl] = wv;
-                wsq = fma(wv, wv, wsq);
+                ws[rl] = sum * xscale;
             }
         }
     } else {  // dense column-major
@@ -754,11 +753,8 @@ __device__ double matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom 
                         s1 = fma(P.Bm[G.r0 + rl + 1 + (long long)k * P.ldb], S->xtail[k], s1);
                     }
                 }
-                s0 *= xscale;
-                s1 *= xscale;
-                ws[rl] = s0;
-                ws[rl + 1] = s1;
-                wsq = fma(s0, s0, fma(s1, s1, wsq));
+                ws[rl] = s0 * xscale;
+                ws[rl + 1] = s1 * xscale;
             }
         } else {
             // direct 16-byte loads (slices with more than 1024 rows per CTA)
@@ -792,36 +788,25 @@ __device__ double matvec_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom 
                             s1 = fma(P.Bm[G.r0 + rl + 1 + (long long)k * P.ldb], S->xtail[k], s1);
                         }
                     }
-                    s0 *= xscale;
-                    s1 *= xscale;
-                    ws[rl] = s0;
-                    ws[rl + 1] = s1;
-                    wsq = fma(s0, s0, fma(s1, s1, wsq));
+                    ws[rl] = s0 * xscale;
+                    ws[rl + 1] = s1 * xscale;
                 }
                 consumer_sync();
             }
         }
     }
-    if (AUG && p > 0 && tid < p && P.myrank == 0 && (int)(blockIdx.x % P.team_size) == 0)
-        wsq = fma(S->wtail[tid], S->wtail[tid], wsq);  // augmented tail rows count once (team rank 0 of GPU 0)
     consumer_sync();
-    return wsq;
 }
 
-// `want_sq`: Arnoldi / IOP steps also reduce ||w||^2 of the incoming w (re-orthogonalisation test, see below) as
-// quantity hi - lo + 1.  It rides in a free accumulator slot of the last batch; returns false if that batch was
-// full (window a multiple of 8 columns) and the caller has to reduce it separately.
 template <int OPK, bool AUG>
-__device__ bool dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
-                             int lo, int hi, long long part_off, bool want_sq, double sq_in) {
+__device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
+                             int lo, int hi, long long part_off) {
     SmemTma *S = cx.S;
     const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
     const double2 *ws2 = reinterpret_cast<const double2 *>(cx.ws);
     int batch = 0;
-    bool sq_done = false;
     for (int cb = lo; cb <= hi; cb += CB, ++batch) {
         const int nb = min(CB, hi - cb + 1);
-        const bool sq_here = want_sq && nb < CB && cb + CB > hi;
         double acc[CB];
 #pragma unroll
         for (int u = 0; u < CB; ++u) acc[u] = 0.0;
@@ -858,24 +843,17 @@ __device__ bool dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
                     for (int kk = 0; kk < P.p; ++kk)
                         acc[u] = fma(V[(long long)(cb + u) * P.ldv + P.n + kk], S->wtail[kk], acc[u]);
         }
-        if (sq_here) {  // the mat-vec's per-thread partial of ||w||^2 rides in the free accumulator slot
-#pragma unroll
-            for (int u = 0; u < CB; ++u)
-                if (u == nb) acc[u] = sq_in;
-            sq_done = true;
-        }
         const double r = warp_reduce8(acc, lane);
         const int buf = batch & 1;
         if ((lane & 3) == 0) S->red[buf][warp][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = r;
         consumer_sync();
-        if (tid < nb + (sq_here ? 1 : 0)) {
+        if (tid < nb) {
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) s += S->red[buf][w][tid];
             P.peer_part[P.myrank][part_off + (long long)(cb - lo + tid) * P.cpad + tm.rank] = s;
         }
     }
-    return sq_done || !want_sq;
 }
 
 template <int OPK, bool AUG>
@@ -945,25 +923,8 @@ __device__ double update_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom 
 // out-of-line functions to keep the hot loop's code size and register allocation unchanged.
 constexpr double REORTH_ETA2 = 0.0625;  // eta = 1/4 (squared norms are compared)
 
-// Per-CTA sum of the mat-vec's per-thread partials of ||w||^2 -> quantity `col` of the step's partial table (only
-// needed when the last inner-product batch has no free accumulator slot, i.e. the window is a multiple of 8 columns).
 // (All of these take plain values, not the Cons / TmaGeom / Team structs of the caller: an address that escapes into an
 // out-of-line call would pin those structs in local memory for the whole hot loop.)
-__device__ __noinline__ void sqnorm_partial_c(const KrylovParams &P, SmemTma *S, double sq, int rank, long long part_off,
-                                              int col) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    sq = warp_sum(sq);
-    if (lane == 0) S->redn[warp] = sq;
-    consumer_sync();
-    if (tid == 0) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) s += S->redn[w];
-        P.peer_part[P.myrank][part_off + (long long)col * P.cpad + rank] = s;
-    }
-    consumer_sync();  // redn is reused by the next block reduction
-}
-
 // Second-pass inner products <v_c, w> for c = lo..hi with direct loads of the CTA's basis slice.
 __device__ __noinline__ void reorth_dots_c(const KrylovParams &P, SmemTma *S, const double *ws, int r0, int nrows, int rank,
                                            const double *V, int lo, int hi, long long part_off, bool aug) {
@@ -1090,9 +1051,14 @@ __device__ __noinline__ void reorth_step_c(const KrylovParams &P, unsigned targe
 }
 
 // One problem on the consumer side.  Mirrors krylov_body<2> of krylov_kernel.cuh.
-template <int OPK, bool AUG>
+// SAFE = false: the fast instance.  When the re-orthogonalisation test fires at step j it records j in stat[4 prob + 3]
+// and stops; the SAFE instance (launched right behind it, or by the host for row-sharded operators) resumes the
+// factorisation at that step like arnoldi!(...; init = j) and runs the second Gram-Schmidt pass where needed.  Keeping
+// the second pass out of the fast instance matters: merely containing the (never executed) call cost 5 % of the C2
+// Arnoldi kernel (profiles/r2_dgks_ab.log).
+template <int OPK, bool AUG, bool SAFE>
 __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom &G, Team &tm, int prob, int nlocal,
-                                 double *xb0, double *xb1, long long xoff0, long long part0, long long partn0) {
+                                 double *xb0, double *xb1, long long xoff0, long long part0, long long partn0, int j0) {
     SmemTma *S = cx.S;
     const int tid = cx.tid;
     const int n = P.n, p = AUG ? P.p : 0;
@@ -1106,14 +1072,14 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
     const double *xsrc;
     double xscale;
     int jstart;
-    int m_out = P.m, breakdown = 0, nreorth = 0;
+    int m_out = P.m, breakdown = 0, nreorth = 0, redo = 0;
     const bool sharded = P.nranks > 1;
     const bool via_xb0 = p > 0 || sharded;            // first gather source must carry tail / halo entries
     const double *lpart = P.peer_part[P.myrank];      // this GPU's inboxes
     const double *lpartn = P.peer_partn[P.myrank];
     const int xt = n + P.nhalo;                       // offset of the augmented tail in the gather buffers
 
-    if (P.j0 == 0) {  // firststep! (arnoldi.jl:230-250 / 257-279)
+    if (j0 == 0) {  // firststep! (arnoldi.jl:230-250 / 257-279)
         double nrm = 0.0;
         for (int i = tid; i < units; i += NTC) {
             const double2 b2 = reinterpret_cast<const double2 *>(b + G.r0)[i];
@@ -1137,6 +1103,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
                 P.stat[prob * 4 + 0] = P.m;
                 P.stat[prob * 4 + 1] = 0;
                 P.stat[prob * 4 + 2] = 0;
+                P.stat[prob * 4 + 3] = 0;
             }
             return;
         }
@@ -1165,7 +1132,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         xscale = 1.0 / beta;
         jstart = 1;
     } else {
-        const double *vj = V + (long long)(P.j0 - 1) * ldv;
+        const double *vj = V + (long long)(j0 - 1) * ldv;
         if (sharded) {  // the resumed column has no halo: stage it in the gather buffer and push the halo
             for (int i = tid; i < units; i += NTC) {
                 const double2 v2 = reinterpret_cast<const double2 *>(vj + G.r0)[i];
@@ -1181,7 +1148,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
             xsrc = vj;
         }
         xscale = 1.0;
-        jstart = P.j0;
+        jstart = j0;
     }
 
     double beta_prev = 0.0;
@@ -1195,12 +1162,11 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         const long long partn = partn0 + (long long)par * P.cpad;
 
         PT_MARK(blockIdx.x, j, 0);
-        const double wsq_part = matvec_phase_c<OPK, AUG>(P, cx, G, xsrc, xscale);
+        matvec_phase_c<OPK, AUG>(P, cx, G, xsrc, xscale);
         PT_MARK(blockIdx.x, j, 1);
 
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
         const int hi = jc;
-        // Arnoldi / IOP: ||w_before||^2 travels with the inner products as quantity nc (re-orthogonalisation test)
 #ifdef B200K_NO_DGKS  // A/B builds only
         const bool dgks = false;
 #else
@@ -1208,10 +1174,9 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
 #endif
         const int nc = hi - lo + 1;
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
-        if (!dots_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, hi, part, dgks, wsq_part))
-            sqnorm_partial_c(P, S, wsq_part, tm.rank, part, nc);
+        dots_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, hi, part);
         PT_MARK(blockIdx.x, j, 2);
-        team_reduce_c(P, cx, tm, lpart + part, dgks ? nc + 1 : nc, S->hs + (lo - ulo), false);
+        team_reduce_c(P, cx, tm, lpart + part, nc, S->hs + (lo - ulo), false);
         PT_MARK(blockIdx.x, j, 3);
         if (tm.rank == 0)
             for (int ci = tid; ci < nc; ci += NTC) Hd[(long long)jc * ldh + lo + ci] = S->hs[lo + ci - ulo];
@@ -1225,15 +1190,33 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, sharded);
         PT_MARK(blockIdx.x, j, 5);
 
-        if (dgks && S->bc[0] < REORTH_ETA2 * S->hs[nc]) {
-            // second classical Gram-Schmidt pass (every CTA of every rank takes the same decision: the reduced values
-            // are bitwise identical everywhere; NaN never triggers it).  Out of line, two more team reductions.
-#ifndef B200K_DGKS_NOCALL  // A/B builds only
-            reorth_step_c(P, tm.target, cx.seq, prob, jc, AUG);
-#endif
-            tm.target += 2u * (unsigned)tm.C;
-            cx.seq += 2u;
-            ++nreorth;
+        // ||w_before||^2 = ||h||^2 + ||w_after||^2 for an orthonormal window (Pythagoras): the test needs no extra
+        // reduction; every thread sums the nc <= 255 coefficients itself (shared-memory broadcast reads)
+        double hsq = 0.0;
+        if (dgks) {
+            double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;  // (four chains: the sum sits on every thread's critical path)
+            int ci = 0;
+            for (; ci + 3 < nc; ci += 4) {
+                h0 = fma(S->hs[ci], S->hs[ci], h0);
+                h1 = fma(S->hs[ci + 1], S->hs[ci + 1], h1);
+                h2 = fma(S->hs[ci + 2], S->hs[ci + 2], h2);
+                h3 = fma(S->hs[ci + 3], S->hs[ci + 3], h3);
+            }
+            for (; ci < nc; ++ci) h0 = fma(S->hs[ci], S->hs[ci], h0);
+            hsq = (h0 + h1) + (h2 + h3);
+        }
+        if (dgks && S->bc[0] < REORTH_ETA2 * (hsq + S->bc[0])) {
+            // every CTA of every rank takes the same decision: the reduced values are bitwise identical everywhere
+            // (NaN never triggers it)
+            if (SAFE) {  // second classical Gram-Schmidt pass, out of line; two more team reductions
+                reorth_step_c(P, tm.target, cx.seq, prob, jc, AUG);
+                tm.target += 2u * (unsigned)tm.C;
+                cx.seq += 2u;
+                ++nreorth;
+            } else {     // hand the rest of the factorisation to the SAFE instance
+                redo = j;
+                break;
+            }
         }
         const double beta = sqrt(S->bc[0]);
         if (tm.rank == 0 && tid == 0) Hd[(long long)jc * ldh + jc + 1] = beta;
@@ -1264,6 +1247,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         P.stat[prob * 4 + 0] = m_out;
         P.stat[prob * 4 + 1] = breakdown;
         P.stat[prob * 4 + 2] = nreorth;  // steps that took the second Gram-Schmidt pass (host: barrier accounting)
+        if (!SAFE) P.stat[prob * 4 + 3] = redo;  // step at which the SAFE instance has to take over (0: never)
     }
 }
 
@@ -1646,7 +1630,7 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
 
 // One instance per (operator kind, augmented or not): the persistent kernel is sensitive to code size (an unused
 // extra mat-vec loop cost 3-5 % everywhere), so each instance carries only the paths it can take.
-template <int OPK, bool AUG, bool XL, int GW = 8>
+template <int OPK, bool AUG, bool XL, int GW = 8, bool SAFE = false>
 __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constant__ KrylovParams P,
                                                             const __grid_constant__ CUtensorMap tmA) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1712,18 +1696,27 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
 
     int nlocal = -1;
     for (int prob = team; prob < P.nprob; prob += P.nteams) {
+        // SAFE instance launched behind the fast one: the step to resume at comes from the fast instance's status
+        // word (0: this problem needed no re-orthogonalisation -- nothing to do)
+        int j0 = P.j0;
+        if (SAFE && P.j0_from_stat) {
+            j0 = P.stat[prob * 4 + 3];
+            if (j0 == 0) continue;  // (uniform for the CTA; the ring stays as the last processed problem left it)
+            if (tid == 0) S->cols_ready = j0;
+            __syncthreads();
+        }
         ++nlocal;
         if (is_producer) {
             if (tid == NTC) {
                 Ring rg{ring, P.nslot, 0, 0u};
                 unsigned issued = 0;
-                producer_problem<OPK, AUG, XL>(P, &tmA, S, rg, G, P.V + (long long)prob * P.V_stride, nlocal + 1, issued, 0);
+                producer_problem<OPK, AUG, XL>(P, &tmA, S, rg, G, P.V + (long long)prob * P.V_stride, nlocal + 1, issued, 0, j0);
             }
             __syncwarp();
         } else {
             cx.rg = Ring{ring, P.nslot, 0, 0u};
             if constexpr (XL) consumer_problem_xl<OPK, AUG, true, GW>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
-            else consumer_problem<OPK, AUG>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
+            else consumer_problem<OPK, AUG, SAFE>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0, j0);
             consumer_sync();
             if (tid == 0) flag_set(&S->stop_seq, nlocal + 1);
         }

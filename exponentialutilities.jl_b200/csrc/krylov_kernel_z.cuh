@@ -265,24 +265,13 @@ __global__ void __launch_bounds__(NT, 1) krylov_z_kernel(const __grid_constant__
                     part[(long long)(cb - lo + tid) * CPAD + tm.rank] = s;
                 }
             }
-            if (dgks && pass == 0) {  // ||w_before||^2 travels with the inner products as quantity nc
-                double sq = 0.0;
-                for (int i = tid; i < nrows; i += NT) {
-                    const double2 w1 = ws[i];
-                    sq = fma(w1.x, w1.x, fma(w1.y, w1.y, sq));
-                }
-                __syncthreads();
-                block_sum_to_z(S, tid, lane, warp, sq, &part[(long long)nc * CPAD + tm.rank].x);
-            }
             team_barrier(tm);
 
-            for (int ci = warp; ci < ((dgks && pass == 0) ? nc + 1 : nc); ci += NW) {
+            for (int ci = warp; ci < nc; ci += NW) {
                 double2 s = team_sum_z(part + (long long)ci * CPAD, tm.C, lane);
                 if (P.lanczos) s.y = 0.0;  // coeff(U <: Real, alpha) = real(alpha)
                 if (lane == 0) {
-                    if (ci == nc) {
-                        S->hs[MAXCOL - 1].x = s.x;  // (m < MAXCOL: the last slot is never a window column)
-                    } else if (pass == 0) {
+                    if (pass == 0) {
                         S->hs[lo + ci - ulo] = s;
                         if (tm.rank == 0) P.Hd[(long long)jc * P.ldh + lo + ci] = s;
                     } else {
@@ -296,7 +285,8 @@ __global__ void __launch_bounds__(NT, 1) krylov_z_kernel(const __grid_constant__
             }
             if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = make_double2(beta_prev, 0.0);
             __syncthreads();
-            if (dgks && pass == 0) wsq_before = S->hs[MAXCOL - 1].x;
+            if (dgks && pass == 0)  // ||w_before||^2 = ||h||^2 + ||w_after||^2 (orthonormal window)
+                for (int ci = 0; ci < nc; ++ci) wsq_before += S->hs[ci].x * S->hs[ci].x + S->hs[ci].y * S->hs[ci].y;
 
             // ---- update w -= sum_c h_c v_c (reverse order), partial ||w||^2, publish the unnormalised w ----
             double nrm = 0.0;
@@ -314,7 +304,7 @@ __global__ void __launch_bounds__(NT, 1) krylov_z_kernel(const __grid_constant__
             block_sum_to_z(S, tid, lane, warp, nrm, partn + tm.rank);
             team_barrier(tm);
             beta2 = team_sum(partn, tm.C, lane);
-            if (!(dgks && pass == 0 && beta2 < 0.0625 * wsq_before)) break;
+            if (!(dgks && pass == 0 && beta2 < 0.0625 * (wsq_before + beta2))) break;
             __syncthreads();
         }
 
