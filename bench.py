@@ -415,6 +415,7 @@ def main():
         pass
 
     kname = {"ldg": "krylov_persistent_kernel", "tma": "krylov_tma_kernel", "tma_xl": "krylov_tma_kernel<XL>",
+             "tma_xl1": "krylov_tma_kernel<XL, one-reduction Lanczos>",
              "tma_mv": "krylov_mv_kernel"}
     line = {
         "metric": "expv/s", "value": value, "unit": "expv/s", "n_gpus": world, "steps": args.steps,

@@ -83,7 +83,7 @@ class Engine:
 
     def set_flag(self, name: str, value: bool):
         """'force_ldg' or 'host_smallexp' (include/b200krylov.h: B200K_FLAG_*)."""
-        flag = {"force_ldg": 1, "host_smallexp": 2, "l2hint": 3, "no_xl": 4, "no_mv": 5, "sym_pade": 6}[name]
+        flag = {"force_ldg": 1, "host_smallexp": 2, "l2hint": 3, "no_xl": 4, "no_mv": 5, "sym_pade": 6, "no_lz1": 7}[name]
         self.check(self.lib.b200k_set_flag(self.handle, flag, int(value)))
 
     def last_kernel(self):
@@ -91,7 +91,7 @@ class Engine:
         (complex kernel) for the last factorisation."""
         w = C.c_int()
         self.check(self.lib.b200k_last_kernel(self.handle, C.byref(w)))
-        return {1: "ldg", 2: "tma", 3: "z", 4: "tma_xl", 5: "tma_mv"}.get(w.value, "none")
+        return {1: "ldg", 2: "tma", 3: "z", 4: "tma_xl", 5: "tma_mv", 6: "tma_xl1"}.get(w.value, "none")
 
     def last_timing(self):
         a, b = C.c_float(), C.c_float()

@@ -88,6 +88,7 @@ struct b200k_context {
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime (no libcuda link dependency)
     int l2hint = -1;        // B200K_FLAG_L2HINT: -1 automatic, 0 never, 1 always evict_first for operator chunks
     long long l2_bytes = 0;
+    int no_lz1 = 0;         // B200K_FLAG_NO_LZ1: two-reduction Lanczos step on the short-window instance (A/B, tests)
     int sym_pade = 0;       // B200K_FLAG_SYM_PADE: device small exponential of a Lanczos H by Pade instead of Chebyshev
     int host_smallexp = 0;  // B200K_SMALLEXP=host: one-shot / batched expv do the small exponential on the host
     DevBuf tdev, errdev;
@@ -138,14 +139,16 @@ struct b200k_comm {
     void *local = nullptr;
     void *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool connected = false;
-    unsigned bar_base = 0;  // local arrivals accumulated by all previous launches (identical on every rank)
-    unsigned seq_base = 0;  // team barriers passed by all previous launches
+    unsigned seq_upper = 0;  // upper bound of the packet sequence numbers consumed so far (exhaustion check only; the
+                             // exact barrier target / sequence number are carried on the device, see state())
+    // {sequence number, barrier target} of the next launch, at byte 512 of the header (written by the kernels)
+    unsigned *state() const { return reinterpret_cast<unsigned *>(reinterpret_cast<char *>(local) + 512); }
     // layout of each rank's buffer: [header: barrier counter @0, LL packet inbox @1024: 2 x (MAXCOL+1) x 8 x 16 B,
     // local packet inbox of the XL instance]
-    // [part 2*MAXCOL*cpad][partn 4*cpad][xbuf 2*xlen] doubles
+    // [part 2*MAXCOL*cpad][partn 4*cpad][xbuf 4*xlen] doubles (four gather buffers: the one-reduction Lanczos step)
     static constexpr size_t PKT_BYTES = (size_t)2 * (MAXCOL + 1) * 8 * 16;
     // + this GPU's own packet inbox of the short-window instance: [2 parities][LLQ quantities][CPAD source CTAs]
-    static constexpr size_t LLLOC_BYTES = (size_t)2 * LLQ * CPAD * 16;
+    static constexpr size_t LLLOC_BYTES = (size_t)2 * LLLOCQ * CPAD * 16;
     static constexpr size_t HDR = 1024 + PKT_BYTES + LLLOC_BYTES;
     uint4 *llloc() const { return reinterpret_cast<uint4 *>(reinterpret_cast<char *>(local) + 1024 + PKT_BYTES); }
     unsigned *bar_of(int r) const { return reinterpret_cast<unsigned *>(peer[r]); }
@@ -159,6 +162,7 @@ struct b200k_operator {
     b200k_comm *comm = nullptr;  // row-sharded operator
     long long nhalo = 0;
     DevBuf send_row, send_peer, send_pos, send_ofs;
+    int send_ofs_C = -1, send_ofs_slice = -1;  // geometry the uploaded send_ofs table was built for
     std::vector<int> send_row_host;
     b200k_context *ctx = nullptr;  // creating handle (NOT dereferenced on destroy: it may already be gone)
     int device = 0;
@@ -305,7 +309,6 @@ struct KrylovCall {
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-void account_sharded(b200k_context *h, b200k_comm *cm, const KrylovCall &c, bool ran, int js, int je, int nreorth);
 
 // Launch the persistent kernel; results land in h->Hd / h->scal / h->stat (device), ldhd = m + 1.
 int launch_krylov(b200k_context *h, const KrylovCall &c) {
@@ -362,7 +365,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
     P.vec2 = vec2 ? 1 : 0;
 
     const int nt = c.g.nteams;
-    CK(h, h->xbuf.ensure((size_t)nt * 2 * P.xlen * 8));
+    CK(h, h->xbuf.ensure((size_t)nt * 4 * P.xlen * 8));  // (four gather buffers per team: one-reduction Lanczos)
     CK(h, h->part.ensure((size_t)nt * 2 * MAXCOL * CPAD * 8));
     CK(h, h->partn.ensure((size_t)nt * 4 * CPAD * 8));
     CK(h, h->bar.ensure((size_t)nt * 4));
@@ -397,7 +400,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
         if (!vec2 || h->force_ldg || c.nprob != 1 || c.g.nteams != 1)
             return fail(h, B200K_EUNSUPPORTED, "row-sharded operators need even nloc/ldv, 16-byte aligned vectors, one problem");
         if (n + op->nhalo + c.p > cm->xlen) return fail(h, B200K_EDIM, "communicator gather buffer (xlen) too small");
-        if (cm->seq_base > 0xf0000000u)  // packet sequence numbers are never reused: ~7e7 factorisations of 30 steps
+        if (cm->seq_upper > 0xf0000000u)  // packet sequence numbers are never reused: ~1.6e7 factorisations of 30 steps
             return fail(h, B200K_ECOMM, "communicator sequence numbers exhausted: destroy and re-create the communicator");
         P.nranks = cm->nranks;
         P.myrank = cm->rank;
@@ -411,23 +414,31 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
             P.peer_pkt[r] = cm->pkt_of(r);
             P.peer_xbuf[r] = cm->xbuf_of(r);
         }
-        // halo push ranges per CTA slice
-        std::vector<int> ofs(c.g.C + 1, 0);
-        const std::vector<int> &sr = op->send_row_host;
-        for (int q = 0; q <= c.g.C; ++q) {
-            const long long bound = std::min<long long>(n, (long long)q * c.g.slice);
-            ofs[q] = (int)(std::lower_bound(sr.begin(), sr.end(), (int)bound) - sr.begin());
+        // halo push ranges per CTA slice (depend on the geometry only: uploaded once per (operator, team size, slice))
+        if (op->send_ofs_C != c.g.C || op->send_ofs_slice != c.g.slice) {
+            std::vector<int> ofs(c.g.C + 1, 0);
+            const std::vector<int> &sr = op->send_row_host;
+            for (int q = 0; q <= c.g.C; ++q) {
+                const long long bound = std::min<long long>(n, (long long)q * c.g.slice);
+                ofs[q] = (int)(std::lower_bound(sr.begin(), sr.end(), (int)bound) - sr.begin());
+            }
+            ofs[c.g.C] = (int)sr.size();
+            CK(h, cudaStreamSynchronize(h->stream));  // (an earlier launch may still read the old table)
+            CK(h, op->send_ofs.ensure((size_t)(c.g.C + 1) * 4));
+            CK(h, cudaMemcpyAsync(op->send_ofs.p, ofs.data(), (size_t)(c.g.C + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+            CK(h, cudaStreamSynchronize(h->stream));  // ofs is a stack vector
+            op->send_ofs_C = c.g.C;
+            op->send_ofs_slice = c.g.slice;
         }
-        ofs[c.g.C] = (int)sr.size();
-        CK(h, op->send_ofs.ensure((size_t)(c.g.C + 1) * 4));
-        CK(h, cudaMemcpyAsync(op->send_ofs.p, ofs.data(), (size_t)(c.g.C + 1) * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));  // ofs is a stack vector
         P.send_row = op->send_row.as<int>();
         P.send_peer = op->send_peer.as<int>();
         P.send_pos = op->send_pos.as<int>();
         P.send_ofs = op->send_ofs.as<int>();
-        bar_base = cm->bar_base;
-        P.seq_base = cm->seq_base;
+        P.comm_state = cm->state();
+        P.llloc = cm->llloc();  // level-1 packet inbox of the two-level all-reduce (both instances)
+        // (upper bound of the sequence numbers used so far: <= 2 reductions per step + 2 per re-orthogonalised step
+        //  + prologue, for the fast and the SAFE instance)
+        cm->seq_upper += 8u * (unsigned)(c.m + 2);
     } else {
         CK(h, cudaMemsetAsync(P.bar, 0, (size_t)nt * 4, h->stream));
     }
@@ -443,6 +454,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
     std::memset(&tmapA, 0, sizeof(tmapA));
     const void *kern = (const void *)krylov_persistent_kernel;
     const void *kern_safe = nullptr;
+    bool lz1 = false;
     int threads = NT;
     if (vec2 && !h->force_ldg) {
         const size_t fixed = sizeof(SmemTma);
@@ -550,6 +562,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
             const bool aug = c.p > 0;
             // Arnoldi / IOP on the general instance: the fast kernel hands over to the SAFE instance (second
             // Gram-Schmidt pass) at the first step whose re-orthogonalisation test fires
+#if !defined(B200K_NO_DGKS) && !defined(B200K_NO_SAFE_LAUNCH)  // (A/B builds only)
             if (!xl && !c.lanczos) {
                 switch (P.op_kind) {
                     case OP_CSR_STREAM: kern_safe = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, false, 8, true> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, false, 8, true>; break;
@@ -557,9 +570,14 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
                     default: kern_safe = aug ? (const void *)krylov_tma_kernel<OP_DENSE, true, false, 8, true> : (const void *)krylov_tma_kernel<OP_DENSE, false, false, 8, true>; break;
                 }
             }
+#endif
             switch (P.op_kind) {
                 case OP_CSR_STREAM:
-                    if (xl && op->max_row_nnz <= 5) kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5>;
+                    if (xl && c.lanczos && !h->no_lz1) {  // one-reduction Lanczos step
+                        if (op->max_row_nnz <= 5) kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5, false, true> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5, false, true>;
+                        else kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 8, false, true> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 8, false, true>;
+                        lz1 = true;
+                    } else if (xl && op->max_row_nnz <= 5) kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5>;
                     else if (xl) kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 8> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 8>;
                     else kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, false> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, false>;
                     break;
@@ -568,7 +586,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
             }
         }
         threads = NT2;
-        h->last_kernel = xl ? 4 : 2;
+        h->last_kernel = lz1 ? 6 : (xl ? 4 : 2);
         h->last_xl = xl ? 1 : 0;
     } else {
         h->last_kernel = 1;
@@ -578,34 +596,13 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
     void *args[] = {(void *)&P, (void *)&tmapA};
     CK(h, cudaLaunchCooperativeKernel(kern, dim3(c.g.C * c.g.nteams), dim3(threads), args, smem, h->stream));
     h->launches += 1;
-    if (cm) {
-        // Row-sharded: the barrier counters / packet sequence numbers of the communicator are never reset, so what the
-        // launch consumed (data dependent: breakdown, hand-over step) is read back before anything else is launched.
-        CK(h, h->stath.ensure(16));
-        CK(h, h->scalh.ensure(32));
-        CK(h, cudaMemcpyAsync(h->stath.p, h->stat.p, 16, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(h->scalh.p, h->scal.p, 8, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));
-        const int *st = h->stath.as<int>();
-        const bool ran = c.j0 != 0 || h->scalh.as<double>()[0] != 0.0;
-        const int js = c.j0 == 0 ? 1 : c.j0;
-        const int redo = (kern_safe && ran) ? st[3] : 0;
-        account_sharded(h, cm, c, ran, js, redo ? redo : st[0], 0);
-        if (redo) {
-            KrylovParams P2 = P;
-            P2.j0 = redo;
-            P2.j0_from_stat = 0;
-            P2.bar_base = cm->bar_base;
-            P2.seq_base = cm->seq_base;
-            void *args2[] = {(void *)&P2, (void *)&tmapA};
-            CK(h, cudaLaunchCooperativeKernel(kern_safe, dim3(c.g.C * c.g.nteams), dim3(threads), args2, smem, h->stream));
-            h->launches += 1;
-            CK(h, cudaMemcpyAsync(h->stath.p, h->stat.p, 16, cudaMemcpyDeviceToHost, h->stream));
-            CK(h, cudaStreamSynchronize(h->stream));
-            KrylovCall c2 = c;
-            c2.j0 = redo;
-            account_sharded(h, cm, c2, true, redo, st[0], st[2]);
-        }
+    if (kern_safe && cm) {
+        // Row-sharded: same hand-over; barrier target / sequence number travel in the communicator buffer on the device
+        KrylovParams P2 = P;
+        P2.j0_from_stat = 1;
+        void *args2[] = {(void *)&P2, (void *)&tmapA};
+        CK(h, cudaLaunchCooperativeKernel(kern_safe, dim3(c.g.C * c.g.nteams), dim3(threads), args2, smem, h->stream));
+        h->launches += 1;
     } else if (kern_safe) {
         // One GPU: the SAFE instance is always queued behind the fast one and reads per problem where to resume
         // (nowhere, normally: 148 CTAs read one word and exit -- a few microseconds, no host round trip).
@@ -726,29 +723,6 @@ int launch_krylov_mv(b200k_context *h, const KrylovCall &c, const BatchPlan &pla
     h->last_kernel = 5;
     h->last_xl = 0;
     return B200K_OK;
-}
-
-// Row-sharded launches never reset the barrier counter / sequence number of the communicator: account for what the
-// launch consumed.  Steps js..je ran; every step passes two reductions (sequence numbers), but the XL instance
-// replaces the counter barrier by packet all-reduces for the norm and for inner-product windows of <= LLQ columns.
-void account_sharded(b200k_context *h, b200k_comm *cm, const KrylovCall &c, bool ran, int js, int je, int nreorth) {
-    unsigned nseq = 1, nbar = 1;  // firststep! (or the halo staging barrier of a resumed factorisation)
-    if (ran) {
-        nseq += 2u * (unsigned)nreorth;  // a re-orthogonalised step passes two more counter-barrier reductions
-        nbar += 2u * (unsigned)nreorth;
-        const int iopw = c.iop > 0 ? c.iop : c.m;
-        for (int j = js; j <= je; ++j) {
-            nseq += 2u;
-            if (!h->last_xl) {
-                nbar += 2u;
-            } else {
-                const int nc = c.lanczos ? 1 : std::min(j, iopw);
-                if (nc > LLQ) nbar += 1u;
-            }
-        }
-    }
-    cm->bar_base += nbar * (unsigned)c.g.C;
-    cm->seq_base += nseq;
 }
 
 // Copy H / beta / (m, breakdown) of nprob problems to pinned host memory and wait.
@@ -1125,6 +1099,8 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
                                  (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5>,
                                  (const void *)krylov_tma_kernel<OP_CSR_WARP, false, false>, (const void *)krylov_tma_kernel<OP_CSR_WARP, true, false>,
                                  (const void *)krylov_tma_kernel<OP_DENSE, false, false>, (const void *)krylov_tma_kernel<OP_DENSE, true, false>,
+                                 (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 8, false, true>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 8, false, true>,
+                                 (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5, false, true>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5, false, true>,
                                  (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, false, 8, true>, (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, false, 8, true>,
                                  (const void *)krylov_tma_kernel<OP_CSR_WARP, false, false, 8, true>, (const void *)krylov_tma_kernel<OP_CSR_WARP, true, false, 8, true>,
                                  (const void *)krylov_tma_kernel<OP_DENSE, false, false, 8, true>, (const void *)krylov_tma_kernel<OP_DENSE, true, false, 8, true>};
@@ -1220,6 +1196,7 @@ int b200k_set_flag(b200k_handle_t h, int flag, int value) {
     else if (flag == B200K_FLAG_NO_MV) h->no_mv = value == 2 ? 2 : (value ? 1 : 0);
     else if (flag == B200K_FLAG_L2HINT) h->l2hint = value < 0 ? -1 : (value ? 1 : 0);
     else if (flag == B200K_FLAG_SYM_PADE) h->sym_pade = value ? 1 : 0;
+    else if (flag == B200K_FLAG_NO_LZ1) h->no_lz1 = value ? 1 : 0;
     else return fail(h, B200K_EARG, "unknown flag");
     return B200K_OK;
 }
@@ -1484,7 +1461,7 @@ int b200k_expv(b200k_handle_t h, b200k_op_t op, double t, const double *b, const
         if (st) return st;
         st = launch_smallexp_project(h, 1, o.m, c.lanczos, &t, h->V.as<double>(), ldv, 0, op->n, w, op->n, 0);
         if (st) return st;
-        if (op->comm || m_out || breakdown || beta_out) {
+        if (m_out || breakdown || beta_out) {
             st = fetch_krylov(h, 1, o.m);
             if (st) return st;
             beta = h->scalh.as<double>()[0];
@@ -2650,7 +2627,7 @@ int b200k_comm_create(b200k_handle_t h, int rank, int nranks, int64_t xlen, unsi
     cm->nranks = nranks;
     cm->xlen = round_up(xlen, 16);
     cm->cpad = (int)round_up((long long)h->max_ctas * nranks, 32);
-    cm->bytes = b200k_comm::HDR + sizeof(double) * ((size_t)2 * MAXCOL * cm->cpad + (size_t)4 * cm->cpad + (size_t)2 * cm->xlen);
+    cm->bytes = b200k_comm::HDR + sizeof(double) * ((size_t)2 * MAXCOL * cm->cpad + (size_t)4 * cm->cpad + (size_t)4 * cm->xlen);
     cudaError_t e = cudaMalloc(&cm->local, cm->bytes);
     if (e == cudaSuccess) e = cudaMemset(cm->local, 0, cm->bytes);
     cudaIpcMemHandle_t hd;

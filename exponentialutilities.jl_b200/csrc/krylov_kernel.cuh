@@ -109,6 +109,7 @@ struct KrylovParams {
     int myrank;
     unsigned bar_base;      // local barrier arrivals accumulated by earlier launches (multi-GPU counters are never reset)
     unsigned seq_base;      // team barriers passed by earlier launches
+    unsigned *comm_state;   // row-sharded: {sequence number, barrier target} carried from launch to launch on the device
     uint4 *peer_pkt[8];     // per GPU: LL inbox [2 parities][MAXCOL + 1 quantities][8 source ranks] of {lo, seq, hi, seq}
     int nhalo;              // remote x entries this GPU gathers (appended after the n local entries)
     int cpad;               // row length of the partial-sum tables: round_up(team_size * nranks, 32)

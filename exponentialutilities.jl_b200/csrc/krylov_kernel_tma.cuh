@@ -43,6 +43,7 @@ struct __align__(128) SmemTma {
     double redn[NW];
     double wtail[MAXP];
     double xtail[MAXP];
+    double ptail[MAXP];  // one-reduction Lanczos: tail rows of the previous vector
     int chunk_a0[MAXCH2];
     int chunk_cnt[MAXCH2];
     int slot_a0[MAXSLOT];
@@ -463,8 +464,9 @@ __device__ __forceinline__ double ll_poll_acquire_sys(const uint4 *p, unsigned s
     } while (f1 != seq || f2 != seq);
     return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
+constexpr int LLLOCQ = MAXCOL + 1;  // quantities the per-GPU level-1 inbox holds per parity (full Arnoldi windows)
 __device__ __forceinline__ uint4 *llloc_slot(const KrylovParams &P, unsigned seq, int ci, int src) {
-    return P.llloc + (((long long)(seq & 1u)) * LLQ + ci) * CPAD + src;
+    return P.llloc + (((long long)(seq & 1u)) * LLLOCQ + ci) * CPAD + src;
 }
 // Called by ALL lanes of warp 0 with the CTA partial v of quantity ci.
 __device__ __forceinline__ void shard_publish_warp(const KrylovParams &P, const Team &tm, unsigned seq, int ci, double v,
@@ -480,8 +482,7 @@ __device__ void shard_collect(const KrylovParams &P, Cons &cx, const Team &tm, i
     cx.seq += 1u;
     const unsigned seq = cx.seq;
     const long long pbase = (long long)(seq & 1u) * (MAXCOL + 1) * 8;
-    if (tm.rank < ncols) {  // owner of quantity ci = tm.rank (uniform for the CTA)
-        const int ci = tm.rank;
+    for (int ci = tm.rank; ci < ncols; ci += tm.C) {  // quantities this CTA owns (uniform for the CTA)
         for (int r = cx.tid; r < tm.C; r += NTC) {
             const uint4 *slot = llloc_slot(P, seq, ci, r);
             S->llv[0][r] = ordered ? ll_poll_acquire(slot, seq) : ll_poll(slot, seq);
@@ -494,6 +495,7 @@ __device__ void shard_collect(const KrylovParams &P, Cons &cx, const Team &tm, i
             if (ordered) asm volatile("fence.acq_rel.sys;" ::: "memory");
             if (cx.lane < P.nranks) ll_push(P.peer_pkt[cx.lane] + pbase + (long long)ci * 8 + P.myrank, s, seq);
         }
+        if (ci + tm.C < ncols) consumer_sync();  // the staging row is reused by the next owned quantity
     }
     for (int ci = cx.warp; ci < ncols; ci += NW) {
         double v = 0.0;
@@ -515,6 +517,26 @@ __device__ __forceinline__ void push_halo(const KrylovParams &P, Cons &cx, const
     const int e1 = P.send_ofs[tm.rank + 1];
     for (int e = P.send_ofs[tm.rank] + cx.tid; e < e1; e += NTC)
         P.peer_xbuf[P.send_peer[e]][xoff + P.send_pos[e]] = cx.ws[P.send_row[e] - G.r0];
+}
+
+// Row-sharded norm-type reduction of the general instance: block sum of `v`, halo push of the finished w slice, then a
+// two-level packet all-reduce that also publishes the gather-buffer stores and the pushed rows (replaces counter
+// barrier + __threadfence_system; the same scheme the short-window instance uses).  Result in out[0].
+__device__ void shard_norm_reduce(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, double v,
+                                  long long xoff, double *out) {
+    v = warp_sum(v);
+    if (cx.lane == 0) cx.S->redn[cx.warp] = v;
+    consumer_sync();  // (also: the whole w slice of this CTA is in place)
+    const bool pushed = P.send_ofs[tm.rank + 1] > P.send_ofs[tm.rank];
+    push_halo(P, cx, G, tm, xoff);
+    consumer_sync();
+    if (cx.warp == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += cx.S->redn[w];
+        shard_publish_warp(P, tm, cx.seq + 1u, 0, s, cx.lane, true, pushed);
+    }
+    shard_collect(P, cx, tm, 1, out, true);
 }
 
 // XL mat-vec (CSR stream): entries whose column lies in this CTA's own row slice are gathered from the shared-memory
@@ -851,7 +873,8 @@ __device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) s += S->red[buf][w][tid];
-            P.peer_part[P.myrank][part_off + (long long)(cb - lo + tid) * P.cpad + tm.rank] = s;
+            if (P.nranks > 1) ll_push(llloc_slot(P, cx.seq + 1u, cb - lo + tid, tm.rank), s, cx.seq + 1u);  // level-1 packet
+            else P.peer_part[P.myrank][part_off + (long long)(cb - lo + tid) * P.cpad + tm.rank] = s;
         }
     }
 }
@@ -927,7 +950,7 @@ constexpr double REORTH_ETA2 = 0.0625;  // eta = 1/4 (squared norms are compared
 // out-of-line call would pin those structs in local memory for the whole hot loop.)
 // Second-pass inner products <v_c, w> for c = lo..hi with direct loads of the CTA's basis slice.
 __device__ __noinline__ void reorth_dots_c(const KrylovParams &P, SmemTma *S, const double *ws, int r0, int nrows, int rank,
-                                           const double *V, int lo, int hi, long long part_off, bool aug) {
+                                           const double *V, int lo, int hi, long long part_off, bool aug, unsigned seq_next) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double2 *ws2 = reinterpret_cast<const double2 *>(ws);
     const int units = nrows >> 1;
@@ -962,7 +985,8 @@ __device__ __noinline__ void reorth_dots_c(const KrylovParams &P, SmemTma *S, co
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) s += S->red[buf][w][tid];
-            P.peer_part[P.myrank][part_off + (long long)(cb - lo + tid) * P.cpad + rank] = s;
+            if (P.nranks > 1) ll_push(llloc_slot(P, seq_next, cb - lo + tid, rank), s, seq_next);
+            else P.peer_part[P.myrank][part_off + (long long)(cb - lo + tid) * P.cpad + rank] = s;
         }
     }
 }
@@ -1038,16 +1062,20 @@ __device__ __noinline__ void reorth_step_c(const KrylovParams &P, unsigned targe
     const double *V = P.V + (long long)prob * P.V_stride;
     double *Hcol = P.Hd + (long long)prob * P.H_stride + (long long)jc * P.ldh + lo;
     const bool sharded = P.nranks > 1;
-    double *h2 = &S->llv[0][0];  // (packet scratch of the XL instance: unused by this instance)
+    double *h2 = &S->llv[1][0];  // (rows 1..3 of the packet staging area: 480 doubles; row 0 is shard_collect's)
     consumer_sync();
-    reorth_dots_c(P, S, cx.ws, G.r0, G.nrows, tm.rank, V, lo, hi, part, aug);
-    team_reduce_c(P, cx, tm, P.peer_part[P.myrank] + part, nc, h2, false);
+    reorth_dots_c(P, S, cx.ws, G.r0, G.nrows, tm.rank, V, lo, hi, part, aug, cx.seq + 1u);
+    if (sharded) shard_collect(P, cx, tm, nc, h2, false);
+    else team_reduce_c(P, cx, tm, P.peer_part[P.myrank] + part, nc, h2, false);
     if (tm.rank == 0)
         for (int ci = cx.tid; ci < nc; ci += NTC) Hcol[ci] = S->hs[ci] + h2[ci];
     const double nrm2 = reorth_update_c(P, S, cx.ws, G.r0, G.nrows, tm.rank, V, lo, hi, h2, xout, aug);
-    block_sum_to_c(P, cx, nrm2, partn + tm.rank);
-    push_halo(P, cx, G, tm, xoff);
-    team_reduce_c(P, cx, tm, P.peer_partn[P.myrank] + partn, 1, S->bc, sharded);
+    if (sharded) {
+        shard_norm_reduce(P, cx, G, tm, nrm2, xoff, S->bc);
+    } else {
+        block_sum_to_c(P, cx, nrm2, partn + tm.rank);
+        team_reduce_c(P, cx, tm, P.peer_partn[P.myrank] + partn, 1, S->bc, false);
+    }
 }
 
 // One problem on the consumer side.  Mirrors krylov_body<2> of krylov_kernel.cuh.
@@ -1093,9 +1121,12 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
             if (P.myrank == 0) nrm = fma(bt, bt, nrm);
         }
         const long long pslot = partn0 + (long long)(2 + (nlocal & 1)) * P.cpad;
-        block_sum_to_c(P, cx, nrm, pslot + tm.rank);
-        push_halo(P, cx, G, tm, xoff0);
-        team_reduce_c(P, cx, tm, lpartn + pslot, 1, S->bc, sharded);
+        if (sharded) {
+            shard_norm_reduce(P, cx, G, tm, nrm, xoff0, S->bc);
+        } else {
+            block_sum_to_c(P, cx, nrm, pslot + tm.rank);
+            team_reduce_c(P, cx, tm, lpartn + pslot, 1, S->bc, false);
+        }
         const double beta = sqrt(S->bc[0]);
         if (tm.rank == 0 && tid == 0) P.scal[prob * 4] = beta;
         if (beta == 0.0) {
@@ -1140,9 +1171,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
                 reinterpret_cast<double2 *>(xb0 + G.r0)[i] = v2;
             }
             if (p > 0 && tm.rank == 0 && tid < p) xb0[xt + tid] = vj[n + tid];
-            block_sum_to_c(P, cx, 0.0, partn0 + 2LL * P.cpad + tm.rank);  // (has the CTA barrier the push needs)
-            push_halo(P, cx, G, tm, xoff0);
-            team_reduce_c(P, cx, tm, lpartn + partn0 + 2LL * P.cpad, 1, S->bc, true);  // every GPU's halo is in place
+            shard_norm_reduce(P, cx, G, tm, 0.0, xoff0, S->bc);  // every GPU's halo is in place afterwards
             xsrc = xb0;
         } else {
             xsrc = vj;
@@ -1176,36 +1205,35 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
         dots_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, hi, part);
         PT_MARK(blockIdx.x, j, 2);
-        team_reduce_c(P, cx, tm, lpart + part, nc, S->hs + (lo - ulo), false);
+        if (sharded) shard_collect(P, cx, tm, nc, S->hs + (lo - ulo), false);
+        else team_reduce_c(P, cx, tm, lpart + part, nc, S->hs + (lo - ulo), false);
         PT_MARK(blockIdx.x, j, 3);
         if (tm.rank == 0)
             for (int ci = tid; ci < nc; ci += NTC) Hd[(long long)jc * ldh + lo + ci] = S->hs[lo + ci - ulo];
         if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = beta_prev;
+        // Re-orthogonalisation test: ||w_before||^2 = ||h||^2 + ||w_after||^2 for an orthonormal window (Pythagoras), so
+        // no extra reduction is needed.  One warp sums the coefficients now and parks the result in shared memory;
+        // nothing is carried in registers through the update phase (doing this in every thread after the norm
+        // reduction cost 4.5 % of the C2 kernel through register pressure, profiles/r2_dgks_ab.log).
+        if (dgks && cx.warp == 1) {
+            double q = 0.0;
+            for (int ci = cx.lane; ci < nc; ci += 32) q = fma(S->hs[ci], S->hs[ci], q);
+            q = warp_sum(q);
+            if (cx.lane == 0) S->bc[1] = q;
+        }
         consumer_sync();
 
         const double nrm = update_phase_c<OPK, AUG>(P, cx, G, tm, V, ulo, hi, xout);
         PT_MARK(blockIdx.x, j, 4);
-        block_sum_to_c(P, cx, nrm, partn + tm.rank);
-        push_halo(P, cx, G, tm, xoff);  // after block_sum's CTA barrier: the whole w slice is in place
-        team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, sharded);
+        if (sharded) {
+            shard_norm_reduce(P, cx, G, tm, nrm, xoff, S->bc);
+        } else {
+            block_sum_to_c(P, cx, nrm, partn + tm.rank);
+            team_reduce_c(P, cx, tm, lpartn + partn, 1, S->bc, false);
+        }
         PT_MARK(blockIdx.x, j, 5);
 
-        // ||w_before||^2 = ||h||^2 + ||w_after||^2 for an orthonormal window (Pythagoras): the test needs no extra
-        // reduction; every thread sums the nc <= 255 coefficients itself (shared-memory broadcast reads)
-        double hsq = 0.0;
-        if (dgks) {
-            double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;  // (four chains: the sum sits on every thread's critical path)
-            int ci = 0;
-            for (; ci + 3 < nc; ci += 4) {
-                h0 = fma(S->hs[ci], S->hs[ci], h0);
-                h1 = fma(S->hs[ci + 1], S->hs[ci + 1], h1);
-                h2 = fma(S->hs[ci + 2], S->hs[ci + 2], h2);
-                h3 = fma(S->hs[ci + 3], S->hs[ci + 3], h3);
-            }
-            for (; ci < nc; ++ci) h0 = fma(S->hs[ci], S->hs[ci], h0);
-            hsq = (h0 + h1) + (h2 + h3);
-        }
-        if (dgks && S->bc[0] < REORTH_ETA2 * (hsq + S->bc[0])) {
+        if (dgks && S->bc[0] < REORTH_ETA2 * (S->bc[1] + S->bc[0])) {
             // every CTA of every rank takes the same decision: the reduced values are bitwise identical everywhere
             // (NaN never triggers it)
             if (SAFE) {  // second classical Gram-Schmidt pass, out of line; two more team reductions
@@ -1515,7 +1543,7 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
 
         double beta;
         {
-            const bool use_ll = nc <= LLQ;  // packet all-reduce (one GPU: ll_*, row-sharded: shard_*)
+            const bool use_ll = sharded || nc <= LLQ;  // packet all-reduce (one GPU: ll_*, <= LLQ columns; row-sharded: shard_*, any)
             // <v_jc, w> was accumulated by the mat-vec (unscaled); its block reduction is also the barrier that
             // completes the w slice.  Columns lo..jc-1 come through the ring as before.
             {
@@ -1628,9 +1656,364 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
     }
 }
 
+// =====================================================================================================================
+// One-reduction Lanczos step (short-window instance, Hermitian operators; reference: lanczos_step!, arnoldi.jl:388-403)
+// =====================================================================================================================
+// The two-reduction step above waits for an all-reduce twice: alpha = <v_j, A v_j>, then ||w||^2 after the update --
+// each a full latency chain over the team (4-6 k cycles on one GPU, 7-8 us over NVLink), and the second one is also the
+// barrier that publishes the updated vector to the CTAs that gather it.  Here ONE all-reduce per step carries
+//     S = <X_j, w'>_pre-fold (-> alpha),   Q = ||w'||^2,   G = <X_j, w'>      with  w' = A v_j - beta_{j-1} v_{j-1},
+// and ||w' - alpha v_j||^2 = Q - 2 alpha g + alpha^2 gives beta_j without a second pass (g = xscale * G; in exact
+// arithmetic g = alpha; a cancellation guard -- beta^2 < Q / 100 -- falls back to an explicit norm reduction, which is
+// exactly where breakdown decisions are taken).  What the second reduction used to publish is reconstructed by the
+// readers instead: w' is written to a gather buffer DURING the mat-vec (published by the step's single all-reduce),
+// and a CTA that needs entry c of the next vector outside its own slice forms
+//     X_{j+1}[c] = w'_j[c] - (alpha_j xscale_j) X_j[c]
+// from two published arrays (GW = w' and GX = X, both double buffered by step parity; X_{j+1} is stored to GX during
+// the local update and becomes visible with the NEXT all-reduce, one step before anyone needs it).  For stencil-like
+// operators only the few out-of-slice entries pay the second load.  The p augmented tail rows of kiops are kept
+// redundantly by every CTA in shared memory (every CTA applies the same update with the same reduced scalars).
+template <bool AUG, int GW>
+__device__ void matvec_xl1(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *gw, const double *gx,
+                           double gam, double xscale, bool learn, bool fold, double foldc, double *gwout,
+                           double &sacc, double &qacc, double &gacc) {
+    SmemTma *S = cx.S;
+    const int tid = cx.tid;
+    const int p = AUG ? P.p : 0;
+    const uint32_t ws_a = cx.ws_a, xin_a = cx.xin_a;
+    const uint32_t xl_a = xin_a - 8u * (uint32_t)G.r0;  // shared address of x(column) for own-slice columns
+    const int nnz_cap = P.nnz_cap;
+    double s1 = 0.0, q1 = 0.0, g1 = 0.0;
+    for (int c = 0; c < G.nch; ++c) {
+        const int rl = c * P.ch_rows + tid;
+        const bool active = tid < P.ch_rows && rl < G.nrows;
+        const bool fast = !learn && c < MAXCH2 && S->chunk_local[c] != 0;
+        cx.wait_full();
+        bool loc = true;
+        if (active) {
+            const unsigned char *base = cx.rg.ptr();
+            const double *vs = reinterpret_cast<const double *>(base);
+            const int *cs = reinterpret_cast<const int *>(base + (size_t)nnz_cap * 8);
+            const int *rp = reinterpret_cast<const int *>(base + (size_t)nnz_cap * 12);
+            const int a0 = S->slot_a0[cx.rg.slot];
+            const int e0 = rp[tid] - a0, e1 = rp[tid + 1] - a0;
+            double sum = 0.0;
+            if (fast) {
+#pragma unroll 1
+                for (int eb = e0; eb < e1; eb += GW) {
+                    double av[GW], xv[GW];
+#pragma unroll
+                    for (int u = 0; u < GW; ++u) {
+                        const bool ok = eb + u < e1;
+                        av[u] = ok ? vs[eb + u] : 0.0;
+                        xv[u] = 0.0;
+                        if (ok) xv[u] = lds1(xl_a + 8u * (uint32_t)cs[eb + u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < GW; ++u) sum = fma(av[u], xv[u], sum);
+                }
+            } else {
+#pragma unroll 1
+                for (int eb = e0; eb < e1; eb += GW) {
+                    double av[GW], xv[GW];
+#pragma unroll
+                    for (int u = 0; u < GW; ++u) {
+                        const bool ok = eb + u < e1;
+                        av[u] = ok ? vs[eb + u] : 0.0;
+                        xv[u] = 0.0;
+                        if (ok) {
+                            const int col = cs[eb + u];
+                            const unsigned lc = (unsigned)(col - G.r0);
+                            const bool here = lc < (unsigned)G.nrows;
+                            loc = loc && here;
+                            if (here) xv[u] = lds1(xin_a + 8u * lc);
+                            else xv[u] = fma(-gam, gx[col], gw[col]);  // X_j[col] rebuilt from the two published arrays
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < GW; ++u) sum = fma(av[u], xv[u], sum);
+                }
+            }
+            if (p > 0) {
+                const double *brow = P.Bm + (G.r0 + rl);
+                for (int k = 0; k < p; ++k) sum = fma(brow[(long long)k * P.ldb], S->xtail[k], sum);
+            }
+            double wv = sum * xscale;
+            const double xr = lds1(xin_a + 8u * (uint32_t)rl);
+            s1 = fma(xr, wv, s1);
+            if (fold) wv = fma(-foldc, lds1(ws_a + 8u * (uint32_t)rl), wv);
+            q1 = fma(wv, wv, q1);
+            g1 = fma(xr, wv, g1);
+            sts1(ws_a + 8u * (uint32_t)rl, wv);
+            gwout[G.r0 + rl] = wv;
+        }
+        if (learn && c < MAXCH2) {
+            if (!__all_sync(0xffffffffu, loc) && cx.lane == 0) S->chunk_local[c] = 0;
+        }
+        cx.release();
+    }
+    sacc = s1;
+    qacc = q1;
+    gacc = g1;
+}
+
+template <int OPK, bool AUG, int GW>
+__device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaGeom &G, Team &tm, int prob, int nlocal,
+                                     double *xbase, long long xoffbase, long long partn0) {
+    SmemTma *S = cx.S;
+    const int tid = cx.tid;
+    const int n = P.n, p = AUG ? P.p : 0;
+    double *V = P.V + (long long)prob * P.V_stride;
+    double *Hd = P.Hd + (long long)prob * P.H_stride;
+    const double *b = P.b + (long long)prob * P.b_stride;
+    const long long ldv = P.ldv;
+    const int ldh = P.ldh;
+    const int units = G.nrows >> 1;
+    const bool sharded = P.nranks > 1;
+    const double *lpartn = P.peer_partn[P.myrank];
+    const int xt = n + P.nhalo;  // offset of the augmented tail in a gather buffer (only the staging of step 1 uses it)
+    // gather buffers of this team: GW[par] = w' of the step with parity par, GX[par] = X_j with j & 1 == par
+    auto GWb = [&](int par) { return xbase + (long long)par * P.xlen; };
+    auto GXb = [&](int par) { return xbase + (long long)(2 + par) * P.xlen; };
+    auto GWo = [&](int par) { return xoffbase + (long long)par * P.xlen; };
+    auto GXo = [&](int par) { return xoffbase + (long long)(2 + par) * P.xlen; };
+    if (nlocal == 0)
+        for (int c = tid; c < MAXCH2; c += NTC) S->chunk_local[c] = 1;
+
+    // ---- X_1: b (firststep!, arnoldi.jl:230-250 / 257-279) or the normalised first column of a resumed subspace
+    const double *src1;  // out-of-slice entries of X_1 are read from here
+    double xscale;
+    const bool stage = p > 0 || sharded;  // X_1 has to be staged in GX[1] (halo landing zone / tail rows)
+    if (P.j0 == 0) {
+        double nrm = 0.0;
+        for (int i = tid; i < units; i += NTC) {
+            const double2 b2 = reinterpret_cast<const double2 *>(b + G.r0)[i];
+            sts2(cx.xin_a + 16u * (uint32_t)i, b2);
+            if (stage) reinterpret_cast<double2 *>(GXb(1) + G.r0)[i] = b2;
+            nrm = fma(b2.x, b2.x, fma(b2.y, b2.y, nrm));
+        }
+        if (p > 0 && tid < p) {
+            const double bt = P.btail[tid];
+            S->xtail[tid] = bt;
+            if (tm.rank == 0 && P.myrank == 0) nrm = fma(bt, bt, nrm);
+        }
+        const long long pslot = partn0 + (long long)(2 + (nlocal & 1)) * P.cpad;
+        block_sum_to_c(P, cx, nrm, pslot + tm.rank);
+        if (sharded) {
+            double *t = cx.ws; cx.ws = cx.xin; push_halo(P, cx, G, tm, GXo(1)); cx.ws = t;
+        }
+        team_reduce_c(P, cx, tm, lpartn + pslot, 1, S->bc, sharded);
+        const double beta = sqrt(S->bc[0]);
+        if (tm.rank == 0 && tid == 0) P.scal[prob * 4] = beta;
+        if (beta == 0.0) {
+            if (tm.rank == 0 && tid == 0) {
+                P.stat[prob * 4 + 0] = P.m;
+                P.stat[prob * 4 + 1] = 0;
+                P.stat[prob * 4 + 2] = 0;
+                P.stat[prob * 4 + 3] = 0;
+            }
+            return;
+        }
+        src1 = stage ? GXb(1) : b;
+        xscale = 1.0 / beta;
+    } else {
+        const double *vj = V;  // lanczos! restarts at column 1 (it ignores init, arnoldi.jl:480)
+        for (int i = tid; i < units; i += NTC) {
+            const double2 v2 = reinterpret_cast<const double2 *>(vj + G.r0)[i];
+            sts2(cx.xin_a + 16u * (uint32_t)i, v2);
+            if (sharded) reinterpret_cast<double2 *>(GXb(1) + G.r0)[i] = v2;
+        }
+        if (p > 0 && tid < p) S->xtail[tid] = vj[n + tid];
+        if (sharded) {
+            block_sum_to_c(P, cx, 0.0, partn0 + 2LL * P.cpad + tm.rank);  // (has the CTA barrier the push needs)
+            double *t = cx.ws; cx.ws = cx.xin; push_halo(P, cx, G, tm, GXo(1)); cx.ws = t;
+            team_reduce_c(P, cx, tm, lpartn + partn0 + 2LL * P.cpad, 1, S->bc, true);
+            src1 = GXb(1);
+        } else {
+            consumer_sync();
+            src1 = vj;
+        }
+        xscale = 1.0;
+    }
+    (void)xt;
+
+    double beta_prev = 0.0, xscale_prev = 0.0, gam = 0.0, beta = 0.0;
+    int m_out = P.m, breakdown = 0, nfall = 0;
+    const bool lazy_v1 = P.j0 == 0;  // (a resumed first column is already in V)
+    for (int j = 1; j <= P.m; ++j) {
+        const int jc = j - 1;
+        const int par = j & 1, parp = par ^ 1;
+        const bool fold = j > 1;
+        PT_MARK(blockIdx.x, j, 0);
+        // ---- tail rows of w' (every CTA keeps them): (K x)_k = x_{k+1}, last row 0
+        double st = 0.0, qt = 0.0, gt = 0.0;
+        if (p > 0) {
+            consumer_sync();
+            if (tid < p) {
+                double wt = (tid < p - 1) ? S->xtail[tid + 1] * xscale : 0.0;
+                st = S->xtail[tid] * wt;
+                if (fold) wt = fma(-(beta_prev * xscale_prev), S->ptail[tid], wt);
+                qt = wt * wt;
+                gt = S->xtail[tid] * wt;
+                S->wtail[tid] = wt;
+            }
+            if (!(tm.rank == 0 && P.myrank == 0)) st = qt = gt = 0.0;  // counted once
+        }
+        double sacc, qacc, gacc;
+        matvec_xl1<AUG, GW>(P, cx, G, j == 1 ? src1 : GWb(parp), j == 1 ? src1 : GXb(parp), j == 1 ? 0.0 : gam, xscale,
+                            nlocal == 0 && j == 1, fold, beta_prev * xscale_prev, GWb(par), sacc, qacc, gacc);
+        sacc += st;
+        qacc += qt;
+        gacc += gt;
+        PT_MARK(blockIdx.x, j, 1);
+        PT_MARK(blockIdx.x, j, 2);
+        // ---- the step's single all-reduce (release / acquire: publishes the w' stores, the previous update's X stores
+        // and, row-sharded, the halo rows pushed to the peers)
+        {
+            double v0 = warp_sum(sacc), v1 = warp_sum(qacc), v2 = warp_sum(gacc);
+            if (cx.lane == 0) {
+                S->red[0][cx.warp][0] = v0;
+                S->red[0][cx.warp][1] = v1;
+                S->red[0][cx.warp][2] = v2;
+            }
+            consumer_sync();  // (also: the whole w' slice of this CTA is in place)
+            bool pushed = false;
+            if (sharded) {
+                pushed = P.send_ofs[tm.rank + 1] > P.send_ofs[tm.rank];
+                push_halo(P, cx, G, tm, GWo(par));
+                consumer_sync();
+            }
+            if (cx.warp == 0) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    s0 += S->red[0][w][0];
+                    s1 += S->red[0][w][1];
+                    s2 += S->red[0][w][2];
+                }
+                if (!sharded) {
+                    ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 0, s0, cx.lane, true);
+                    ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 1, s1, cx.lane, false);
+                    ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 2, s2, cx.lane, false);
+                } else {
+                    shard_publish_warp(P, tm, cx.seq + 1u, 0, s0, cx.lane, true, pushed);
+                    shard_publish_warp(P, tm, cx.seq + 1u, 1, s1, cx.lane, false, false);
+                    shard_publish_warp(P, tm, cx.seq + 1u, 2, s2, cx.lane, false, false);
+                }
+            }
+        }
+        PT_MARK(blockIdx.x, j, 7);
+        // v_j = X_j * xscale goes to V while the packets fly
+        if (j > 1 || lazy_v1) {
+            double2 *vl2 = reinterpret_cast<double2 *>(V + (long long)jc * ldv + G.r0);
+            const uint32_t xin_a = cx.xin_a;
+            for (int i = tid; i < units; i += NTC) {
+                const double2 x2 = lds2(xin_a + 16u * (uint32_t)i);
+                vl2[i] = make_double2(x2.x * xscale, x2.y * xscale);
+            }
+            if (p > 0 && tm.rank == 0 && tid < p) V[(long long)jc * ldv + n + tid] = S->xtail[tid] * xscale;
+        }
+        PT_MARK(blockIdx.x, j, 8);
+        if (!sharded) ll_collect(P, cx, tm, 3, S->hs, true);
+        else shard_collect(P, cx, tm, 3, S->hs, true);
+        PT_MARK(blockIdx.x, j, 3);
+        const double alpha = S->hs[0] * xscale, Q = S->hs[1], g = S->hs[2] * xscale;
+        double beta2 = (Q - 2.0 * alpha * g) + alpha * alpha;
+        const bool fallback = !(beta2 > 0.01 * Q);  // cancellation (or NaN): take the norm explicitly
+        consumer_sync();  // S->hs is rewritten by the next collect
+        // ---- local update X_{j+1} = w' - alpha v_j (shared memory + GX[(j+1) & 1]); no reduction needed
+        const double coef = alpha * xscale;
+        double nrm = 0.0;
+        {
+            const uint32_t ws_a = cx.ws_a, xin_a = cx.xin_a;
+            double2 *xo2 = reinterpret_cast<double2 *>(GXb(parp) + G.r0);
+            for (int i = tid; i < units; i += NTC) {
+                double2 w2 = lds2(ws_a + 16u * (uint32_t)i);
+                const double2 x2 = lds2(xin_a + 16u * (uint32_t)i);
+                w2.x = fma(-coef, x2.x, w2.x);
+                w2.y = fma(-coef, x2.y, w2.y);
+                sts2(ws_a + 16u * (uint32_t)i, w2);
+                xo2[i] = w2;
+                nrm = fma(w2.x, w2.x, fma(w2.y, w2.y, nrm));
+            }
+        }
+        if (p > 0) {
+            consumer_sync();
+            if (tid < p) {
+                const double nt = fma(-coef, S->xtail[tid], S->wtail[tid]);
+                S->ptail[tid] = S->xtail[tid];
+                S->wtail[tid] = nt;  // X_{j+1} tail (copied to xtail below)
+                if (tm.rank == 0 && P.myrank == 0) nrm = fma(nt, nt, nrm);
+            }
+            consumer_sync();
+            if (tid < p) S->xtail[tid] = S->wtail[tid];
+        }
+        if (sharded) {  // halo rows of X_{j+1}: published by the NEXT step's all-reduce, needed one step after that
+            consumer_sync();
+            push_halo(P, cx, G, tm, GXo(parp));
+        }
+        PT_MARK(blockIdx.x, j, 4);
+        if (fallback) {  // (uniform: every CTA of every rank sees the same reduced values)
+            const double v = warp_sum(nrm);
+            if (cx.lane == 0) S->redn[cx.warp] = v;
+            consumer_sync();
+            if (cx.warp == 0) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) s += S->redn[w];
+                if (!sharded) ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 0, s, cx.lane, false);
+                else shard_publish_warp(P, tm, cx.seq + 1u, 0, s, cx.lane, false, false);
+            }
+            if (!sharded) ll_collect(P, cx, tm, 1, S->bc, false);
+            else shard_collect(P, cx, tm, 1, S->bc, false);
+            beta2 = S->bc[0];
+            ++nfall;
+        }
+        PT_MARK(blockIdx.x, j, 5);
+        beta = sqrt(beta2);
+        if (tm.rank == 0 && tid == 0) {
+            Hd[(long long)jc * ldh + jc] = alpha;
+            Hd[(long long)jc * ldh + jc + 1] = beta;
+        }
+        {  // the new vector becomes the resident one
+            double *t = cx.ws; cx.ws = cx.xin; cx.xin = t;
+            const uint32_t ta = cx.ws_a; cx.ws_a = cx.xin_a; cx.xin_a = ta;
+        }
+        PT_MARK(blockIdx.x, j, 6);
+        gam = coef;
+        xscale_prev = xscale;
+        xscale = 1.0 / beta;
+        beta_prev = beta;
+        if (beta < P.tol) {
+            m_out = j;
+            breakdown = 1;
+        }
+        if (breakdown || j == P.m) {
+            // epilogue: v_{j+1} = X_{j+1} / beta (true division: beta may be tiny on breakdown, arnoldi.jl:306)
+            consumer_sync();
+            double *vn = V + (long long)(jc + 1) * ldv;
+            const uint32_t xin_a = cx.xin_a;
+            for (int i = tid; i < units; i += NTC) {
+                double2 w2 = lds2(xin_a + 16u * (uint32_t)i);
+                w2.x /= beta;
+                w2.y /= beta;
+                reinterpret_cast<double2 *>(vn + G.r0)[i] = w2;
+            }
+            if (p > 0 && tm.rank == 0 && tid < p) vn[n + tid] = S->xtail[tid] / beta;
+            break;
+        }
+    }
+    if (tm.rank == 0 && tid == 0) {
+        P.stat[prob * 4 + 0] = m_out;
+        P.stat[prob * 4 + 1] = breakdown;
+        P.stat[prob * 4 + 2] = nfall;
+        P.stat[prob * 4 + 3] = 0;
+    }
+}
+
 // One instance per (operator kind, augmented or not): the persistent kernel is sensitive to code size (an unused
 // extra mat-vec loop cost 3-5 % everywhere), so each instance carries only the paths it can take.
-template <int OPK, bool AUG, bool XL, int GW = 8, bool SAFE = false>
+template <int OPK, bool AUG, bool XL, int GW = 8, bool SAFE = false, bool LZ1 = false>
 __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constant__ KrylovParams P,
                                                             const __grid_constant__ CUtensorMap tmA) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1645,8 +2028,11 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
     tm.rank = blockIdx.x % P.team_size;
     tm.C = P.team_size;
     tm.bar = P.peer_bar[P.myrank] + team;
-    tm.target = P.bar_base;
-    tm.seq = P.seq_base;
+    // Row-sharded: the barrier target / packet sequence number continue where the previous launch on this communicator
+    // stopped.  How far a launch gets is data dependent (breakdown, hand-over to the SAFE instance), so the state lives
+    // in the communicator buffer on the device -- every GPU keeps an identical copy -- not in host bookkeeping.
+    tm.target = P.comm_state ? P.comm_state[1] : P.bar_base;
+    tm.seq = P.comm_state ? P.comm_state[0] : P.seq_base;
     TmaGeom G;
     G.r0 = min(P.n, tm.rank * P.slice);
     G.nrows = min(P.n, G.r0 + P.slice) - G.r0;
@@ -1675,7 +2061,7 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
     }
     __syncthreads();
 
-    const long long xoff0 = (long long)team * 2 * P.xlen;
+    const long long xoff0 = (long long)team * (LZ1 ? 4 : 2) * P.xlen;  // (LZ1: four gather buffers per team)
     double *xb0 = P.peer_xbuf[P.myrank] + xoff0;
     double *xb1 = xb0 + P.xlen;
     const long long part0 = (long long)team * 2 * MAXCOL * P.cpad;
@@ -1692,7 +2078,7 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
     cx.tid = tid;
     cx.lane = tid & 31;
     cx.warp = tid >> 5;
-    cx.seq = P.seq_base;
+    cx.seq = tm.seq;
 
     int nlocal = -1;
     for (int prob = team; prob < P.nprob; prob += P.nteams) {
@@ -1715,7 +2101,8 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
             __syncwarp();
         } else {
             cx.rg = Ring{ring, P.nslot, 0, 0u};
-            if constexpr (XL) consumer_problem_xl<OPK, AUG, true, GW>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
+            if constexpr (XL && LZ1) consumer_problem_xl1<OPK, AUG, GW>(P, cx, G, tm, prob, nlocal, xb0, xoff0, partn0);
+            else if constexpr (XL) consumer_problem_xl<OPK, AUG, true, GW>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0);
             else consumer_problem<OPK, AUG, SAFE>(P, cx, G, tm, prob, nlocal, xb0, xb1, xoff0, part0, partn0, j0);
             consumer_sync();
             if (tid == 0) flag_set(&S->stop_seq, nlocal + 1);
@@ -1735,6 +2122,12 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
             }
             __syncthreads();
         }
+    }
+    // (no CTA can get here before every CTA of every GPU has read the state above: all of them take part in the first
+    // reduction of the launch; a launch without any reduction leaves the state as it is)
+    if (P.comm_state && blockIdx.x == 0 && tid == 0) {
+        P.comm_state[0] = cx.seq;
+        P.comm_state[1] = tm.target;
     }
 }
 

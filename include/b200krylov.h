@@ -294,7 +294,7 @@ int b200k_set_timing(b200k_handle_t h, int enabled);
 /* Which Krylov kernel the last factorisation used: 1 = LDG kernel (krylov_persistent_kernel, any layout),
  * 2 = TMA-ring kernel (krylov_tma_kernel; needs even n / ldv and 16-byte aligned bases), 3 = complex kernel,
  * 4 = the short-window (Lanczos / IOP) instance of the TMA-ring kernel (resident basis vector), 5 = the lock-step
- * multi-vector Lanczos kernel of batched expv.  The environment
+ * multi-vector Lanczos kernel of batched expv, 6 = the short-window instance with the one-reduction Lanczos step.  The environment
  * variable B200K_KERNEL=ldg, read at b200k_create, forces 1 (A/B measurements). */
 int b200k_last_kernel(b200k_handle_t h, int *which);
 /* Runtime switches (A/B measurements and tests): B200K_FLAG_FORCE_LDG = 1 uses krylov_persistent_kernel even
@@ -310,6 +310,8 @@ int b200k_last_kernel(b200k_handle_t h, int *which);
                               2 = whenever possible, 0 (default) = when the cost model says it is faster */
 #define B200K_FLAG_SYM_PADE 6 /* 1: the device-side small exponential of a symmetric tridiagonal (Lanczos) H uses the
                                  Pade path instead of the one-warp Chebyshev evaluation of exp(tT) e1 (A/B, tests) */
+#define B200K_FLAG_NO_LZ1 7 /* 1: Lanczos on the short-window instance takes the two-reduction step (alpha, then the norm)
+                               instead of the one-reduction step (krylov_kernel_tma.cuh, "One-reduction Lanczos step") */
 int b200k_set_flag(b200k_handle_t h, int flag, int value);
 
 #ifdef __cplusplus

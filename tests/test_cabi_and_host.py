@@ -166,7 +166,7 @@ def test_runtime_flags_match_header(eu):
     import inspect
     txt = open(os.path.join(ROOT, "include", "b200krylov.h")).read()
     flags = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"#define\s+B200K_FLAG_(\w+)\s+(\d+)", txt)}
-    assert flags == {"force_ldg": 1, "host_smallexp": 2, "l2hint": 3, "no_xl": 4, "no_mv": 5, "sym_pade": 6}
+    assert flags == {"force_ldg": 1, "host_smallexp": 2, "l2hint": 3, "no_xl": 4, "no_mv": 5, "sym_pade": 6, "no_lz1": 7}
     src = inspect.getsource(eu.api.Engine.set_flag)
     for name, val in flags.items():
         assert f'"{name}": {val}' in src, name
