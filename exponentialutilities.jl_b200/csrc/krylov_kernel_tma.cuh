@@ -53,6 +53,7 @@ struct __align__(128) SmemTma {
     // Flags the producer lane polls while the consumers run (single writer, single reader).  flag_set / flag_get are
     // volatile accesses in the product and shared-memory atomics in -DB200K_ATOMIC_FLAGS builds: a polled flag is a
     // data race by definition for plain loads and stores, which compute-sanitizer racecheck reports.
+    int j0_found;    // SAFE instance: step at which it takes over (0: nowhere)
     int cols_ready;  // number of complete basis columns of the current problem
     int stop_seq;    // consumers finished local problem #stop_seq (1-based)
 };
@@ -1079,11 +1080,13 @@ __device__ __noinline__ void reorth_step_c(const KrylovParams &P, unsigned targe
 }
 
 // One problem on the consumer side.  Mirrors krylov_body<2> of krylov_kernel.cuh.
-// SAFE = false: the fast instance.  When the re-orthogonalisation test fires at step j it records j in stat[4 prob + 3]
-// and stops; the SAFE instance (launched right behind it, or by the host for row-sharded operators) resumes the
-// factorisation at that step like arnoldi!(...; init = j) and runs the second Gram-Schmidt pass where needed.  Keeping
-// the second pass out of the fast instance matters: merely containing the (never executed) call cost 5 % of the C2
-// Arnoldi kernel (profiles/r2_dgks_ab.log).
+// SAFE = false: the fast instance -- no re-orthogonalisation code at all (any such code inside the step loop, even a
+// never-taken branch, cost 4-5 % of the C2 Arnoldi kernel through its effect on code generation,
+// profiles/r2_dgks_ab.md).  The test needs nothing the fast instance does not already leave behind: ||w_after|| is
+// H[j+1, j] and ||h||^2 the sum of squares of the column above it, so it is evaluated AFTERWARDS from the stored
+// Hessenberg matrix by the SAFE instance (launched right behind the fast one): if no step fails the test it exits at
+// once; otherwise it resumes the factorisation at the first failing step like arnoldi!(...; init = j), with the second
+// Gram-Schmidt pass wherever the test fires, and overwrites what the fast instance computed from there on.
 template <int OPK, bool AUG, bool SAFE>
 __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom &G, Team &tm, int prob, int nlocal,
                                  double *xb0, double *xb1, long long xoff0, long long part0, long long partn0, int j0) {
@@ -1100,7 +1103,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
     const double *xsrc;
     double xscale;
     int jstart;
-    int m_out = P.m, breakdown = 0, nreorth = 0, redo = 0;
+    int m_out = P.m, breakdown = 0, nreorth = 0;
     const bool sharded = P.nranks > 1;
     const bool via_xb0 = p > 0 || sharded;            // first gather source must carry tail / halo entries
     const double *lpart = P.peer_part[P.myrank];      // this GPU's inboxes
@@ -1196,11 +1199,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
 
         const int lo = P.lanczos ? jc : max(0, jc - iopw + 1);
         const int hi = jc;
-#ifdef B200K_NO_DGKS  // A/B builds only
-        const bool dgks = false;
-#else
-        const bool dgks = !P.lanczos;
-#endif
+        const bool dgks = SAFE && !P.lanczos;
         const int nc = hi - lo + 1;
         const int ulo = (P.lanczos && jc >= 1) ? jc - 1 : lo;
         dots_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, hi, part);
@@ -1213,8 +1212,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = beta_prev;
         // Re-orthogonalisation test: ||w_before||^2 = ||h||^2 + ||w_after||^2 for an orthonormal window (Pythagoras), so
         // no extra reduction is needed.  One warp sums the coefficients now and parks the result in shared memory;
-        // nothing is carried in registers through the update phase (doing this in every thread after the norm
-        // reduction cost 4.5 % of the C2 kernel through register pressure, profiles/r2_dgks_ab.log).
+        // nothing is carried in registers through the update phase.  (SAFE instance only.)
         if (dgks && cx.warp == 1) {
             double q = 0.0;
             for (int ci = cx.lane; ci < nc; ci += 32) q = fma(S->hs[ci], S->hs[ci], q);
@@ -1234,17 +1232,12 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         PT_MARK(blockIdx.x, j, 5);
 
         if (dgks && S->bc[0] < REORTH_ETA2 * (S->bc[1] + S->bc[0])) {
-            // every CTA of every rank takes the same decision: the reduced values are bitwise identical everywhere
-            // (NaN never triggers it)
-            if (SAFE) {  // second classical Gram-Schmidt pass, out of line; two more team reductions
-                reorth_step_c(P, tm.target, cx.seq, prob, jc, AUG);
-                tm.target += 2u * (unsigned)tm.C;
-                cx.seq += 2u;
-                ++nreorth;
-            } else {     // hand the rest of the factorisation to the SAFE instance
-                redo = j;
-                break;
-            }
+            // second classical Gram-Schmidt pass, out of line; two more team reductions (every CTA of every rank takes
+            // the same decision: the reduced values are bitwise identical everywhere; NaN never triggers it)
+            reorth_step_c(P, tm.target, cx.seq, prob, jc, AUG);
+            tm.target += 2u * (unsigned)tm.C;
+            cx.seq += 2u;
+            ++nreorth;
         }
         const double beta = sqrt(S->bc[0]);
         if (tm.rank == 0 && tid == 0) Hd[(long long)jc * ldh + jc + 1] = beta;
@@ -1275,7 +1268,6 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         P.stat[prob * 4 + 0] = m_out;
         P.stat[prob * 4 + 1] = breakdown;
         P.stat[prob * 4 + 2] = nreorth;  // steps that took the second Gram-Schmidt pass (host: barrier accounting)
-        if (!SAFE) P.stat[prob * 4 + 3] = redo;  // step at which the SAFE instance has to take over (0: never)
     }
 }
 
@@ -1783,13 +1775,13 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
     // ---- X_1: b (firststep!, arnoldi.jl:230-250 / 257-279) or the normalised first column of a resumed subspace
     const double *src1;  // out-of-slice entries of X_1 are read from here
     double xscale;
-    const bool stage = p > 0 || sharded;  // X_1 has to be staged in GX[1] (halo landing zone / tail rows)
+    // X_1 is always stored to GX[1]: step 2 rebuilds out-of-slice entries of X_2 from w'_1 and X_1
     if (P.j0 == 0) {
         double nrm = 0.0;
         for (int i = tid; i < units; i += NTC) {
             const double2 b2 = reinterpret_cast<const double2 *>(b + G.r0)[i];
             sts2(cx.xin_a + 16u * (uint32_t)i, b2);
-            if (stage) reinterpret_cast<double2 *>(GXb(1) + G.r0)[i] = b2;
+            reinterpret_cast<double2 *>(GXb(1) + G.r0)[i] = b2;
             nrm = fma(b2.x, b2.x, fma(b2.y, b2.y, nrm));
         }
         if (p > 0 && tid < p) {
@@ -1814,14 +1806,14 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
             }
             return;
         }
-        src1 = stage ? GXb(1) : b;
+        src1 = GXb(1);  // (published by the reduction above)
         xscale = 1.0 / beta;
     } else {
         const double *vj = V;  // lanczos! restarts at column 1 (it ignores init, arnoldi.jl:480)
         for (int i = tid; i < units; i += NTC) {
             const double2 v2 = reinterpret_cast<const double2 *>(vj + G.r0)[i];
             sts2(cx.xin_a + 16u * (uint32_t)i, v2);
-            if (sharded) reinterpret_cast<double2 *>(GXb(1) + G.r0)[i] = v2;
+            reinterpret_cast<double2 *>(GXb(1) + G.r0)[i] = v2;  // (visible to the team from step 2 on)
         }
         if (p > 0 && tid < p) S->xtail[tid] = vj[n + tid];
         if (sharded) {
@@ -2086,7 +2078,29 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
         // word (0: this problem needed no re-orthogonalisation -- nothing to do)
         int j0 = P.j0;
         if (SAFE && P.j0_from_stat) {
-            j0 = P.stat[prob * 4 + 3];
+            // first step j whose update removed most of the vector: H[j+1, j]^2 < eta^2 (||H[lo..j, j]||^2 + H[j+1, j]^2).
+            // Columns the fast instance never reached are zero (no trigger); so is every column in the normal case.
+            if (tid < 32) {
+                const double *Hp = P.Hd + (long long)prob * P.H_stride;
+                const int iopw = P.iop > 0 ? P.iop : P.m;
+                int first = 0x7fffffff;
+                for (int jc = tid; jc < P.m; jc += 32) {
+                    const int lo = max(0, jc - iopw + 1);
+                    double hsq = 0.0;
+                    for (int i = lo; i <= jc; ++i) {
+                        const double hv = Hp[(long long)jc * P.ldh + i];
+                        hsq = fma(hv, hv, hsq);
+                    }
+                    const double bj = Hp[(long long)jc * P.ldh + jc + 1];
+                    if (bj * bj < REORTH_ETA2 * (hsq + bj * bj)) first = min(first, jc + 1);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+                if (tid == 0) S->j0_found = first == 0x7fffffff ? 0 : first;
+            }
+            __syncthreads();
+            j0 = S->j0_found;
+            __syncthreads();
             if (j0 == 0) continue;  // (uniform for the CTA; the ring stays as the last processed problem left it)
             if (tid == 0) S->cols_ready = j0;
             __syncthreads();
