@@ -88,7 +88,7 @@ struct b200k_context {
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime (no libcuda link dependency)
     int l2hint = -1;        // B200K_FLAG_L2HINT: -1 automatic, 0 never, 1 always evict_first for operator chunks
     long long l2_bytes = 0;
-    int no_lz1 = 0;         // B200K_FLAG_NO_LZ1: two-reduction Lanczos step on the short-window instance (A/B, tests)
+    int no_lz1 = 0;         // B200K_FLAG_NO_LZ1: 0 = one-reduction Lanczos step for row-sharded operators only, 1 = never, 2 = always
     int sym_pade = 0;       // B200K_FLAG_SYM_PADE: device small exponential of a Lanczos H by Pade instead of Chebyshev
     int host_smallexp = 0;  // B200K_SMALLEXP=host: one-shot / batched expv do the small exponential on the host
     DevBuf tdev, errdev;
@@ -573,7 +573,7 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
 #endif
             switch (P.op_kind) {
                 case OP_CSR_STREAM:
-                    if (xl && c.lanczos && !h->no_lz1) {  // one-reduction Lanczos step
+                    if (xl && c.lanczos && (h->no_lz1 == 2 || (h->no_lz1 == 0 && cm))) {  // one-reduction Lanczos step (row-sharded)
                         if (op->max_row_nnz <= 5) kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5, false, true> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5, false, true>;
                         else kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 8, false, true> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 8, false, true>;
                         lz1 = true;
@@ -1196,7 +1196,7 @@ int b200k_set_flag(b200k_handle_t h, int flag, int value) {
     else if (flag == B200K_FLAG_NO_MV) h->no_mv = value == 2 ? 2 : (value ? 1 : 0);
     else if (flag == B200K_FLAG_L2HINT) h->l2hint = value < 0 ? -1 : (value ? 1 : 0);
     else if (flag == B200K_FLAG_SYM_PADE) h->sym_pade = value ? 1 : 0;
-    else if (flag == B200K_FLAG_NO_LZ1) h->no_lz1 = value ? 1 : 0;
+    else if (flag == B200K_FLAG_NO_LZ1) h->no_lz1 = value == 2 ? 2 : (value ? 1 : 0);
     else return fail(h, B200K_EARG, "unknown flag");
     return B200K_OK;
 }

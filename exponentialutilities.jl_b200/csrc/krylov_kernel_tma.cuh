@@ -1654,10 +1654,15 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
 // The two-reduction step above waits for an all-reduce twice: alpha = <v_j, A v_j>, then ||w||^2 after the update --
 // each a full latency chain over the team (4-6 k cycles on one GPU, 7-8 us over NVLink), and the second one is also the
 // barrier that publishes the updated vector to the CTAs that gather it.  Here ONE all-reduce per step carries
-//     S = <X_j, w'>_pre-fold (-> alpha),   Q = ||w'||^2,   G = <X_j, w'>      with  w' = A v_j - beta_{j-1} v_{j-1},
-// and ||w' - alpha v_j||^2 = Q - 2 alpha g + alpha^2 gives beta_j without a second pass (g = xscale * G; in exact
-// arithmetic g = alpha; a cancellation guard -- beta^2 < Q / 100 -- falls back to an explicit norm reduction, which is
-// exactly where breakdown decisions are taken).  What the second reduction used to publish is reconstructed by the
+//     S = <X_j, A v_j> (-> alpha),   Q = ||w'||^2,   G = <X_j, w'>,   N = ||X_j||^2      with  w' = A v_j - beta_{j-1} v_{j-1},
+// and ||w' - alpha v_j||^2 = Q - 2 alpha g + alpha^2 nu gives beta_j without a second pass (g = xscale G,
+// nu = xscale^2 N = ||v_j||^2, alpha = xscale S / nu).  nu is what makes this usable: v_j was normalised with the
+// PREDICTED beta_{j-1}, so ||v_j|| = 1 + O(eps Q / beta^2); assuming nu = 1 feeds that error back into the next
+// prediction and it grows ~4x per step (measured: garbage after 25 steps); with the measured nu every prediction is
+// exact for the vector actually used and the error stays at rounding level (1e-14 after 100 steps).  A cancellation
+// guard -- beta^2 < Q / 100, which is also where breakdown decisions are taken -- falls back to an explicit norm
+// reduction.  Used for row-sharded operators (an all-reduce over NVLink costs 7-8 us); on one GPU the release fence
+// behind 54 KB of gather-buffer stores per CTA makes the single reduction as expensive as the two it replaces.  What the second reduction used to publish is reconstructed by the
 // readers instead: w' is written to a gather buffer DURING the mat-vec (published by the step's single all-reduce),
 // and a CTA that needs entry c of the next vector outside its own slice forms
 //     X_{j+1}[c] = w'_j[c] - (alpha_j xscale_j) X_j[c]
@@ -1668,14 +1673,14 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
 template <bool AUG, int GW>
 __device__ void matvec_xl1(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *gw, const double *gx,
                            double gam, double xscale, bool learn, bool fold, double foldc, double *gwout,
-                           double &sacc, double &qacc, double &gacc) {
+                           double &sacc, double &qacc, double &gacc, double &nacc) {
     SmemTma *S = cx.S;
     const int tid = cx.tid;
     const int p = AUG ? P.p : 0;
     const uint32_t ws_a = cx.ws_a, xin_a = cx.xin_a;
     const uint32_t xl_a = xin_a - 8u * (uint32_t)G.r0;  // shared address of x(column) for own-slice columns
     const int nnz_cap = P.nnz_cap;
-    double s1 = 0.0, q1 = 0.0, g1 = 0.0;
+    double s1 = 0.0, q1 = 0.0, g1 = 0.0, n1 = 0.0;
     for (int c = 0; c < G.nch; ++c) {
         const int rl = c * P.ch_rows + tid;
         const bool active = tid < P.ch_rows && rl < G.nrows;
@@ -1733,6 +1738,7 @@ __device__ void matvec_xl1(const KrylovParams &P, Cons &cx, const TmaGeom &G, co
             double wv = sum * xscale;
             const double xr = lds1(xin_a + 8u * (uint32_t)rl);
             s1 = fma(xr, wv, s1);
+            n1 = fma(xr, xr, n1);
             if (fold) wv = fma(-foldc, lds1(ws_a + 8u * (uint32_t)rl), wv);
             q1 = fma(wv, wv, q1);
             g1 = fma(xr, wv, g1);
@@ -1747,6 +1753,7 @@ __device__ void matvec_xl1(const KrylovParams &P, Cons &cx, const TmaGeom &G, co
     sacc = s1;
     qacc = q1;
     gacc = g1;
+    nacc = n1;
 }
 
 template <int OPK, bool AUG, int GW>
@@ -1838,35 +1845,38 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
         const bool fold = j > 1;
         PT_MARK(blockIdx.x, j, 0);
         // ---- tail rows of w' (every CTA keeps them): (K x)_k = x_{k+1}, last row 0
-        double st = 0.0, qt = 0.0, gt = 0.0;
+        double st = 0.0, qt = 0.0, gt = 0.0, nt0 = 0.0;
         if (p > 0) {
             consumer_sync();
             if (tid < p) {
                 double wt = (tid < p - 1) ? S->xtail[tid + 1] * xscale : 0.0;
                 st = S->xtail[tid] * wt;
+                nt0 = S->xtail[tid] * S->xtail[tid];
                 if (fold) wt = fma(-(beta_prev * xscale_prev), S->ptail[tid], wt);
                 qt = wt * wt;
                 gt = S->xtail[tid] * wt;
                 S->wtail[tid] = wt;
             }
-            if (!(tm.rank == 0 && P.myrank == 0)) st = qt = gt = 0.0;  // counted once
+            if (!(tm.rank == 0 && P.myrank == 0)) st = qt = gt = nt0 = 0.0;  // counted once
         }
-        double sacc, qacc, gacc;
+        double sacc, qacc, gacc, nacc;
         matvec_xl1<AUG, GW>(P, cx, G, j == 1 ? src1 : GWb(parp), j == 1 ? src1 : GXb(parp), j == 1 ? 0.0 : gam, xscale,
-                            nlocal == 0 && j == 1, fold, beta_prev * xscale_prev, GWb(par), sacc, qacc, gacc);
+                            nlocal == 0 && j == 1, fold, beta_prev * xscale_prev, GWb(par), sacc, qacc, gacc, nacc);
         sacc += st;
         qacc += qt;
         gacc += gt;
+        nacc += nt0;
         PT_MARK(blockIdx.x, j, 1);
         PT_MARK(blockIdx.x, j, 2);
         // ---- the step's single all-reduce (release / acquire: publishes the w' stores, the previous update's X stores
         // and, row-sharded, the halo rows pushed to the peers)
         {
-            double v0 = warp_sum(sacc), v1 = warp_sum(qacc), v2 = warp_sum(gacc);
+            double v0 = warp_sum(sacc), v1 = warp_sum(qacc), v2 = warp_sum(gacc), v3 = warp_sum(nacc);
             if (cx.lane == 0) {
                 S->red[0][cx.warp][0] = v0;
                 S->red[0][cx.warp][1] = v1;
                 S->red[0][cx.warp][2] = v2;
+                S->red[0][cx.warp][3] = v3;
             }
             consumer_sync();  // (also: the whole w' slice of this CTA is in place)
             bool pushed = false;
@@ -1876,21 +1886,24 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
                 consumer_sync();
             }
             if (cx.warp == 0) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) {
                     s0 += S->red[0][w][0];
                     s1 += S->red[0][w][1];
                     s2 += S->red[0][w][2];
+                    s3 += S->red[0][w][3];
                 }
                 if (!sharded) {
                     ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 0, s0, cx.lane, true);
                     ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 1, s1, cx.lane, false);
                     ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 2, s2, cx.lane, false);
+                    ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 3, s3, cx.lane, false);
                 } else {
                     shard_publish_warp(P, tm, cx.seq + 1u, 0, s0, cx.lane, true, pushed);
                     shard_publish_warp(P, tm, cx.seq + 1u, 1, s1, cx.lane, false, false);
                     shard_publish_warp(P, tm, cx.seq + 1u, 2, s2, cx.lane, false, false);
+                    shard_publish_warp(P, tm, cx.seq + 1u, 3, s3, cx.lane, false, false);
                 }
             }
         }
@@ -1906,11 +1919,12 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
             if (p > 0 && tm.rank == 0 && tid < p) V[(long long)jc * ldv + n + tid] = S->xtail[tid] * xscale;
         }
         PT_MARK(blockIdx.x, j, 8);
-        if (!sharded) ll_collect(P, cx, tm, 3, S->hs, true);
-        else shard_collect(P, cx, tm, 3, S->hs, true);
+        if (!sharded) ll_collect(P, cx, tm, 4, S->hs, true);
+        else shard_collect(P, cx, tm, 4, S->hs, true);
         PT_MARK(blockIdx.x, j, 3);
-        const double alpha = S->hs[0] * xscale, Q = S->hs[1], g = S->hs[2] * xscale;
-        double beta2 = (Q - 2.0 * alpha * g) + alpha * alpha;
+        const double nu = xscale * xscale * S->hs[3];  // ||v_j||^2 as actually used (1 + O(eps))
+        const double alpha = S->hs[0] * xscale / nu, Q = S->hs[1], g = S->hs[2] * xscale;
+        double beta2 = (Q - 2.0 * alpha * g) + alpha * alpha * nu;
         const bool fallback = !(beta2 > 0.01 * Q);  // cancellation (or NaN): take the norm explicitly
         consumer_sync();  // S->hs is rewritten by the next collect
         // ---- local update X_{j+1} = w' - alpha v_j (shared memory + GX[(j+1) & 1]); no reduction needed

@@ -310,8 +310,9 @@ int b200k_last_kernel(b200k_handle_t h, int *which);
                               2 = whenever possible, 0 (default) = when the cost model says it is faster */
 #define B200K_FLAG_SYM_PADE 6 /* 1: the device-side small exponential of a symmetric tridiagonal (Lanczos) H uses the
                                  Pade path instead of the one-warp Chebyshev evaluation of exp(tT) e1 (A/B, tests) */
-#define B200K_FLAG_NO_LZ1 7 /* 1: Lanczos on the short-window instance takes the two-reduction step (alpha, then the norm)
-                               instead of the one-reduction step (krylov_kernel_tma.cuh, "One-reduction Lanczos step") */
+#define B200K_FLAG_NO_LZ1 7 /* Lanczos on the short-window instance: 0 (default) = the one-reduction step (krylov_kernel_tma.cuh,
+                               "One-reduction Lanczos step") for row-sharded operators, the two-reduction step on one GPU;
+                               1 = never the one-reduction step, 2 = always */
 int b200k_set_flag(b200k_handle_t h, int flag, int value);
 
 #ifdef __cplusplus

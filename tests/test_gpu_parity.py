@@ -289,14 +289,15 @@ def test_short_window_instance_xl(gpu, oracle):
     opA, opL = gpu.operator(A), gpu.operator(L)
     res = {}
     try:
-        # (False: default = one-reduction Lanczos step on the XL instance; "lz2": its two-reduction step; True: general)
-        for no_xl in (False, "lz2", True):
+        # (False: default = XL instance, two-reduction Lanczos step; "lz1": its one-reduction step (the default of
+        #  row-sharded operators); True: general instance)
+        for no_xl in (False, "lz1", True):
             eng.set_flag("no_xl", no_xl is True)
-            eng.set_flag("no_lz1", no_xl == "lz2")
+            eng.set_flag("no_lz1", 2 if no_xl == "lz1" else 0)
             want = "tma" if no_xl is True else "tma_xl"
             r = {}
             Ks = gpu.arnoldi(opL, b, m=30)  # Hermitian -> lanczos!
-            assert eng.last_kernel() == ("tma_xl1" if no_xl is False else want)
+            assert eng.last_kernel() == ("tma_xl1" if no_xl == "lz1" else want)
             r["lan_H"], r["lan_V"], r["lan_beta"] = Ks.getH().copy(), Ks.getV().cpu().numpy().copy(), Ks.beta
             r["lan_w"] = gpu.expv(0.8, opL, b, m=30)
             for q in (2, 6):
@@ -319,7 +320,7 @@ def test_short_window_instance_xl(gpu, oracle):
         eng.set_flag("no_xl", False)
         eng.set_flag("no_lz1", False)
     g = res[True]
-    for variant in (False, "lz2"):
+    for variant in (False, "lz1"):
         x = res[variant]
         for k in x:
             if k.endswith("_st"):
@@ -357,7 +358,7 @@ def test_batched_multivector_lanczos(gpu, oracle):
             eng.set_flag("no_mv", 1 if no_mv else 2)  # 2: always (the cost model prefers per-problem teams for 9 problems)
             for m in (30, 7):
                 out[(no_mv, m)] = gpu.expv_batched(ts, op, B, m=m)
-                assert eng.last_kernel() == ("tma_xl1" if no_mv else "tma_mv")
+                assert eng.last_kernel() == ("tma_xl" if no_mv else "tma_mv")
     finally:
         eng.set_flag("no_mv", 0)
     # problems of one group that break down at different steps (Krylov dimensions 3, 2, 0, 3, 1) while others run on
@@ -477,7 +478,7 @@ def test_edge_layouts_and_breakdown_in_stream_mode(gpu, oracle):
     for herm in (True, False):
         Ks = gpu.arnoldi(Dg, bn, m=30, ishermitian=herm)
         Ko = oracle.arnoldi(Dg, bn, m=30, ishermitian_=herm)
-        assert eng.last_kernel() == ("tma_xl1" if herm else "tma")
+        assert eng.last_kernel() == ("tma_xl" if herm else "tma")
         assert Ks.m == Ko.m == 3 and Ks.wasbreakdown
         w = gpu.expv(0.9, Dg, bn, m=30, ishermitian=herm)
         assert relerr(w, np.exp(0.9 * d) * bn) < 1e-9

@@ -289,7 +289,7 @@ def test_expv_phiv_with_reference_style_caches(gpu, oracle):
             W1 = torch.empty((4, 1200), dtype=torch.float64, device="cuda")
             _, e0 = gpu.phiv_(W0, 0.7, Ks, 3, correct=correct, errest=True)
             _, e1 = gpu.phiv_(W1, 0.7, Ks, 3, cache=pc, correct=correct, errest=True)
-            assert relerr(W1.cpu().numpy(), W0.cpu().numpy()) < 1e-13 and abs(e0 - e1) <= 1e-12 * abs(e0)
+            assert relerr(W1.cpu().numpy(), W0.cpu().numpy()) < 1e-13 and abs(e0 - e1) <= 1e-12 * abs(e0) + 1e-18
             Wo, eo = oracle.phiv_ks(0.7, Ko, 3, correct=correct, errest=True)
-            assert relerr(W1.t().cpu().numpy(), Wo) < RTOL and abs(e1 - eo) <= 1e-8 * abs(eo)
+            assert relerr(W1.t().cpu().numpy(), Wo) < RTOL and abs(e1 - eo) <= 1e-8 * abs(eo) + 1e-18  # (converged: ~1e-24)
     assert ec.mem.size >= 25 * 25 and len(ec.expcache) == 3 and len(pc.expcache) == 3
