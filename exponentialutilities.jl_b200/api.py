@@ -861,6 +861,13 @@ def phiv_timestep(ts, A, B, *, tau=0.0, m=None, tol=1.0e-7, opnorm=None, iop=0, 
     list of output times; ``opnorm`` None (Arnoldi estimate), a scalar, or a callable (A, inf) -> bound."""
     op = operator(A)
     eng = op.engine
+    if op.is_complex or _is_complex_value(B):
+        nco = 1 if (not hasattr(B, "shape") or len(B.shape) == 1) else int(B.shape[1])
+        if nco != 1:
+            raise _lib.UnsupportedError("ComplexF64 phiv_timestep with p > 0 is not implemented (expv_timestep is)")
+        return _expv_timestep_z(ts, op, B, tau=tau, m=m, tol=tol, opnorm=opnorm, iop=iop, correct=correct,
+                                adaptive=adaptive, delta=delta, ishermitian=ishermitian, gamma=gamma, NA=NA,
+                                return_steps=return_steps)
     scalar_t = np.isscalar(ts)
     tsa = np.ascontiguousarray(np.atleast_1d(np.asarray(ts, dtype=np.float64)))
     Bd, was_np = _to_device(B, eng)
@@ -893,6 +900,113 @@ def phiv_timestep(ts, A, B, *, tau=0.0, m=None, tol=1.0e-7, opnorm=None, iop=0, 
     out = Uo[:, 0] if scalar_t else Uo
     out = out.cpu().numpy() if was_np else out
     return (out, nsteps.value) if return_steps else out
+
+
+def _ts_flops(m, tau, n, p, NA, iop, Hnorm, maxtau):
+    """_phiv_timestep_estimate_flops -- src/krylov_phiv_adaptive.jl:482-501."""
+    iop = m if iop == 0 else iop
+    flops = 2 * (p - 1) * (NA + n) + (2 * p + 1) * n + 2 * m * NA + sum(3 * min(i, iop) for i in range(1, m + 1))
+    MH = 44 / 3 + 2 * math.ceil(max(0.0, math.log2(Hnorm / 5.37)))
+    return (flops + round(MH * (m + p) ** 3)) * int(math.ceil(maxtau / tau))
+
+
+def _ts_adapt(m, tau, eps, m_old, tau_old, eps_old, q, kappa, gamma, omega, maxtau, n, p, NA, iop, Hnorm):
+    """_phiv_timestep_adapt (Niesen-Wright, Algorithm 4) -- src/krylov_phiv_adaptive.jl:455-481."""
+    if tau_old > tau:
+        q = math.log(tau / tau_old) / math.log(eps / eps_old) - 1
+    tau_new = min(max(tau * (gamma / omega) ** (1 / (q + 1)), tau / 5), 2 * tau, maxtau)
+    if m_old < m:
+        kappa = (eps / eps_old) ** (1 / (m_old - m))
+    m_new = m + math.ceil(math.log(omega / gamma) / math.log(kappa))
+    m_new = min(max(m_new, (3 * m) // 4, 1), int(math.ceil(4 * m / 3)))
+    if _ts_flops(m, tau_new, n, p, NA, iop, Hnorm, maxtau) < _ts_flops(m_new, tau, n, p, NA, iop, Hnorm, maxtau):
+        m_new = m
+    else:
+        tau_new = tau
+    return m_new, tau_new, q, kappa
+
+
+def _expv_timestep_z(ts, op, b, *, tau, m, tol, opnorm, iop, correct, adaptive, delta, ishermitian, gamma, NA,
+                     return_steps):
+    """expv_timestep for ComplexF64 operators / vectors (the reference's own GPU test, test/gpu/gputests.jl:41-58).
+    The Niesen-Wright controller of phiv_timestep! (src/krylov_phiv_adaptive.jl:260-453) with p = 0, on the host as in
+    the reference; every length-n operation runs in the library (b200k_arnoldi_z, b200k_phiv_ks_z)."""
+    eng = op.engine
+    opz = op.as_complex()
+    scalar_t = np.isscalar(ts)
+    tsa = np.sort(np.atleast_1d(np.asarray(ts, dtype=np.float64)))
+    bd, was_np = _to_device(b, eng)
+    bd = bd.reshape(-1).to(torch.complex128).contiguous()
+    n = opz.n
+    if bd.numel() != n:
+        raise DimensionMismatch("Dimension mismatch")
+    m = int(min(10, n) if m is None else m)
+    herm = opz.ishermitian if ishermitian is None else bool(ishermitian)
+    abstol = opn = None
+    if opnorm is not None:
+        opn = float(opnorm(op, np.inf)) if callable(opnorm) else float(opnorm)
+        abstol = tol * opn
+    b0norm = float(bd.abs().max().item())
+
+    def tau_guess(mm):
+        return 10 / opn * (abstol * ((mm + 1) / math.e) ** (mm + 1) * math.sqrt(2 * math.pi * (mm + 1)) /
+                           (4 * opn * b0norm)) ** (1 / mm)
+
+    if opn is not None and tau == 0:
+        tau = tau_guess(m)
+    tend = float(tsa[-1])
+    seed = opn is None and tau == 0
+    if seed:
+        tau = tend
+    if adaptive:
+        if herm:
+            iop = 2
+        if NA == 0:
+            NA = opz.nnz
+    Ut = torch.zeros((tsa.size, n), dtype=torch.complex128, device=eng.device)
+    u = bd.clone()
+    Ks = KrylovSubspace(n, m, engine=eng, dtype=np.complex128)
+    w = torch.empty((2, n), dtype=torch.complex128, device=eng.device)
+    ws = torch.empty((2, n), dtype=torch.complex128, device=eng.device)
+    t, snapshot, nsteps = 0.0, 1, 0
+    while t < tend:
+        if t + tau > tend:
+            tau = tend - t
+        arnoldi_(Ks, opz, u, tol=tol, m=m, iop=iop)
+        if abstol is None:
+            opn = float(np.linalg.norm(Ks.getH(), 1))
+            abstol = tol * opn
+            if seed:
+                tau = min(tend - t, gamma * tau_guess(m))
+        if Ks.wasbreakdown:
+            tau = tend - t
+        _, eps = phiv_(w, tau, Ks, 1, correct=correct, errest=True)
+        if adaptive:
+            omega = (tend / tau) * (eps / abstol)
+            eps_old, m_old, tau_old = eps, m, tau
+            q, kappa = m / 4, 2.0
+            maxtau = tend - t
+            guard = 0
+            while omega > delta and guard < 200:
+                guard += 1
+                m_new, tau_new, q, kappa = _ts_adapt(m, tau, eps, m_old, tau_old, eps_old, q, kappa, gamma, omega, maxtau,
+                                                     n, 0, NA, iop, float(np.linalg.norm(Ks.getH(), 1)))
+                m, m_old = m_new, m
+                tau, tau_old = tau_new, tau
+                arnoldi_(Ks, opz, u, tol=tol, m=m, iop=iop)
+                _, eps_new = phiv_(w, tau, Ks, 1, correct=correct, errest=True)
+                eps, eps_old = eps_new, eps
+                omega = (tend / tau) * (eps / abstol)
+        while snapshot <= tsa.size and t + tau >= tsa[snapshot - 1]:
+            phiv_(ws, float(tsa[snapshot - 1] - t), Ks, 1, correct=correct)
+            Ut[snapshot - 1].copy_(ws[0])
+            snapshot += 1
+        u = w[0].clone()  # u = tau^0 * P[:, end-1]: the phi_0 column
+        t += tau
+        nsteps += 1
+    out = Ut[0] if scalar_t else Ut.t()
+    out = out.cpu().numpy() if was_np else out
+    return (out, nsteps) if return_steps else out
 
 
 def expv_timestep(ts, A, b, **kw):

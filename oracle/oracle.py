@@ -640,7 +640,10 @@ def phiv_timestep(ts, A, B, *, tau=0.0, m=None, tol=1e-7, opnorm=None, iop=0, co
     (or a vector for p = 0, which is expv_timestep).  Returns U (n x len(ts)), or a vector for a scalar ``ts``."""
     scalar_t = np.isscalar(ts)
     ts = np.sort(np.atleast_1d(np.asarray(ts, dtype=float)))
-    B = np.asarray(B, dtype=float)
+    # T = promote_type(eltype(A), eltype(B)) (krylov_phiv_adaptive.jl:116-131): ComplexF64 operators / vectors are fine
+    cplx = np.iscomplexobj(B) or np.iscomplexobj(A if not sp.issparse(A) else A.data)
+    dt = np.complex128 if cplx else np.float64
+    B = np.asarray(B, dtype=dt)
     Bm = B.reshape(B.shape[0], -1)
     n = A.shape[0]
     if m is None:
@@ -662,10 +665,10 @@ def phiv_timestep(ts, A, B, *, tau=0.0, m=None, tol=1e-7, opnorm=None, iop=0, co
     if seed_arnoldi_tau:
         tau = tend
     p = Bm.shape[1] - 1
-    U = np.zeros((n, ts.size), order="F")
+    U = np.zeros((n, ts.size), order="F", dtype=dt)
     u = Bm[:, 0].copy()
-    W = np.zeros((n, p + 1), order="F")
-    Ks = KrylovSubspace(n, m)
+    W = np.zeros((n, p + 1), order="F", dtype=dt)
+    Ks = KrylovSubspace(n, m, dtype=dt, hdtype=(np.float64 if (cplx and ishermitian_) else dt))
     coeffs = np.ones(max(p, 0))
     if adaptive:
         if ishermitian_:
@@ -734,7 +737,7 @@ def phiv_timestep(ts, A, B, *, tau=0.0, m=None, tol=1e-7, opnorm=None, iop=0, co
 
 def expv_timestep(ts, A, b, **kw):
     """expv_timestep(ts, A, b; ...) -- src/krylov_phiv_adaptive.jl:57-114 (phiv_timestep with p = 0)."""
-    return phiv_timestep(ts, A, np.asarray(b, dtype=float).reshape(-1), **kw)
+    return phiv_timestep(ts, A, np.asarray(b).reshape(-1), **kw)
 
 
 # --------------------------------------------------------------------------------------

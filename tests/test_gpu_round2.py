@@ -293,3 +293,31 @@ def test_expv_phiv_with_reference_style_caches(gpu, oracle):
             Wo, eo = oracle.phiv_ks(0.7, Ko, 3, correct=correct, errest=True)
             assert relerr(W1.t().cpu().numpy(), Wo) < RTOL and abs(e1 - eo) <= 1e-8 * abs(eo) + 1e-18  # (converged: ~1e-24)
     assert ec.mem.size >= 25 * 25 and len(ec.expcache) == 3 and len(pc.expcache) == 3
+
+
+def test_complex_expv_timestep_reference_gpu_test(gpu, oracle):
+    """The reference's own GPU test (test/gpu/gputests.jl:41-58): ComplexF64 sparse operator (strictly upper triangular
+    plus a sprinkle), complex b, expv(t, A, b) and expv_timestep over 300 snapshot times; also adaptive stepping and a
+    Hermitian (Schroedinger-type) operator."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(41)
+    n = 1000
+    A = sp.random(n, n, density=10 / n, random_state=1, data_rvs=rng.standard_normal).astype(np.complex128)
+    A = A + 1j * sp.random(n, n, density=10 / n, random_state=2, data_rvs=rng.standard_normal)
+    A = (sp.triu(A, 1) + sp.random(n, n, density=1 / n, random_state=3, data_rvs=rng.standard_normal)
+         + 1j * sp.random(n, n, density=1 / n, random_state=4, data_rvs=rng.standard_normal)).tocsr()
+    b = rng.random(n) + 1j * rng.random(n)
+    assert relerr(gpu.expv(0.1, A, b), oracle.expv(0.1, A, b)) < RTOL
+    ts = np.linspace(0, 1, 300)
+    U, ns = gpu.expv_timestep(ts, A, b, return_steps=True)
+    Uo, nso = oracle.expv_timestep(ts, A, b, return_steps=True)
+    assert ns == nso and U.shape == (n, 300)
+    assert relerr(U, Uo) < 1e-8   # (same steps; each step is a Krylov approximation that matches to 1e-10)
+    U, ns = gpu.expv_timestep([0.3, 1.0], A, b, adaptive=True, tol=1e-8, return_steps=True)
+    Uo, nso = oracle.expv_timestep([0.3, 1.0], A, b, adaptive=True, tol=1e-8, return_steps=True)
+    assert ns == nso and relerr(U, Uo) < 1e-8
+    Hm = (-laplacian2d(30, 30)).astype(np.complex128) * 1j   # i * (-Laplacian): exp(tA) is unitary
+    psi = rng.standard_normal(900) + 1j * rng.standard_normal(900)
+    U = gpu.expv_timestep([0.2, 0.5], Hm, psi, m=20)
+    assert relerr(U, oracle.expv_timestep([0.2, 0.5], Hm, psi, m=20)) < 1e-8
+    assert abs(np.linalg.norm(U[:, 1]) / np.linalg.norm(psi) - 1) < 1e-6
