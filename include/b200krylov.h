@@ -64,6 +64,11 @@ const char *b200k_last_error(b200k_handle_t h);
 int b200k_device_info(b200k_handle_t h, int *sm_count, int *max_team, int64_t *launches);
 
 /* ---- operators: the reference's operator interface (docs/src/interfaces.md:9-36) ------------
+ * NOT offered: matrix-free operators (a `mul!` callback, SURVEY.md 8b `b200k_op_callback`).  The whole design rests on
+ * fusing the mat-vec into the persistent Krylov kernel (the operator is streamed by the kernel's own TMA producer);
+ * a host- or device-side callback per step would break that fusion and fall back to one launch per step -- the
+ * reference's generic path already does that.  Concrete CSR and dense operators, real and ComplexF64, are covered. */
+/*
  * size / eltype / mul! / ishermitian / opnorm of a concrete fp64 matrix.  The arrays are copied
  * into library-owned, 0-based, padded device storage ("operator ingestion"), so the caller may
  * free its copies afterwards.  `location`: 0 = the pointers are device pointers, 1 = host.
