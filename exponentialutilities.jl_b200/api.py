@@ -648,6 +648,8 @@ def expv(t, A, b=None, *, mode="happy_breakdown", m=None, tol=1.0e-7, ishermitia
     st = eng.lib.b200k_expv(eng.handle, op.ptr, float(t), C.c_void_p(bd.data_ptr()), C.byref(opts),
                             C.c_void_p(w.data_ptr()), None, None, None)
     eng.check(st)
+    if was_np:  # host result: complete the call here, which also surfaces a deferred SingularException of the device-side
+        eng.synchronize()  # small exponential (CUDA-tensor callers stay asynchronous and get it at their next synchronize())
     return _from_device(w, was_np)
 
 
@@ -802,6 +804,8 @@ def expv_batched(ts, A, B, *, m=30, tol=1.0e-7, ishermitian=None, iop=0, out=Non
                                     C.c_void_p(Bt.data_ptr()), ld, C.byref(opts), C.c_void_p(Wt.data_ptr()), ldw,
                                     None, None)
     eng.check(st)
+    if was_np:
+        eng.synchronize()  # (surfaces a deferred SingularException of the device-side small exponentials)
     W = Wt[:, : op.n].t()
     return W.cpu().numpy() if was_np else W
 
