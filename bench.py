@@ -21,8 +21,9 @@ After the headline the same run measures, under "also" (each with an in-run pari
     lanczos   the reference's default dispatch for this symmetric operator, with its own roofline (rank 0)
     c5        BASELINE configs[4]: 1024 independent (t_i, v_i), Laplacian 250x400 (n = 1e5), split over the ranks
     c2s       N >= 2: configs[1] as ONE problem row-sharded over the N GPUs (in-kernel NVLink halo + all-reduce)
+    c3s       N >= 2: configs[2] (phiv K = 4, dense n = 16384) with the dense operator in row blocks over the N GPUs
     c4        N == 8: configs[3]: kiops, Laplacian 2500x4000 (n = 1e7), row-sharded over the 8 GPUs
-`--also lanczos,c5,c2s,c4,none` overrides the default selection.
+`--also lanczos,c5,c2s,c3s,c4,none` overrides the default selection.
 
 The headline path is full Arnoldi (ishermitian=false), the north-star kernel; --path lanczos times the
 reference's default dispatch for this (symmetric) operator as the headline instead.
@@ -231,7 +232,7 @@ def main():
     ap.add_argument("--path", default="arnoldi", choices=["arnoldi", "lanczos"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-reps", type=int, default=8)
-    ap.add_argument("--also", default="auto", help="comma list of lanczos,c5,c2s,c4 or none / auto")
+    ap.add_argument("--also", default="auto", help="comma list of lanczos,c5,c2s,c3s,c4 or none / auto")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -292,7 +293,7 @@ def main():
     eng = eu.get_engine(local_rank)
 
     if args.also == "auto":
-        also_set = {"lanczos", "c5"} | ({"c2s"} if world >= 2 else set()) | ({"c4"} if world == 8 else set())
+        also_set = {"lanczos", "c5"} | ({"c2s", "c3s"} if world >= 2 else set()) | ({"c4"} if world == 8 else set())
     else:
         also_set = {s for s in args.also.split(",") if s and s != "none"}
 
@@ -576,6 +577,49 @@ def main():
                     r["parity_rel_err_vs_oracle"] = relerr(wf, O.expv(T, A, b2, m=M, ishermitian_=h2))
             sec2[path2] = r
         also["c2_row_sharded"] = sec2
+        barrier()
+        sop.close()
+
+    # ------------------------------------------------------------------------------------------------------
+    # also.c3_dense_row_sharded: BASELINE configs[2] (phiv K = 4, dense n = 16384, m = 30) with the operator split into
+    # row blocks over the N GPUs: the all-gather of x happens inside the persistent kernel
+    # ------------------------------------------------------------------------------------------------------
+    if "c3s" in also_set and world >= 2:
+        n3 = 16384
+        ranges = P.row_partition(n3, world)
+        starts = [r[0] for r in ranges] + [n3]
+        r0, nl = ranges[rank]
+        g3 = torch.Generator(device=dev).manual_seed(2)  # every rank generates the same matrix and keeps its rows
+        A3 = torch.randn(n3, n3, dtype=torch.float64, device=dev, generator=g3) / 128
+        b3 = torch.randn(n3, dtype=torch.float64, device=dev, generator=g3)
+        sop = P.ShardedDenseOperator(A3[r0:r0 + nl], starts, ishermitian=False)
+        bl = b3[r0:r0 + nl].contiguous()
+        Ks3 = eu.KrylovSubspace(nl, M, engine=eng)
+        W3 = torch.empty((5, nl), dtype=torch.float64, device=dev)
+
+        def step3():
+            eu.arnoldi_(Ks3, sop.op, bl, m=M, ishermitian=False)
+            eu.phiv_(W3, 1.0, Ks3, 4)
+
+        ms3 = timed(step3, 5, 2) / 5
+        by3 = M * (8 * n3 * n3 + 16 * n3) + 8 * n3 * M * (M + 1) + 16 * n3 + 8 * n3 * M + 8 * n3 * 5  # BASELINE.md 3 (whole operator)
+        sec3 = {"n": n3, "k": 4, "m": M, "rows_per_rank": nl, "ms_per_phiv": ms3, "phiv_per_s": 1e3 / ms3,
+                "kernel": kname.get(eng.last_kernel(), "?"), "bytes_all_gpus": by3,
+                "achieved_gbs_per_gpu": by3 / world / (ms3 * 1e-3) / 1e9, "frac": by3 / world / (ms3 * 1e-3) / 1e9 / peak,
+                "x_allgather": "in-kernel peer stores: %d doubles pushed per rank and step" % (nl * (world - 1))}
+        cols3 = [gather_rows(W3[c].contiguous(), ranges) for c in range(5)]
+        if rank == 0:
+            op1 = eu.operator(A3)  # the whole matrix on one GPU: same call, same library
+            W1 = eu.phiv(1.0, op1, b3, 4, m=M)
+            sec3["rel_err_vs_one_gpu"] = relerr(np.stack(cols3, 1), W1.cpu().numpy())
+            del op1, W1
+            if not args.no_cpu_baseline:
+                from oracle import oracle as O
+                with all_host_threads():
+                    Wo = O.phiv(1.0, A3.cpu().numpy(), b3.cpu().numpy(), 4, m=M)
+                sec3["parity_rel_err_vs_oracle"] = relerr(np.stack(cols3, 1), Wo)
+        also["c3_dense_row_sharded"] = sec3
+        del A3
         barrier()
         sop.close()
 

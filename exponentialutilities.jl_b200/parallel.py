@@ -128,6 +128,25 @@ class ShardedOperator:
             self.comm = None
 
 
+def dense_gather_position(g, row_starts, q: int):
+    """Position of global row/column ``g`` in rank ``q``'s gather buffer for a row-sharded DENSE operator: the rank's own
+    entries come first, every other row follows in ascending global order (the layout b200k_op_dense_create_sharded
+    permutes the block's columns into and builds its send list for)."""
+    g = np.asarray(g, dtype=np.int64)
+    q0, q1 = int(row_starts[q]), int(row_starts[q + 1])
+    nq = q1 - q0
+    return np.where((g >= q0) & (g < q1), g - q0, np.where(g < q0, nq + g, g))
+
+
+def dense_block_in_gather_order(A_block, row_starts, q: int):
+    """Columns of rank q's row block permuted into its gather order (host mirror of what the library does at ingestion)."""
+    n = int(row_starts[-1])
+    pos = dense_gather_position(np.arange(n), row_starts, q)
+    out = np.empty_like(A_block)
+    out[:, pos] = A_block
+    return out
+
+
 class ShardedDenseOperator:
     """A dense operator whose rows are split across the ranks (BASELINE config 3 beyond one GPU).  ``A_block`` is this
     rank's (nloc x n) row block (NumPy array or CUDA tensor, columns in global order); every rank passes the same

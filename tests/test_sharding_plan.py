@@ -115,3 +115,59 @@ def test_halo_exchange_world2_gloo():
     for p in procs:
         p.join(120)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+
+
+def _dense_worker(rank, world, port, n, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import eu_b200 as eu
+    P = eu.parallel
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((n, n))
+    x = rng.standard_normal(n)
+    parts = P.row_partition(n, world, align=2)
+    starts = np.array([p[0] for p in parts] + [n])
+    r0, nl = parts[rank]
+    blk = P.dense_block_in_gather_order(A[r0:r0 + nl], starts, rank)
+    # the "all-gather of x" the kernel performs with peer stores: every rank writes its rows into every peer's buffer
+    # at the planned positions (here: one all_gather, then each rank scatters into its own gather order)
+    mx = max(p[1] for p in parts)
+    mine = torch.zeros(mx, dtype=torch.float64)
+    mine[:nl] = torch.from_numpy(x[r0:r0 + nl])
+    outs = [torch.zeros(mx, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(outs, mine)
+    xbuf = np.full(n, np.nan)
+    for q, (q0, nq) in enumerate(parts):
+        xbuf[P.dense_gather_position(np.arange(q0, q0 + nq), starts, rank)] = outs[q][:nq].numpy()
+    y = blk @ xbuf
+    ok = bool(np.allclose(y, (A @ x)[r0:r0 + nl], rtol=1e-13, atol=1e-13)) and not np.isnan(xbuf).any()
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+def test_dense_row_sharding_gather_order_gloo_world2(eu):
+    """Dense row blocks: the gather-order permutation of the block's columns and the all-gather of x,
+    world size 2 on CPU."""
+    P = eu.parallel
+    starts = np.array([0, 6, 10, 16])
+    for q in range(3):
+        pos = P.dense_gather_position(np.arange(16), starts, q)
+        assert sorted(pos.tolist()) == list(range(16))                      # a permutation
+        q0, q1 = starts[q], starts[q + 1]
+        assert pos[q0:q1].tolist() == list(range(q1 - q0))                  # own entries first
+        rest = np.concatenate([pos[:q0], pos[q1:]])
+        assert rest.tolist() == list(range(q1 - q0, 16))                    # the others in ascending global order
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dense_worker, args=(r, 2, port, 64, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs)
+    assert ret.get(timeout=5) == 1
