@@ -98,6 +98,33 @@ if "dense" in which:
             print(f"[{name}] kiops herm={herm} relerr {relerr(wf, wo[:, 0]):.3e} stats {st} vs {so}", flush=True)
         dist.barrier(); sop.close()
 
+if "reorth" in which:
+    # ill-conditioned Krylov sequence on a row-sharded operator: the SAFE instance (second Gram-Schmidt pass) with the
+    # two-level packet all-reduces, CSR and dense row blocks
+    from oracle import oracle as O
+    import scipy.sparse as sp
+    rng = np.random.default_rng(9)
+    n = 2048
+    d = np.concatenate([-np.ones(1024), -2 * np.ones(512), -1e3 * np.ones(512)]) + 1e-8 * rng.standard_normal(n)
+    D = sp.diags(d).tocsr()
+    D.indices = D.indices.astype(np.int32); D.indptr = D.indptr.astype(np.int32)
+    b = rng.standard_normal(n)
+    sop, ranges, r0, nl = make(D, False)
+    bl = torch.from_numpy(b[r0:r0 + nl]).cuda()
+    w = eu.expv(0.01, sop.op, bl, m=30, ishermitian=False)
+    wf = gather_rows(w, ranges)
+    if rank == 0:
+        print(f"[clustered diag, CSR sharded] expv relerr {relerr(wf, O.expv(0.01, D, b, m=30, ishermitian_=False)):.3e}", flush=True)
+    dist.barrier(); sop.close()
+    starts = [r[0] for r in ranges] + [n]
+    Dd = D.toarray() + 1e-9 * np.random.default_rng(3).standard_normal((n, n))
+    sopd = P.ShardedDenseOperator(Dd[r0:r0 + nl], starts, ishermitian=False)
+    w = eu.expv(0.01, sopd.op, bl, m=30, ishermitian=False)
+    wf = gather_rows(w, ranges)
+    if rank == 0:
+        print(f"[clustered diag, dense sharded] expv relerr {relerr(wf, O.expv(0.01, Dd, b, m=30, ishermitian_=False)):.3e}", flush=True)
+    dist.barrier(); sopd.close()
+
 def timed(fn, reps, warm=3):
     for _ in range(warm): fn()
     dist.barrier(); torch.cuda.synchronize()

@@ -331,3 +331,31 @@ def test_complex_expv_timestep_reference_gpu_test(gpu, oracle):
     U = gpu.expv_timestep([0.2, 0.5], Hm, psi, m=20)
     assert relerr(U, oracle.expv_timestep([0.2, 0.5], Hm, psi, m=20)) < 1e-8
     assert abs(np.linalg.norm(U[:, 1]) / np.linalg.norm(psi) - 1) < 1e-6
+
+
+def test_reorthogonalisation_in_a_batch_and_on_the_ldg_kernel(gpu, oracle):
+    """The SAFE instance inside a batch (only some problems fail the test: the others are skipped by it) and the inline
+    two-pass loop of the LDG kernel (odd n -> no 16-byte alignment -> krylov_persistent_kernel)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(29)
+    n = 2000
+    d = np.concatenate([-np.ones(1000), -2 * np.ones(500), -1e3 * np.ones(500)]) + 1e-8 * rng.standard_normal(n)
+    D = sp.diags(d).tocsr()
+    B = rng.standard_normal((n, 7))
+    B[:, 2] = 0.0                       # a zero problem in the middle
+    B[1000:, 4] = 0.0                   # lives in one cluster: happy breakdown after one step
+    ts = np.full(7, 0.01)
+    W = gpu.expv_batched(ts, D, B, m=30, ishermitian=False)
+    for i in range(7):
+        wo = oracle.expv(0.01, D, B[:, i], m=30, ishermitian_=False)
+        if i == 2:
+            assert np.all(W[:, i] == 0.0)
+        else:
+            assert relerr(W[:, i], wo) < RTOL, (i, relerr(W[:, i], wo))
+    # odd dimension: LDG kernel
+    no = 1999
+    Do = sp.diags(d[:no]).tocsr()
+    bo = rng.standard_normal(no)
+    w = gpu.expv(0.01, Do, bo, m=30, ishermitian=False)
+    assert gpu.get_engine().last_kernel() == "ldg"
+    assert relerr(w, oracle.expv(0.01, Do, bo, m=30, ishermitian_=False)) < RTOL
