@@ -577,7 +577,6 @@ int launch_krylov(b200k_context *h, const KrylovCall &c) {
                         if (op->max_row_nnz <= 5) kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5, false, true> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5, false, true>;
                         else kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 8, false, true> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 8, false, true>;
                         lz1 = true;
-                        P.lz_order = 1;
                     } else if (xl && op->max_row_nnz <= 5) kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 5> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 5>;
                     else if (xl) kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, true, 8> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, true, 8>;
                     else kern = aug ? (const void *)krylov_tma_kernel<OP_CSR_STREAM, true, false> : (const void *)krylov_tma_kernel<OP_CSR_STREAM, false, false>;
@@ -1131,7 +1130,6 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
                          6 * SE_MAXM * SE_MAXM * 8);
     if (const char *env = std::getenv("B200K_MV")) h->no_mv = std::strcmp(env, "0") == 0 ? 1 : (std::strcmp(env, "2") == 0 ? 2 : 0);
     if (const char *env = std::getenv("B200K_XL")) h->no_xl = std::strcmp(env, "0") == 0 ? 1 : 0;
-    if (const char *env = std::getenv("B200K_LZ1")) h->no_lz1 = std::atoi(env);  // 0 auto, 1 never, 2 always (A/B runs)
     if (const char *env = std::getenv("B200K_KERNEL")) h->force_ldg = std::strcmp(env, "ldg") == 0 ? 1 : 0;
     h->max_ctas = std::min(h->sm_count, CPAD);  // one CTA per SM
     for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);

@@ -101,7 +101,6 @@ struct KrylovParams {
     int dscratch_off;  // byte offset of the dense mat-vec reduction scratch in dynamic shared memory
     uint4 *llpkt;      // single-GPU packet all-reduce inboxes [2 parities][LLQ][CPAD dest CTA][CPAD source rank]
     uint4 *llloc;      // row-sharded XL: this GPU's local packet inbox [2 parities][LLQ][CPAD source CTAs] (in the comm buffer)
-    int lz_order;      // one-reduction Lanczos instance: the producer streams the chunks in S->chunk_order (local first)
     int xl;            // XL instance: the current basis vector's slice stays in shared memory (second w-sized buffer)
     // row sharding across GPUs (krylov_kernel_tma.cuh; nranks == 1: single GPU, peers point to local buffers).
     // Every CTA of every GPU writes its partial sums into the inbox of EVERY GPU (peer stores over NVLink) and

@@ -47,10 +47,7 @@ struct __align__(128) SmemTma {
     int chunk_a0[MAXCH2];
     int chunk_cnt[MAXCH2];
     int slot_a0[MAXSLOT];
-    int chunk_local[MAXCH2];  // XL: every column of the chunk lies in this CTA's slice (learnt by the first mat-vec;
-                              // one-reduction Lanczos instance: found by the prologue scan)
-    int chunk_order[MAXCH2];  // one-reduction Lanczos instance: chunk indices, local chunks first
-    int nloc_chunks;
+    int chunk_local[MAXCH2];  // XL: every column of the chunk lies in this CTA's slice (learnt by the first mat-vec)
     double bc[2];             // reduced scalars (squared norm) broadcast to the CTA
     double llv[LLQ][CPAD];    // packets of a fused barrier + all-reduce (ll_collect), one value per CTA of the team
     // Flags the producer lane polls while the consumers run (single writer, single reader).  flag_set / flag_get are
@@ -241,9 +238,7 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
             long long pt_acq = 0;
             const long long pt_begin = clock64();
 #endif
-            for (int ci = 0; ci < G.nch; ++ci) {
-                // (one-reduction Lanczos instance: local chunks first, in the order the consumers take them)
-                const int c = (P.lz_order && G.nch <= MAXCH2) ? S->chunk_order[ci] : ci;
+            for (int c = 0; c < G.nch; ++c) {
 #ifdef B200K_PHASE_TIMING
                 const long long pa0 = clock64();
                 const bool got = prod_acquire(S, rg, seq, lane);
@@ -1654,45 +1649,44 @@ __device__ void consumer_problem_xl(const KrylovParams &P, Cons &cx, const TmaGe
 }
 
 // =====================================================================================================================
-// One-reduction Lanczos step with a deferred publication barrier (short-window instance, Hermitian operators;
-// reference: lanczos_step!, arnoldi.jl:388-403)
+// One-reduction Lanczos step (short-window instance, Hermitian operators; reference: lanczos_step!, arnoldi.jl:388-403)
 // =====================================================================================================================
-// The two-reduction step waits for an all-reduce twice per step: alpha = <v_j, A v_j> after the mat-vec, then ||w||^2
-// after the update -- each a full latency chain over the team (4-6 k cycles on one GPU, 7-8 us over NVLink); the second
-// one is also the barrier that publishes the updated vector to the CTAs that gather entries of it.  Here:
-//  * ONE all-reduce per step, after the mat-vec, carries
-//        S = <X_j, A v_j> (-> alpha),  Q = ||w'||^2,  G = <X_j, w'>,  N = ||X_j||^2,    w' = A v_j - beta_{j-1} v_{j-1},
-//    and beta_j^2 = ||w' - alpha v_j||^2 = Q - 2 alpha g + alpha^2 nu  (g = xscale G, nu = xscale^2 N = ||v_j||^2,
-//    alpha = xscale S / nu).  nu is what makes this usable: v_j was normalised with the PREDICTED beta_{j-1}, so
-//    ||v_j|| = 1 + O(eps Q / beta^2); assuming nu = 1 feeds that error back into the next prediction and it grows ~4x per
-//    step (garbage after 25 steps -- found by the parity tests); with the measured nu every prediction is exact for the
-//    vector actually used and the error stays at rounding level (1e-14 after 100 steps).  A cancellation guard --
-//    beta^2 < Q / 100, which is also where breakdown decisions are taken -- falls back to an explicit norm reduction.
-//  * What is left of the second reduction is a PUBLICATION BARRIER for the gather-buffer copy of X_{j+1} (and, row-sharded,
-//    the halo rows pushed to the peers).  It is published after the update but only waited for in the middle of the next
-//    mat-vec: the chunks whose columns all lie in the CTA's own slice (for stencil-like operators: all but the first and
-//    last) read the resident vector out of shared memory and run first; the barrier is collected before the few
-//    boundary chunks.  Its latency -- an L2 round trip on one GPU, a two-level NVLink exchange when row-sharded -- is
-//    hidden behind the local part of the mat-vec.  The producer streams the chunks in the same order (local first); which
-//    chunks are local is found by a scan of the slice's column indices in the kernel prologue.
-//  * The p augmented tail rows of kiops are kept redundantly by every CTA in shared memory (every CTA applies the same
-//    update with the same reduced scalars).
+// The two-reduction step above waits for an all-reduce twice: alpha = <v_j, A v_j>, then ||w||^2 after the update --
+// each a full latency chain over the team (4-6 k cycles on one GPU, 7-8 us over NVLink), and the second one is also the
+// barrier that publishes the updated vector to the CTAs that gather it.  Here ONE all-reduce per step carries
+//     S = <X_j, A v_j> (-> alpha),   Q = ||w'||^2,   G = <X_j, w'>,   N = ||X_j||^2      with  w' = A v_j - beta_{j-1} v_{j-1},
+// and ||w' - alpha v_j||^2 = Q - 2 alpha g + alpha^2 nu gives beta_j without a second pass (g = xscale G,
+// nu = xscale^2 N = ||v_j||^2, alpha = xscale S / nu).  nu is what makes this usable: v_j was normalised with the
+// PREDICTED beta_{j-1}, so ||v_j|| = 1 + O(eps Q / beta^2); assuming nu = 1 feeds that error back into the next
+// prediction and it grows ~4x per step (measured: garbage after 25 steps); with the measured nu every prediction is
+// exact for the vector actually used and the error stays at rounding level (1e-14 after 100 steps).  A cancellation
+// guard -- beta^2 < Q / 100, which is also where breakdown decisions are taken -- falls back to an explicit norm
+// reduction.  Used for row-sharded operators (an all-reduce over NVLink costs 7-8 us); on one GPU the release fence
+// behind 54 KB of gather-buffer stores per CTA makes the single reduction as expensive as the two it replaces.  What the second reduction used to publish is reconstructed by the
+// readers instead: w' is written to a gather buffer DURING the mat-vec (published by the step's single all-reduce),
+// and a CTA that needs entry c of the next vector outside its own slice forms
+//     X_{j+1}[c] = w'_j[c] - (alpha_j xscale_j) X_j[c]
+// from two published arrays (GW = w' and GX = X, both double buffered by step parity; X_{j+1} is stored to GX during
+// the local update and becomes visible with the NEXT all-reduce, one step before anyone needs it).  For stencil-like
+// operators only the few out-of-slice entries pay the second load.  The p augmented tail rows of kiops are kept
+// redundantly by every CTA in shared memory (every CTA applies the same update with the same reduced scalars).
 template <bool AUG, int GW>
-__device__ void matvec_xl1(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *xg, double xscale, bool fold,
-                           double foldc, int i0, int i1, bool local_only, double &sacc, double &qacc, double &gacc,
-                           double &nacc) {
+__device__ void matvec_xl1(const KrylovParams &P, Cons &cx, const TmaGeom &G, const double *gw, const double *gx,
+                           double gam, double xscale, bool learn, bool fold, double foldc, double *gwout,
+                           double &sacc, double &qacc, double &gacc, double &nacc) {
     SmemTma *S = cx.S;
     const int tid = cx.tid;
     const int p = AUG ? P.p : 0;
     const uint32_t ws_a = cx.ws_a, xin_a = cx.xin_a;
     const uint32_t xl_a = xin_a - 8u * (uint32_t)G.r0;  // shared address of x(column) for own-slice columns
     const int nnz_cap = P.nnz_cap;
-    double s1 = sacc, q1 = qacc, g1 = gacc, n1 = nacc;
-    for (int i = i0; i < i1; ++i) {
-        const int c = G.nch <= MAXCH2 ? S->chunk_order[i] : i;
+    double s1 = 0.0, q1 = 0.0, g1 = 0.0, n1 = 0.0;
+    for (int c = 0; c < G.nch; ++c) {
         const int rl = c * P.ch_rows + tid;
         const bool active = tid < P.ch_rows && rl < G.nrows;
+        const bool fast = !learn && c < MAXCH2 && S->chunk_local[c] != 0;
         cx.wait_full();
+        bool loc = true;
         if (active) {
             const unsigned char *base = cx.rg.ptr();
             const double *vs = reinterpret_cast<const double *>(base);
@@ -1701,7 +1695,7 @@ __device__ void matvec_xl1(const KrylovParams &P, Cons &cx, const TmaGeom &G, co
             const int a0 = S->slot_a0[cx.rg.slot];
             const int e0 = rp[tid] - a0, e1 = rp[tid + 1] - a0;
             double sum = 0.0;
-            if (local_only) {
+            if (fast) {
 #pragma unroll 1
                 for (int eb = e0; eb < e1; eb += GW) {
                     double av[GW], xv[GW];
@@ -1727,8 +1721,10 @@ __device__ void matvec_xl1(const KrylovParams &P, Cons &cx, const TmaGeom &G, co
                         if (ok) {
                             const int col = cs[eb + u];
                             const unsigned lc = (unsigned)(col - G.r0);
-                            if (lc < (unsigned)G.nrows) xv[u] = lds1(xin_a + 8u * lc);
-                            else xv[u] = xg[col];
+                            const bool here = lc < (unsigned)G.nrows;
+                            loc = loc && here;
+                            if (here) xv[u] = lds1(xin_a + 8u * lc);
+                            else xv[u] = fma(-gam, gx[col], gw[col]);  // X_j[col] rebuilt from the two published arrays
                         }
                     }
 #pragma unroll
@@ -1747,6 +1743,10 @@ __device__ void matvec_xl1(const KrylovParams &P, Cons &cx, const TmaGeom &G, co
             q1 = fma(wv, wv, q1);
             g1 = fma(xr, wv, g1);
             sts1(ws_a + 8u * (uint32_t)rl, wv);
+            gwout[G.r0 + rl] = wv;
+        }
+        if (learn && c < MAXCH2) {
+            if (!__all_sync(0xffffffffu, loc) && cx.lane == 0) S->chunk_local[c] = 0;
         }
         cx.release();
     }
@@ -1770,21 +1770,25 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
     const int units = G.nrows >> 1;
     const bool sharded = P.nranks > 1;
     const double *lpartn = P.peer_partn[P.myrank];
-    // gather buffers of this team: XB(par) holds the unnormalised X_j with j & 1 == par
-    auto XB = [&](int par) { return xbase + (long long)par * P.xlen; };
-    auto XBo = [&](int par) { return xoffbase + (long long)par * P.xlen; };
-    const int nch = G.nch;
-    const int nlc = nch <= MAXCH2 ? S->nloc_chunks : 0;  // local chunks come first in S->chunk_order
+    const int xt = n + P.nhalo;  // offset of the augmented tail in a gather buffer (only the staging of step 1 uses it)
+    // gather buffers of this team: GW[par] = w' of the step with parity par, GX[par] = X_j with j & 1 == par
+    auto GWb = [&](int par) { return xbase + (long long)par * P.xlen; };
+    auto GXb = [&](int par) { return xbase + (long long)(2 + par) * P.xlen; };
+    auto GWo = [&](int par) { return xoffbase + (long long)par * P.xlen; };
+    auto GXo = [&](int par) { return xoffbase + (long long)(2 + par) * P.xlen; };
+    if (nlocal == 0)
+        for (int c = tid; c < MAXCH2; c += NTC) S->chunk_local[c] = 1;
 
     // ---- X_1: b (firststep!, arnoldi.jl:230-250 / 257-279) or the normalised first column of a resumed subspace
     const double *src1;  // out-of-slice entries of X_1 are read from here
     double xscale;
+    // X_1 is always stored to GX[1]: step 2 rebuilds out-of-slice entries of X_2 from w'_1 and X_1
     if (P.j0 == 0) {
         double nrm = 0.0;
         for (int i = tid; i < units; i += NTC) {
             const double2 b2 = reinterpret_cast<const double2 *>(b + G.r0)[i];
             sts2(cx.xin_a + 16u * (uint32_t)i, b2);
-            reinterpret_cast<double2 *>(XB(1) + G.r0)[i] = b2;
+            reinterpret_cast<double2 *>(GXb(1) + G.r0)[i] = b2;
             nrm = fma(b2.x, b2.x, fma(b2.y, b2.y, nrm));
         }
         if (p > 0 && tid < p) {
@@ -1795,7 +1799,7 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
         const long long pslot = partn0 + (long long)(2 + (nlocal & 1)) * P.cpad;
         block_sum_to_c(P, cx, nrm, pslot + tm.rank);
         if (sharded) {
-            double *t = cx.ws; cx.ws = cx.xin; push_halo(P, cx, G, tm, XBo(1)); cx.ws = t;
+            double *t = cx.ws; cx.ws = cx.xin; push_halo(P, cx, G, tm, GXo(1)); cx.ws = t;
         }
         team_reduce_c(P, cx, tm, lpartn + pslot, 1, S->bc, sharded);
         const double beta = sqrt(S->bc[0]);
@@ -1809,71 +1813,65 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
             }
             return;
         }
-        src1 = XB(1);  // (published by the reduction above)
+        src1 = GXb(1);  // (published by the reduction above)
         xscale = 1.0 / beta;
     } else {
         const double *vj = V;  // lanczos! restarts at column 1 (it ignores init, arnoldi.jl:480)
         for (int i = tid; i < units; i += NTC) {
             const double2 v2 = reinterpret_cast<const double2 *>(vj + G.r0)[i];
             sts2(cx.xin_a + 16u * (uint32_t)i, v2);
-            if (sharded) reinterpret_cast<double2 *>(XB(1) + G.r0)[i] = v2;
+            reinterpret_cast<double2 *>(GXb(1) + G.r0)[i] = v2;  // (visible to the team from step 2 on)
         }
         if (p > 0 && tid < p) S->xtail[tid] = vj[n + tid];
         if (sharded) {
             block_sum_to_c(P, cx, 0.0, partn0 + 2LL * P.cpad + tm.rank);  // (has the CTA barrier the push needs)
-            double *t = cx.ws; cx.ws = cx.xin; push_halo(P, cx, G, tm, XBo(1)); cx.ws = t;
+            double *t = cx.ws; cx.ws = cx.xin; push_halo(P, cx, G, tm, GXo(1)); cx.ws = t;
             team_reduce_c(P, cx, tm, lpartn + partn0 + 2LL * P.cpad, 1, S->bc, true);
-            src1 = XB(1);
+            src1 = GXb(1);
         } else {
             consumer_sync();
             src1 = vj;
         }
         xscale = 1.0;
     }
+    (void)xt;
 
-    double beta_prev = 0.0, xscale_prev = 0.0, beta = 0.0;
+    double beta_prev = 0.0, xscale_prev = 0.0, gam = 0.0, beta = 0.0;
     int m_out = P.m, breakdown = 0, nfall = 0;
     const bool lazy_v1 = P.j0 == 0;  // (a resumed first column is already in V)
     for (int j = 1; j <= P.m; ++j) {
         const int jc = j - 1;
         const int par = j & 1, parp = par ^ 1;
         const bool fold = j > 1;
-        const double foldc = beta_prev * xscale_prev;
         PT_MARK(blockIdx.x, j, 0);
         // ---- tail rows of w' (every CTA keeps them): (K x)_k = x_{k+1}, last row 0
-        double sacc = 0.0, qacc = 0.0, gacc = 0.0, nacc = 0.0;
+        double st = 0.0, qt = 0.0, gt = 0.0, nt0 = 0.0;
         if (p > 0) {
             consumer_sync();
             if (tid < p) {
                 double wt = (tid < p - 1) ? S->xtail[tid + 1] * xscale : 0.0;
-                const double xt = S->xtail[tid];
-                const bool mine = tm.rank == 0 && P.myrank == 0;  // counted once
-                if (mine) {
-                    sacc = xt * wt;
-                    nacc = xt * xt;
-                }
-                if (fold) wt = fma(-foldc, S->ptail[tid], wt);
-                if (mine) {
-                    qacc = wt * wt;
-                    gacc = xt * wt;
-                }
+                st = S->xtail[tid] * wt;
+                nt0 = S->xtail[tid] * S->xtail[tid];
+                if (fold) wt = fma(-(beta_prev * xscale_prev), S->ptail[tid], wt);
+                qt = wt * wt;
+                gt = S->xtail[tid] * wt;
                 S->wtail[tid] = wt;
             }
+            if (!(tm.rank == 0 && P.myrank == 0)) st = qt = gt = nt0 = 0.0;  // counted once
         }
-        // ---- mat-vec, local chunks first; the publication barrier of the previous update is collected in between
-        matvec_xl1<AUG, GW>(P, cx, G, nullptr, xscale, fold, foldc, 0, nlc, true, sacc, qacc, gacc, nacc);
-        PT_MARK(blockIdx.x, j, 9);
-        if (j > 1) {
-            if (!sharded) ll_collect(P, cx, tm, 1, S->bc, true);
-            else shard_collect(P, cx, tm, 1, S->bc, true);
-        }
-        PT_MARK(blockIdx.x, j, 10);
-        matvec_xl1<AUG, GW>(P, cx, G, j == 1 ? src1 : XB(par), xscale, fold, foldc, nlc, nch, false, sacc, qacc, gacc, nacc);
+        double sacc, qacc, gacc, nacc;
+        matvec_xl1<AUG, GW>(P, cx, G, j == 1 ? src1 : GWb(parp), j == 1 ? src1 : GXb(parp), j == 1 ? 0.0 : gam, xscale,
+                            nlocal == 0 && j == 1, fold, beta_prev * xscale_prev, GWb(par), sacc, qacc, gacc, nacc);
+        sacc += st;
+        qacc += qt;
+        gacc += gt;
+        nacc += nt0;
         PT_MARK(blockIdx.x, j, 1);
         PT_MARK(blockIdx.x, j, 2);
-        // ---- the step's all-reduce of (S, Q, G, N)
+        // ---- the step's single all-reduce (release / acquire: publishes the w' stores, the previous update's X stores
+        // and, row-sharded, the halo rows pushed to the peers)
         {
-            const double v0 = warp_sum(sacc), v1 = warp_sum(qacc), v2 = warp_sum(gacc), v3 = warp_sum(nacc);
+            double v0 = warp_sum(sacc), v1 = warp_sum(qacc), v2 = warp_sum(gacc), v3 = warp_sum(nacc);
             if (cx.lane == 0) {
                 S->red[0][cx.warp][0] = v0;
                 S->red[0][cx.warp][1] = v1;
@@ -1881,6 +1879,12 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
                 S->red[0][cx.warp][3] = v3;
             }
             consumer_sync();  // (also: the whole w' slice of this CTA is in place)
+            bool pushed = false;
+            if (sharded) {
+                pushed = P.send_ofs[tm.rank + 1] > P.send_ofs[tm.rank];
+                push_halo(P, cx, G, tm, GWo(par));
+                consumer_sync();
+            }
             if (cx.warp == 0) {
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
@@ -1891,12 +1895,12 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
                     s3 += S->red[0][w][3];
                 }
                 if (!sharded) {
-                    ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 0, s0, cx.lane, false);
+                    ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 0, s0, cx.lane, true);
                     ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 1, s1, cx.lane, false);
                     ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 2, s2, cx.lane, false);
                     ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 3, s3, cx.lane, false);
                 } else {
-                    shard_publish_warp(P, tm, cx.seq + 1u, 0, s0, cx.lane, false, false);
+                    shard_publish_warp(P, tm, cx.seq + 1u, 0, s0, cx.lane, true, pushed);
                     shard_publish_warp(P, tm, cx.seq + 1u, 1, s1, cx.lane, false, false);
                     shard_publish_warp(P, tm, cx.seq + 1u, 2, s2, cx.lane, false, false);
                     shard_publish_warp(P, tm, cx.seq + 1u, 3, s3, cx.lane, false, false);
@@ -1915,20 +1919,20 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
             if (p > 0 && tm.rank == 0 && tid < p) V[(long long)jc * ldv + n + tid] = S->xtail[tid] * xscale;
         }
         PT_MARK(blockIdx.x, j, 8);
-        if (!sharded) ll_collect(P, cx, tm, 4, S->hs, false);
-        else shard_collect(P, cx, tm, 4, S->hs, false);
+        if (!sharded) ll_collect(P, cx, tm, 4, S->hs, true);
+        else shard_collect(P, cx, tm, 4, S->hs, true);
         PT_MARK(blockIdx.x, j, 3);
         const double nu = xscale * xscale * S->hs[3];  // ||v_j||^2 as actually used (1 + O(eps))
         const double alpha = S->hs[0] * xscale / nu, Q = S->hs[1], g = S->hs[2] * xscale;
         double beta2 = (Q - 2.0 * alpha * g) + alpha * alpha * nu;
         const bool fallback = !(beta2 > 0.01 * Q);  // cancellation (or NaN): take the norm explicitly
         consumer_sync();  // S->hs is rewritten by the next collect
-        // ---- local update X_{j+1} = w' - alpha v_j: shared memory + the gather buffer XB((j+1) & 1)
+        // ---- local update X_{j+1} = w' - alpha v_j (shared memory + GX[(j+1) & 1]); no reduction needed
         const double coef = alpha * xscale;
         double nrm = 0.0;
         {
             const uint32_t ws_a = cx.ws_a, xin_a = cx.xin_a;
-            double2 *xo2 = reinterpret_cast<double2 *>(XB(parp) + G.r0);
+            double2 *xo2 = reinterpret_cast<double2 *>(GXb(parp) + G.r0);
             for (int i = tid; i < units; i += NTC) {
                 double2 w2 = lds2(ws_a + 16u * (uint32_t)i);
                 const double2 x2 = lds2(xin_a + 16u * (uint32_t)i);
@@ -1950,6 +1954,10 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
             consumer_sync();
             if (tid < p) S->xtail[tid] = S->wtail[tid];
         }
+        if (sharded) {  // halo rows of X_{j+1}: published by the NEXT step's all-reduce, needed one step after that
+            consumer_sync();
+            push_halo(P, cx, G, tm, GXo(parp));
+        }
         PT_MARK(blockIdx.x, j, 4);
         if (fallback) {  // (uniform: every CTA of every rank sees the same reduced values)
             const double v = warp_sum(nrm);
@@ -1967,27 +1975,8 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
             beta2 = S->bc[0];
             ++nfall;
         }
-        beta = sqrt(beta2);
-        if (beta < P.tol) {
-            m_out = j;
-            breakdown = 1;
-        }
-        const bool last = breakdown || j == P.m;
-        // ---- publication barrier for XB((j+1) & 1) (+ halo rows): published now, collected inside the next mat-vec
-        if (!last) {
-            consumer_sync();  // every thread's gather-buffer stores are issued
-            bool pushed = false;
-            if (sharded) {
-                pushed = P.send_ofs[tm.rank + 1] > P.send_ofs[tm.rank];
-                push_halo(P, cx, G, tm, XBo(parp));
-                consumer_sync();
-            }
-            if (cx.warp == 0) {
-                if (!sharded) ll_publish_warp(P, cx.team, tm, cx.seq + 1u, 0, 0.0, cx.lane, true);
-                else shard_publish_warp(P, tm, cx.seq + 1u, 0, 0.0, cx.lane, true, pushed);
-            }
-        }
         PT_MARK(blockIdx.x, j, 5);
+        beta = sqrt(beta2);
         if (tm.rank == 0 && tid == 0) {
             Hd[(long long)jc * ldh + jc] = alpha;
             Hd[(long long)jc * ldh + jc + 1] = beta;
@@ -1997,10 +1986,15 @@ __device__ void consumer_problem_xl1(const KrylovParams &P, Cons &cx, const TmaG
             const uint32_t ta = cx.ws_a; cx.ws_a = cx.xin_a; cx.xin_a = ta;
         }
         PT_MARK(blockIdx.x, j, 6);
+        gam = coef;
         xscale_prev = xscale;
         xscale = 1.0 / beta;
         beta_prev = beta;
-        if (last) {
+        if (beta < P.tol) {
+            m_out = j;
+            breakdown = 1;
+        }
+        if (breakdown || j == P.m) {
             // epilogue: v_{j+1} = X_{j+1} / beta (true division: beta may be tiny on breakdown, arnoldi.jl:306)
             consumer_sync();
             double *vn = V + (long long)(jc + 1) * ldv;
@@ -2060,31 +2054,6 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_kernel(const __grid_constan
             const int a0 = e0 & ~3;
             S->chunk_a0[c] = a0;
             S->chunk_cnt[c] = ((e1 + 3) & ~3) - a0;
-        }
-    }
-    if constexpr (LZ1) {
-        // which chunks read nothing outside this CTA's own slice (one warp per chunk scans its column indices)
-        if (G.nch <= MAXCH2) {
-            for (int c = tid >> 5; c < G.nch; c += NT2 / 32) {
-                const int rs = G.r0 + c * P.ch_rows;
-                const int re = min(G.r0 + G.nrows, rs + P.ch_rows);
-                bool loc = true;
-                for (int e = P.rowptr[rs] + (tid & 31); e < P.rowptr[re]; e += 32)
-                    loc = loc && (unsigned)(P.colind[e] - G.r0) < (unsigned)G.nrows;
-                loc = __all_sync(0xffffffffu, loc);
-                if ((tid & 31) == 0) S->chunk_local[c] = loc ? 1 : 0;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int k = 0;
-                for (int c = 0; c < G.nch; ++c)
-                    if (S->chunk_local[c]) S->chunk_order[k++] = c;
-                S->nloc_chunks = k;
-                for (int c = 0; c < G.nch; ++c)
-                    if (!S->chunk_local[c]) S->chunk_order[k++] = c;
-            }
-        } else if (tid == 0) {
-            S->nloc_chunks = 0;
         }
     }
     if (tid == 0) {
