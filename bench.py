@@ -19,11 +19,12 @@ small dense exp(tH)e1, and the projection w = beta V y.
 
 After the headline the same run measures, under "also" (each with an in-run parity check against the CPU oracle):
     lanczos   the reference's default dispatch for this symmetric operator, with its own roofline (rank 0)
+    complex   SURVEY 8(f)-2: ComplexF64 operators of the headline size, general (Arnoldi) and Hermitian (Lanczos)
     c5        BASELINE configs[4]: 1024 independent (t_i, v_i), Laplacian 250x400 (n = 1e5), split over the ranks
     c2s       N >= 2: configs[1] as ONE problem row-sharded over the N GPUs (in-kernel NVLink halo + all-reduce)
     c3s       N >= 2: configs[2] (phiv K = 4, dense n = 16384) with the dense operator in row blocks over the N GPUs
     c4        N == 8: configs[3]: kiops, Laplacian 2500x4000 (n = 1e7), row-sharded over the 8 GPUs
-`--also lanczos,c5,c2s,c3s,c4,none` overrides the default selection.
+`--also lanczos,complex,c5,c2s,c3s,c4,none` overrides the default selection.
 
 The headline path is full Arnoldi (ishermitian=false), the north-star kernel; --path lanczos times the
 reference's default dispatch for this (symmetric) operator as the headline instead.
@@ -157,12 +158,26 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+try:
+    ORIG_AFFINITY = os.sched_getaffinity(0)
+except Exception:
+    ORIG_AFFINITY = None
+
+
 class all_host_threads:
     """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline must still get every host core
-    (the BLAS-1 calls of the port are threaded by OpenBLAS, exactly as in the Julia package)."""
+    (the BLAS-1 calls of the port are threaded by OpenBLAS, exactly as in the Julia package).  The GPU arm narrows the
+    process to the socket next to its GPU (parallel.bind_host_near_gpu); the CPU legs run on the original mask."""
 
     def __enter__(self):
         self.ctx = None
+        self.narrow = None
+        try:
+            if ORIG_AFFINITY is not None and os.sched_getaffinity(0) != ORIG_AFFINITY:
+                self.narrow = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, ORIG_AFFINITY)
+        except Exception:
+            self.narrow = None
         try:
             from threadpoolctl import threadpool_limits
             self.ctx = threadpool_limits(limits=host_threads())
@@ -174,6 +189,11 @@ class all_host_threads:
     def __exit__(self, *a):
         if self.ctx is not None:
             self.ctx.__exit__(*a)
+        if self.narrow is not None:
+            try:
+                os.sched_setaffinity(0, self.narrow)
+            except Exception:
+                pass
 
 
 def blas_threads():
@@ -285,6 +305,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 engine has no CPU path)")
     torch.cuda.set_device(local_rank)
+    from eu_b200 import parallel as eu_parallel
+    host_binding = eu_parallel.bind_host_near_gpu(local_rank)  # (before any pinned allocation)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -293,7 +315,7 @@ def main():
     eng = eu.get_engine(local_rank)
 
     if args.also == "auto":
-        also_set = {"lanczos", "c5"} | ({"c2s", "c3s"} if world >= 2 else set()) | ({"c4"} if world == 8 else set())
+        also_set = {"lanczos", "c5", "complex"} | ({"c2s", "c3s"} if world >= 2 else set()) | ({"c4"} if world == 8 else set())
     else:
         also_set = {s for s in args.also.split(",") if s and s != "none"}
 
@@ -431,7 +453,9 @@ def main():
                                        "note": "synchronous b200k_expv_host: H2D -> kernels -> D2H serialised per call "
                                                "(CUDA events)"},
                 "pipelined_results_agree": pipe_check,
-                "note": "through the C ABI with HOST buffers; operator resident (uploaded once at ingestion)"},
+                "host_binding": host_binding,
+                "note": "through the C ABI with HOST buffers; operator resident (uploaded once at ingestion); the rank's "
+                        "host threads and pinned buffers sit on the NUMA node of its GPU (host_binding)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": kname.get(headline_kernel, "?"), "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -472,6 +496,42 @@ def main():
             sec["parity_rel_err_vs_oracle"] = relerr(step_other().cpu().numpy(), w_ref)
         also[f"{other}_expv_per_s_one_gpu"] = sec["expv_per_s_one_gpu"]  # (round-1 key, kept)
         also[other] = sec
+
+    # ------------------------------------------------------------------------------------------------------
+    # also.complex: SURVEY 8(f)-2 -- ComplexF64 operators of the headline size (n = 1e6, m = 30): a general complex one
+    # (Arnoldi) and a Hermitian one (Schroedinger-type propagation exp(-i t H) psi, Lanczos with real coefficients)
+    # ------------------------------------------------------------------------------------------------------
+    if "complex" in also_set:
+        import scipy.sparse as sp
+        Hs = (-1.0 * A).astype(np.complex128).tocsr()
+        Az = (A.astype(np.complex128) + sp.diags([0.3j * np.ones(n - 1), 0.3j * np.ones(n - 1)], [1, -1])).tocsr()
+        rngz = np.random.default_rng(12 + rank)
+        psi_h = rngz.standard_normal(n) + 1j * rngz.standard_normal(n)
+        psi = torch.from_numpy(psi_h).to(dev)
+        secz = {"n": n, "m": M, "byte_model": "BASELINE.md 3 with 16-byte vector elements and 20 bytes per stored entry"}
+        for name, Mz, tz in (("general_arnoldi", Az, 0.5), ("hermitian_lanczos", Hs, -0.5j)):
+            opz = eu.operator(Mz)
+
+            def stepz():
+                return eu.expv(tz, opz, psi, m=M)
+
+            ms_z = timed(stepz, 10, 3) / 10
+            kz, pz = kernel_times(stepz, 5)
+            S_Az = 20 * Mz.nnz + 4 * (n + 1)
+            Bz = (30 * (S_Az + 48 * n) + 32 * n) if opz.ishermitian else (30 * (S_Az + 32 * n) + 16 * n * 30 * 31 + 32 * n)
+            ez = {"ms_per_expv": ms_z, "expv_per_s_one_gpu": 1e3 / ms_z, "kernel": eng.last_kernel(), "kernel_ms": kz,
+                  "roofline": {"bound": "hbm", "achieved": Bz / (kz * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": Bz / (kz * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": Bz}}
+            if rank == 0 and not args.no_cpu_baseline:
+                from oracle import oracle as O
+                with all_host_threads():
+                    t0 = time.perf_counter()
+                    wz = O.expv(tz, Mz, psi_h, m=M)
+                    ez["cpu_oracle_s"] = time.perf_counter() - t0
+                ez["parity_rel_err_vs_oracle"] = relerr(stepz().cpu().numpy(), wz)
+            secz[name] = ez
+            del opz
+        also["complex"] = secz
 
     # ------------------------------------------------------------------------------------------------------
     # also.c5: BASELINE configs[4] -- 1024 independent (t_i, v_i) on a shared Laplacian 250x400, split over the ranks

@@ -87,11 +87,11 @@ class Engine:
         self.check(self.lib.b200k_set_flag(self.handle, flag, int(value)))
 
     def last_kernel(self):
-        """'ldg' (krylov_persistent_kernel), 'tma' (krylov_tma_kernel), 'tma_xl' (its short-window instance) or 'z'
-        (complex kernel) for the last factorisation."""
+        """'ldg' (krylov_persistent_kernel), 'tma' (krylov_tma_kernel), 'tma_xl' (its short-window instance), 'z'
+        (complex LDG kernel) or 'tma_z' (complex kernel on the TMA ring) for the last factorisation."""
         w = C.c_int()
         self.check(self.lib.b200k_last_kernel(self.handle, C.byref(w)))
-        return {1: "ldg", 2: "tma", 3: "z", 4: "tma_xl", 5: "tma_mv", 6: "tma_xl1"}.get(w.value, "none")
+        return {1: "ldg", 2: "tma", 3: "z", 4: "tma_xl", 5: "tma_mv", 6: "tma_xl1", 7: "tma_z"}.get(w.value, "none")
 
     def last_timing(self):
         a, b = C.c_float(), C.c_float()

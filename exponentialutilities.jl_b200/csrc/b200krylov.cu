@@ -19,6 +19,7 @@
 #include "krylov_kernel_tma.cuh"
 #include "krylov_kernel_mv.cuh"
 #include "krylov_kernel_z.cuh"
+#include "krylov_kernel_tma_z.cuh"
 #include "smallexp_kernel.cuh"
 #include "smallmat.hpp"
 
@@ -1124,6 +1125,7 @@ int b200k_create(b200k_handle_t *out, int device, void *stream) {
     }
     if (const char *env = std::getenv("B200K_SMALLEXP")) h->host_smallexp = std::strcmp(env, "host") == 0 ? 1 : 0;
     cudaFuncSetAttribute((const void *)krylov_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    cudaFuncSetAttribute((const void *)krylov_tma_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     cudaFuncSetAttribute((const void *)small_exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          6 * SE_MAXM * SE_MAXM * 8);
     cudaFuncSetAttribute((const void *)small_exp_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2129,12 +2131,60 @@ int arnoldi_z_core(b200k_context *h, b200k_operator *op, const double *b, const 
     CK(h, cudaMemsetAsync(P.Hd, 0, (size_t)ldhd * (m + 1) * 16, h->stream));
     CK(h, cudaMemsetAsync(P.scal, 0, 32, h->stream));
     if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
+    // ---- kernel selection: the TMA-ring instance for CSR operators with short rows whose w slice fits next to >= 3
+    // ring slots (16-byte aligned bases; every complex element is one 16-byte unit, so no parity condition on n / ldv)
+    bool tma = false;
+    if (op->kind == 0 && !h->force_ldg && P.w_in_smem && ((uintptr_t)V & 15) == 0 && ((uintptr_t)b & 15) == 0) {
+        const int mrn = std::max(op->max_row_nnz, 1);
+        int ch_rows = (int)((SLOT_BYTES - 20 * 8 - 16) / (20LL * mrn + 4));
+        ch_rows = std::min(ch_rows, CHZ_ROWS_MAX) / 32 * 32;
+        const size_t wsb = (size_t)round_up((long long)g.slice * 16, 128);
+        const long long ring_room = (long long)SMEM_LIMIT - (long long)sizeof(SmemTmaZ) - (long long)wsb;
+        const int nslot = (int)std::min<long long>(ring_room / SLOT_BYTES, MAXSLOT);
+        if (ch_rows >= 64 && nslot >= 3) {
+            tma = true;
+            P.ch_rows = ch_rows;
+            P.nnz_cap = (int)round_up((long long)ch_rows * mrn + 8, 4);
+            P.nslot = nslot;
+            const int ntk0 = (g.slice + TILE_ROWS_Z - 1) / TILE_ROWS_Z;
+            P.tile_rows = (int)round_up((g.slice + ntk0 - 1) / ntk0, 16);
+            // L2 policy of the operator stream, as for the real kernel: evict_first once operator + two passes over the
+            // orthogonalisation window no longer fit in 3/4 of L2
+            P.hintA_cols = 1 << 30;
+            if (h->l2hint == 1) P.hintA_cols = 0;
+            else if (h->l2hint < 0) {
+                const double budget = 0.75 * (double)h->l2_bytes;
+                const double opb = 20.0 * (double)op->nnz + 4.0 * (double)(n + 1);
+                const double colb = 16.0 * (double)n;
+                const double cols = (budget - opb) / (2.0 * colb);
+                P.hintA_cols = cols < 1.0 ? 1 : (cols > 1e9 ? (1 << 30) : (int)cols);
+            }
+            smem = sizeof(SmemTmaZ) + wsb + (size_t)nslot * SLOT_BYTES;
+        }
+    }
     void *args[] = {(void *)&P};
-    CK(h, cudaLaunchCooperativeKernel((const void *)krylov_z_kernel, dim3(g.C), dim3(NT), args, smem, h->stream));
+    if (tma) {
+        CK(h, cudaLaunchCooperativeKernel((const void *)krylov_tma_z_kernel, dim3(g.C), dim3(NT2), args, smem, h->stream));
+        h->launches += 1;
+        if (!herm) {
+            // re-orthogonalisation check from the stored H (exits at once in the normal case), DESIGN 3.1e
+            KrylovParamsZ P2 = P;
+            P2.safe_scan = 1;
+            P2.op_kind = OP_CSR_WARP;
+            const size_t smem2 = sizeof(SmemZ) + (size_t)g.slice * 16;
+            void *args2[] = {(void *)&P2};
+            CK(h, cudaMemsetAsync(P.bar, 0, 4, h->stream));
+            CK(h, cudaLaunchCooperativeKernel((const void *)krylov_z_kernel, dim3(g.C), dim3(NT), args2, smem2, h->stream));
+            h->launches += 1;
+        }
+        h->last_kernel = 7;
+    } else {
+        CK(h, cudaLaunchCooperativeKernel((const void *)krylov_z_kernel, dim3(g.C), dim3(NT), args, smem, h->stream));
+        h->launches += 1;
+        h->last_kernel = 3;
+    }
     if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
     if (h->timing) { h->ev_k = true; h->ev_p = false; }
-    h->launches += 1;
-    h->last_kernel = 3;
     const size_t hbytes = (size_t)ldhd * (m + 1) * 16;
     CK(h, h->zHh.ensure(hbytes + 64));
     CK(h, h->scalh.ensure(64));

@@ -39,9 +39,20 @@ struct KrylovParamsZ {
     unsigned *bar;
     double2 *wglob;
     int w_in_smem;
+    // krylov_tma_z_kernel (krylov_kernel_tma_z.cuh) only
+    int nnz_cap;     // entries one ring slot holds (val 16 B | colind 4 B | rowptr segment)
+    int ch_rows;     // rows per CSR chunk (<= 256: two consumer lanes per row)
+    int nslot;       // ring depth
+    int tile_rows;   // complex rows per basis tile (multiple of 16, <= 2048)
+    int hintA_cols;  // operator chunks get L2::evict_first in steps whose window has >= this many columns
+    // krylov_z_kernel launched behind the TMA instance: find the first step whose update removed most of the vector
+    // from the stored H and redo the factorisation from there with the two-pass loop; exit at once if there is none
+    int safe_scan;
 };
 
 struct __align__(16) SmemZ {
+    int j0_found;
+    int pad_[3];
     double2 hs[MAXCOL];
     double2 red[2][NW][CB];
     double redn[NW];
@@ -113,7 +124,31 @@ __global__ void __launch_bounds__(NT, 1) krylov_z_kernel(const __grid_constant__
     int jstart;
     int m_out = P.m, breakdown = 0;
 
-    if (P.j0 == 0) {  // firststep!
+    int j0 = P.j0;
+    if (P.safe_scan) {
+        // H[j+1, j]^2 < eta^2 (||H[lo..j, j]||^2 + H[j+1, j]^2) (Pythagoras form of the DGKS test); columns the
+        // fast instance never reached are zero and never trigger, NaN never triggers
+        if (tid < 32) {
+            const int iopw0 = P.iop > 0 ? P.iop : P.m;
+            int first = 0x7fffffff;
+            for (int jc = tid; jc < P.m; jc += 32) {
+                double hsq = 0.0;
+                for (int i = max(0, jc - iopw0 + 1); i <= jc; ++i) {
+                    const double2 hv = P.Hd[(long long)jc * P.ldh + i];
+                    hsq = fma(hv.x, hv.x, fma(hv.y, hv.y, hsq));
+                }
+                const double bj = P.Hd[(long long)jc * P.ldh + jc + 1].x;
+                if (bj * bj < 0.0625 * (hsq + bj * bj)) first = min(first, jc + 1);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            if (tid == 0) S->j0_found = first == 0x7fffffff ? 0 : first;
+        }
+        __syncthreads();
+        j0 = S->j0_found;
+        if (j0 == 0) return;  // (every CTA takes the same decision: H is complete when this launch starts)
+    }
+    if (j0 == 0) {  // firststep!
         double nrm = 0.0;
         for (int i = tid; i < nrows; i += NT) {
             const double2 b1 = P.b[r0 + i];
@@ -143,9 +178,9 @@ __global__ void __launch_bounds__(NT, 1) krylov_z_kernel(const __grid_constant__
         xscale = inv;
         jstart = 1;
     } else {
-        xsrc = V + (long long)(P.j0 - 1) * ldv;
+        xsrc = V + (long long)(j0 - 1) * ldv;
         xscale = 1.0;
-        jstart = P.j0;
+        jstart = j0;
     }
 
     double beta_prev = 0.0;

@@ -15,6 +15,55 @@ import numpy as np
 from . import _lib
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index: int):
+    """(NUMA node, its CPUs) of the PCIe root the GPU hangs off, from sysfs; (None, set()) when the platform does not
+    say (single-socket hosts report -1)."""
+    import torch
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return None, set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            return node, _parse_cpulist(f.read())
+    except Exception:
+        return None, set()
+
+
+def bind_host_near_gpu(device_index: int):
+    """One process per GPU: run this rank's host threads on the socket its GPU is attached to, BEFORE the pinned
+    staging buffers are allocated (they are placed on the allocating thread's node), so that every H2D / D2H copy of the
+    end-to-end path crosses one PCIe root and no socket interconnect.  Without it the ranks whose GPU sits on the other
+    socket copy through remote memory and set the max-over-ranks time of a multi-GPU job.  Returns a small record for
+    the bench line; a no-op (and says so) when the node is unknown or the affinity mask cannot be narrowed."""
+    import os
+    node, cpus = gpu_numa_node(device_index)
+    rec = {"numa_node": node, "bound": False}
+    if node is None:
+        return rec
+    try:
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            rec["bound"] = True
+            rec["cpus"] = len(allowed)
+    except Exception:
+        pass
+    return rec
+
+
 def row_partition(n: int, world: int, align: int = 16):
     """Contiguous, `align`-row-aligned blocks: returns [(row0, nloc)] for every rank."""
     base = (n // world) // align * align

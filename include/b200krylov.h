@@ -299,7 +299,8 @@ int b200k_set_timing(b200k_handle_t h, int enabled);
 /* Which Krylov kernel the last factorisation used: 1 = LDG kernel (krylov_persistent_kernel, any layout),
  * 2 = TMA-ring kernel (krylov_tma_kernel; needs even n / ldv and 16-byte aligned bases), 3 = complex kernel,
  * 4 = the short-window (Lanczos / IOP) instance of the TMA-ring kernel (resident basis vector), 5 = the lock-step
- * multi-vector Lanczos kernel of batched expv, 6 = the short-window instance with the one-reduction Lanczos step.  The environment
+ * multi-vector Lanczos kernel of batched expv, 6 = the short-window instance with the one-reduction Lanczos step,
+ * 7 = the complex kernel on the TMA ring (krylov_tma_z_kernel; CSR operators with short rows).  The environment
  * variable B200K_KERNEL=ldg, read at b200k_create, forces 1 (A/B measurements). */
 int b200k_last_kernel(b200k_handle_t h, int *which);
 /* Runtime switches (A/B measurements and tests): B200K_FLAG_FORCE_LDG = 1 uses krylov_persistent_kernel even

@@ -359,3 +359,73 @@ def test_reorthogonalisation_in_a_batch_and_on_the_ldg_kernel(gpu, oracle):
     w = gpu.expv(0.01, Do, bo, m=30, ishermitian=False)
     assert gpu.get_engine().last_kernel() == "ldg"
     assert relerr(w, oracle.expv(0.01, Do, bo, m=30, ishermitian_=False)) < RTOL
+
+
+# ---- complex kernel on the TMA ring ------------------------------------------------------------------------------------
+def test_complex_kernel_on_the_tma_ring(gpu, oracle):
+    """krylov_tma_z_kernel (CSR operators with short rows): general complex Arnoldi, Hermitian Lanczos with real
+    coefficients, IOP window, continuation (init), happy breakdown, the re-orthogonalisation hand-over to the LDG kernel,
+    several chunks / basis tiles per CTA and an n that is not a multiple of anything; against the oracle and against the
+    LDG complex kernel (B200K_FLAG_FORCE_LDG)."""
+    import scipy.sparse as sp
+    import torch
+    eng = gpu.get_engine()
+    rng = np.random.default_rng(77)
+    for (nx, ny, m) in ((37, 53, 20), (400, 451, 30), (1000, 700, 12)):
+        n = nx * ny
+        L = laplacian2d(nx, ny)
+        Az = (L.astype(np.complex128) + sp.diags([0.3j * np.ones(n - 1), 0.2j * np.ones(n - 1)], [1, -1])).tocsr()
+        b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        w = gpu.expv(0.4 - 0.1j, Az, b, m=m)
+        assert eng.last_kernel() == "tma_z"
+        assert relerr(w, oracle.expv(0.4 - 0.1j, Az, b, m=m)) < RTOL
+        Ks = gpu.arnoldi(Az, b, m=m)
+        eng.set_flag("force_ldg", 1)
+        try:
+            Kl = gpu.arnoldi(Az, b, m=m)
+            assert eng.last_kernel() == "z"
+        finally:
+            eng.set_flag("force_ldg", 0)
+        assert np.abs(Ks.getH() - Kl.getH()).max() < 1e-11 * np.abs(Kl.getH()).max()
+        assert (Ks.getV() - Kl.getV()).abs().max().item() < 1e-11
+        # Hermitian: Lanczos, real coefficients
+        Hm = (L + 0.5 * sp.diags([1j * np.ones(n - 1), -1j * np.ones(n - 1)], [1, -1])).tocsr()
+        w = gpu.expv(-0.3j, Hm, b, m=m)
+        assert eng.last_kernel() == "tma_z"
+        assert relerr(w, oracle.expv(-0.3j, Hm, b, m=m)) < RTOL
+    # factorisation parity, IOP window and continuation on a mid-sized operator
+    n = 300 * 211
+    L = laplacian2d(300, 211)
+    Az = (L.astype(np.complex128) + sp.diags([0.3j * np.ones(n - 1), 0.2j * np.ones(n - 1)], [1, -1])).tocsr()
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    Ks = gpu.arnoldi(Az, b, m=16)
+    Ko = oracle.arnoldi(Az, b, m=16)
+    assert eng.last_kernel() == "tma_z" and Ks.m == Ko.m and abs(Ks.beta - Ko.beta) < 1e-12 * Ko.beta
+    assert np.abs(Ks.getH() - Ko.getH()).max() < 1e-11 and np.abs(Ks.getV().cpu().numpy() - Ko.getV()).max() < 1e-11
+    Ki = gpu.arnoldi(Az, b, m=16, iop=2)
+    Kio = oracle.arnoldi(Az, b, m=16, iop=2)
+    assert np.abs(Ki.getH() - Kio.getH()).max() < 1e-11
+    K2 = gpu.KrylovSubspace(n, 16, dtype=np.complex128)
+    gpu.arnoldi_(K2, Az, b, m=8)
+    gpu.arnoldi_(K2, Az, b, m=16, init=8)
+    assert np.abs(K2.getH() - Ks.getH()).max() < 1e-12 and (K2.getV() - Ks.getV()).abs().max().item() < 1e-12
+    # happy breakdown: b in a 3-dimensional invariant subspace of a diagonal operator
+    d = np.concatenate([-np.ones(4000), (-2 + 1j) * np.ones(4000), -3j * np.ones(4000)])
+    D = sp.diags(d).tocsr()
+    Kb = gpu.arnoldi(D, np.ones(12000) + 0j, m=10)
+    assert eng.last_kernel() == "tma_z" and Kb.m == 3 and Kb.wasbreakdown
+    bz = np.ones(12000) + 0j
+    assert relerr(gpu.expv(0.5, D, bz, m=10), np.exp(0.5 * d) * bz) < RTOL
+    # loss of orthogonality: the stored H fails the test, the LDG kernel redoes the tail with two passes
+    n = 2000
+    dc = np.concatenate([-np.ones(1000), -2 * np.ones(500), -1e3 * np.ones(500)]) + 1e-8 * rng.standard_normal(n)
+    Ac = (sp.diags(dc).astype(np.complex128) + 1e-3j * sp.diags(rng.standard_normal(n))).tocsr()
+    bc = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    w = gpu.expv(0.01, Ac, bc, m=30)
+    assert eng.last_kernel() == "tma_z"
+    assert relerr(w, oracle.expv(0.01, Ac, bc, m=30)) < RTOL
+    Kc = gpu.arnoldi(Ac, bc, m=30)
+    if not Kc.wasbreakdown:
+        V = Kc.getV()
+        G = (V.conj().t() @ V).cpu().numpy()
+        assert np.abs(G - np.eye(G.shape[0])).max() < 1e-12
