@@ -2136,18 +2136,37 @@ int arnoldi_z_core(b200k_context *h, b200k_operator *op, const double *b, const 
     bool tma = false;
     if (op->kind == 0 && !h->force_ldg && P.w_in_smem && ((uintptr_t)V & 15) == 0 && ((uintptr_t)b & 15) == 0) {
         const int mrn = std::max(op->max_row_nnz, 1);
-        int ch_rows = (int)((SLOT_BYTES - 20 * 8 - 16) / (20LL * mrn + 4));
-        ch_rows = std::min(ch_rows, CHZ_ROWS_MAX) / 32 * 32;
         const size_t wsb = (size_t)round_up((long long)g.slice * 16, 128);
         const long long ring_room = (long long)SMEM_LIMIT - (long long)sizeof(SmemTmaZ) - (long long)wsb;
-        const int nslot = (int)std::min<long long>(ring_room / SLOT_BYTES, MAXSLOT);
-        if (ch_rows >= 64 && nslot >= 3) {
+        // slot size = one basis tile; among the tilings of the slice pick the one with the most bytes in flight
+        // (fewer, larger tiles on ties: every tile costs one mbarrier round trip)
+        const int ntk0 = (g.slice + TILE_ROWS_Z - 1) / TILE_ROWS_Z;
+        int best_ntk = 0, best_slot = 0, best_nslot = 0;
+        long long best_inflight = 0;
+        for (int ntk = ntk0; ntk <= ntk0 + 3; ++ntk) {
+            const int tr = (int)round_up((g.slice + ntk - 1) / ntk, 16);
+            // (a slot also holds one CSR chunk: room for the 256 rows the consumers can work on at once, up to 32 KB)
+            const long long want_chunk = std::min<long long>(SLOT_BYTES, (long long)CHZ_ROWS_MAX * (20LL * mrn + 4) + 272);
+            const int sb = (int)round_up(std::max<long long>((long long)tr * 16, want_chunk), 128);
+            const int ns = (int)std::min<long long>(ring_room / sb, MAXSLOT);
+            if (ns < 3) continue;
+            const long long inflight = (long long)ns * tr * 16;
+            if (inflight > best_inflight + best_inflight / 16) {
+                best_inflight = inflight;
+                best_ntk = ntk;
+                best_slot = sb;
+                best_nslot = ns;
+            }
+        }
+        int ch_rows = best_slot > 0 ? (int)((best_slot - 20 * 12 - 32) / (20LL * mrn + 4)) : 0;
+        ch_rows = std::min(ch_rows, CHZ_ROWS_MAX) / 32 * 32;
+        if (ch_rows >= 64 && best_nslot >= 3) {
             tma = true;
             P.ch_rows = ch_rows;
             P.nnz_cap = (int)round_up((long long)ch_rows * mrn + 8, 4);
-            P.nslot = nslot;
-            const int ntk0 = (g.slice + TILE_ROWS_Z - 1) / TILE_ROWS_Z;
-            P.tile_rows = (int)round_up((g.slice + ntk0 - 1) / ntk0, 16);
+            P.nslot = best_nslot;
+            P.slot_bytes = best_slot;
+            P.tile_rows = (int)round_up((g.slice + best_ntk - 1) / best_ntk, 16);
             // L2 policy of the operator stream, as for the real kernel: evict_first once operator + two passes over the
             // orthogonalisation window no longer fit in 3/4 of L2
             P.hintA_cols = 1 << 30;
@@ -2159,7 +2178,7 @@ int arnoldi_z_core(b200k_context *h, b200k_operator *op, const double *b, const 
                 const double cols = (budget - opb) / (2.0 * colb);
                 P.hintA_cols = cols < 1.0 ? 1 : (cols > 1e9 ? (1 << 30) : (int)cols);
             }
-            smem = sizeof(SmemTmaZ) + wsb + (size_t)nslot * SLOT_BYTES;
+            smem = sizeof(SmemTmaZ) + wsb + (size_t)best_nslot * best_slot;
         }
     }
     void *args[] = {(void *)&P};

@@ -12,8 +12,9 @@
 //   [A chunks 0..nch-1]                 one slot = val (16 B / entry) | colind (4 B / entry) | rowptr segment
 //   [dots  : for cb in lo..hi step 8 : for k < ntk : for u < nb : basis tile (column cb+u, rows k)]
 //   [update: for k < ntk : for col = hi..ulo : basis tile (col, rows k)]
-// A basis tile holds <= 2048 complex rows (32 KB).  Two consumer lanes share a CSR row (even / odd entries), so a chunk
-// of <= 256 rows keeps all 512 consumer threads busy although a complex entry needs 20 bytes of slot space.
+// A basis tile holds <= 2048 complex rows (32 KB); the ring slots are sized to the tile (RingZ).  Two consumer lanes
+// share a CSR row (even / odd entries), so a chunk of <= 256 rows keeps all 512 consumer threads busy although a complex
+// entry needs 20 bytes of slot space.
 //
 // Scope: one problem per launch, CSR rows short enough for >= 64 rows per chunk, w slice resident in shared memory, no
 // augmentation, no row sharding; everything else stays on krylov_z_kernel.  This instance carries no DGKS code: like
@@ -45,11 +46,29 @@ struct __align__(128) SmemTmaZ {
     int stop_seq;    // consumers are done (1)
 };
 
+// Ring with a run-time slot size: the w slice of a complex problem takes twice the shared memory of a real one, so the
+// host sizes the slots to the basis tile (and the CSR chunk to the slot) instead of a fixed 32 KB -- one more slot in
+// flight at n = 10^6 (4 x 27 KB instead of 3 x 32 KB with 27 KB used).
+struct RingZ {
+    unsigned char *base;
+    int nslot;
+    int slot;
+    unsigned phase;
+    uint32_t slot_bytes;
+    __device__ __forceinline__ void advance() {
+        if (++slot == nslot) {
+            slot = 0;
+            phase ^= 1u;
+        }
+    }
+    __device__ __forceinline__ unsigned char *ptr() const { return base + (size_t)slot * slot_bytes; }
+};
+
 struct ConsZ {
     SmemTmaZ *S;
     double2 *ws;
     int tid, lane, warp;
-    Ring rg;
+    RingZ rg;
     __device__ __forceinline__ void wait_full() { mbar_wait(&S->full[rg.slot], rg.phase); }
     __device__ __forceinline__ void release() {
         __syncwarp();
@@ -58,7 +77,7 @@ struct ConsZ {
     }
 };
 
-__device__ __forceinline__ bool prodz_acquire(SmemTmaZ *S, const Ring &rg) {
+__device__ __forceinline__ bool prodz_acquire(SmemTmaZ *S, const RingZ &rg) {
     unsigned spins = 0;
     while (!mbar_try_wait(&S->empty[rg.slot], rg.phase ^ 1u)) {
         if ((++spins & 7u) == 0u && flag_get(&S->stop_seq) >= 1) return false;
@@ -73,7 +92,7 @@ __device__ __forceinline__ bool prodz_wait_col(SmemTmaZ *S, int col) {
 }
 
 // ---- producer (one lane) ----------------------------------------------------------------------------------------------
-__device__ void producer_z(const KrylovParamsZ &P, SmemTmaZ *S, Ring &rg, const TmaGeom &G) {
+__device__ void producer_z(const KrylovParamsZ &P, SmemTmaZ *S, RingZ &rg, const TmaGeom &G) {
     const long long ldv = P.ldv;
     const int jstart = P.j0 == 0 ? 1 : P.j0;
     const int iopw = P.iop > 0 ? P.iop : P.m;
@@ -471,7 +490,7 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_z_kernel(const __grid_const
 
     if (tid >= NTC) {
         if (tid == NTC) {
-            Ring rg{ring, P.nslot, 0, 0u};
+            RingZ rg{ring, P.nslot, 0, 0u, (uint32_t)P.slot_bytes};
             producer_z(P, S, rg, G);
         }
         __syncwarp();
@@ -482,7 +501,7 @@ __global__ void __launch_bounds__(NT2, 1) krylov_tma_z_kernel(const __grid_const
         cx.tid = tid;
         cx.lane = tid & 31;
         cx.warp = tid >> 5;
-        cx.rg = Ring{ring, P.nslot, 0, 0u};
+        cx.rg = RingZ{ring, P.nslot, 0, 0u, (uint32_t)P.slot_bytes};
         consumer_z(P, cx, G, tm);
         consumer_sync();
         if (tid == 0) flag_set(&S->stop_seq, 1);

@@ -43,6 +43,7 @@ struct KrylovParamsZ {
     int nnz_cap;     // entries one ring slot holds (val 16 B | colind 4 B | rowptr segment)
     int ch_rows;     // rows per CSR chunk (<= 256: two consumer lanes per row)
     int nslot;       // ring depth
+    int slot_bytes;  // bytes per ring slot (multiple of 128; >= one basis tile and >= one CSR chunk)
     int tile_rows;   // complex rows per basis tile (multiple of 16, <= 2048)
     int hintA_cols;  // operator chunks get L2::evict_first in steps whose window has >= this many columns
     // krylov_z_kernel launched behind the TMA instance: find the first step whose update removed most of the vector

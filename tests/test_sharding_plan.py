@@ -171,3 +171,24 @@ def test_dense_row_sharding_gather_order_gloo_world2(eu):
         p.join(120)
     assert all(p.exitcode == 0 for p in procs)
     assert ret.get(timeout=5) == 1
+
+
+def test_host_binding_helpers(eu, monkeypatch):
+    """parallel.bind_host_near_gpu: sysfs cpulist parsing; unknown NUMA node (no GPU here, or a single-socket host that
+    reports -1) is a recorded no-op that leaves the affinity mask alone; a known node narrows the mask to its CPUs."""
+    import os
+    P = eu.parallel
+    assert P._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert P._parse_cpulist("") == set() and P._parse_cpulist("5") == {5}
+    before = os.sched_getaffinity(0)
+    rec = P.bind_host_near_gpu(0)
+    assert rec == {"numa_node": None, "bound": False} and os.sched_getaffinity(0) == before
+    one = {sorted(before)[0]}
+    monkeypatch.setattr(P, "gpu_numa_node", lambda d: (1, one | {10**6}))
+    try:
+        rec = P.bind_host_near_gpu(0)
+        assert rec["bound"] and rec["numa_node"] == 1 and rec["cpus"] == 1 and os.sched_getaffinity(0) == one
+        monkeypatch.setattr(P, "gpu_numa_node", lambda d: (1, {10**6}))   # no overlap with the allowed CPUs: untouched
+        assert not P.bind_host_near_gpu(0)["bound"] and os.sched_getaffinity(0) == one
+    finally:
+        os.sched_setaffinity(0, before)
