@@ -40,6 +40,16 @@ if "reorth" in which:
 if "z" in which:
     Az = (L.astype(np.complex128) + 0.3j * C).tocsr(); bz = b + 1j * rng.standard_normal(n)
     chk("complex arnoldi", eu.expv(0.5, Az, bz, m=10), O.expv(0.5, Az, bz, m=10))
+    import scipy.sparse as sp
+    Hz = (L + 0.5 * sp.diags([1j * np.ones(n - 1), -1j * np.ones(n - 1)], [1, -1])).tocsr()
+    chk("complex hermitian lanczos", eu.expv(-0.3j, Hz, bz, m=10), O.expv(-0.3j, Hz, bz, m=10))
+    dz = np.concatenate([-np.ones(1000), -2 * np.ones(500), -1e3 * np.ones(500)]) + 1e-8 * rng.standard_normal(2000)
+    Dz = (sp.diags(dz).astype(np.complex128) + 1e-3j * sp.diags(rng.standard_normal(2000))).tocsr()
+    bzz = rng.standard_normal(2000) + 1j * rng.standard_normal(2000)
+    chk("complex reorth hand-over", eu.expv(0.01, Dz, bzz, m=20), O.expv(0.01, Dz, bzz, m=20))
+    eng.set_flag("force_ldg", 1)
+    chk("complex arnoldi ldg", eu.expv(0.5, Az, bz, m=10), O.expv(0.5, Az, bz, m=10))
+    eng.set_flag("force_ldg", 0)
 if "kiops" in which:
     u = rng.standard_normal((n, 2))
     w, st = eu.kiops(0.5, C, u); wo, so = O.kiops(0.5, C, u)
