@@ -334,21 +334,27 @@ __device__ void producer_problem(const KrylovParams &P, const CUtensorMap *tmA, 
                 }
             }
         }
-        for (int k = 0; k < G.ntk && !stopped; ++k) {
-            const int rows = min(G.TR, G.nrows - k * G.TR);
-            for (int col = hi; col >= ulo; --col) {
-                // (XL: column jc - 1 is written lazily during the previous step's update phase)
-                if ((XL && !prod_wait_col(S, col, seq, lane)) || !prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 8u);
-                    {
+        // update tiles.  General instance: the exact reverse of the dots order (column batches, row tiles and columns
+        // descending; see update_phase_c).  XL: one pass over the row tiles (short windows).
+        const int nbatch = XL ? 1 : (hi - lo) / CB + 1;
+        for (int bi = nbatch - 1; bi >= 0 && !stopped; --bi) {
+            const int c0 = (XL || bi == 0) ? ulo : lo + bi * CB;
+            const int c1 = XL ? hi : min(lo + bi * CB + CB - 1, hi);
+            for (int kk = 0; kk < G.ntk && !stopped; ++kk) {
+                const int k = XL ? kk : G.ntk - 1 - kk;
+                const int rows = min(G.TR, G.nrows - k * G.TR);
+                for (int col = c1; col >= c0; --col) {
+                    // (XL: column jc - 1 is written lazily during the previous step's update phase)
+                    if ((XL && !prod_wait_col(S, col, seq, lane)) || !prod_acquire(S, rg, seq, lane)) { stopped = true; break; }
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 8u);
                         const double *src = V + (long long)col * ldv + G.r0 + (long long)k * G.TR;
                         if (hintV) bulk_g2s_hint(rg.ptr(), src, (uint32_t)rows * 8u, &S->full[rg.slot], polV);
                         else bulk_g2s(rg.ptr(), src, (uint32_t)rows * 8u, &S->full[rg.slot]);
                     }
+                    rg.advance();
+                    ++issued;
                 }
-                rg.advance();
-                ++issued;
             }
         }
     }
@@ -880,46 +886,65 @@ __device__ void dots_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, 
     }
 }
 
+// w -= sum_c h_c v_c (c = uhi..ulo), partial ||w||^2, unnormalised w to the gather buffer.
+// Traversal = the exact reverse of the dots phase at tile granularity (column batches descending, row tiles descending,
+// columns descending): the update starts with what the dots phase touched last, so under LRU whatever is among the last
+// ~100 MB of the dots traffic is an L2 hit.  A row-tile-outer loop evicts the later row tiles of the recent columns
+// while it misses on the old columns of the first row tile.  Per element the columns are still subtracted in the order
+// uhi..ulo (bitwise identical results); the price is one shared-memory load + store of the w tile per (batch, tile).
 template <int OPK, bool AUG>
 __device__ double update_phase_c(const KrylovParams &P, Cons &cx, const TmaGeom &G, const Team &tm, const double *V,
-                                 int ulo, int uhi, double *xout) {
+                                 int lo, int ulo, int uhi, double *xout) {
     SmemTma *S = cx.S;
     const int tid = cx.tid;
     double2 *ws2 = reinterpret_cast<double2 *>(cx.ws);
     double2 *xo2 = reinterpret_cast<double2 *>(xout + G.r0);
     const double *hs = S->hs;
     double nrm = 0.0;
-    for (int k = 0; k < G.ntk; ++k) {
-        const int pairs = min(G.TR, G.nrows - k * G.TR) >> 1;
-        const int pbase = (k * G.TR) >> 1;
-        double2 wr[PPT];
-#pragma unroll
-        for (int q = 0; q < PPT; ++q) {
-            const int idx = tid + q * NTC;
-            wr[q] = idx < pairs ? ws2[pbase + idx] : make_double2(0.0, 0.0);
-        }
-        for (int col = uhi; col >= ulo; --col) {
-            const double hc = hs[col - ulo];
-            cx.wait_full();
-            const double2 *vt = reinterpret_cast<const double2 *>(cx.rg.ptr());
+    const int nbatch = (uhi - lo) / CB + 1;
+    for (int bi = nbatch - 1; bi >= 0; --bi) {
+        const int c0 = bi == 0 ? ulo : lo + bi * CB;
+        const int c1 = min(lo + bi * CB + CB - 1, uhi);
+        for (int k = G.ntk - 1; k >= 0; --k) {
+            const int pairs = min(G.TR, G.nrows - k * G.TR) >> 1;
+            const int pbase = (k * G.TR) >> 1;
+            double2 wr[PPT];
 #pragma unroll
             for (int q = 0; q < PPT; ++q) {
                 const int idx = tid + q * NTC;
-                if (idx < pairs) {
-                    const double2 v2 = vt[idx];
-                    wr[q].x = fma(-hc, v2.x, wr[q].x);
-                    wr[q].y = fma(-hc, v2.y, wr[q].y);
-                }
+                wr[q] = idx < pairs ? ws2[pbase + idx] : make_double2(0.0, 0.0);
             }
-            cx.release();
-        }
+            for (int col = c1; col >= c0; --col) {
+                const double hc = hs[col - ulo];
+                cx.wait_full();
+                const double2 *vt = reinterpret_cast<const double2 *>(cx.rg.ptr());
 #pragma unroll
-        for (int q = 0; q < PPT; ++q) {
-            const int idx = tid + q * NTC;
-            if (idx < pairs) {
-                ws2[pbase + idx] = wr[q];
-                xo2[pbase + idx] = wr[q];
-                nrm = fma(wr[q].x, wr[q].x, fma(wr[q].y, wr[q].y, nrm));
+                for (int q = 0; q < PPT; ++q) {
+                    const int idx = tid + q * NTC;
+                    if (idx < pairs) {
+                        const double2 v2 = vt[idx];
+                        wr[q].x = fma(-hc, v2.x, wr[q].x);
+                        wr[q].y = fma(-hc, v2.y, wr[q].y);
+                    }
+                }
+                cx.release();
+            }
+            if (bi == 0) {  // last batch: the tile is final
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    const int idx = tid + q * NTC;
+                    if (idx < pairs) {
+                        ws2[pbase + idx] = wr[q];
+                        xo2[pbase + idx] = wr[q];
+                        nrm = fma(wr[q].x, wr[q].x, fma(wr[q].y, wr[q].y, nrm));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    const int idx = tid + q * NTC;
+                    if (idx < pairs) ws2[pbase + idx] = wr[q];
+                }
             }
         }
     }
@@ -1221,7 +1246,7 @@ __device__ void consumer_problem(const KrylovParams &P, Cons &cx, const TmaGeom 
         }
         consumer_sync();
 
-        const double nrm = update_phase_c<OPK, AUG>(P, cx, G, tm, V, ulo, hi, xout);
+        const double nrm = update_phase_c<OPK, AUG>(P, cx, G, tm, V, lo, ulo, hi, xout);
         PT_MARK(blockIdx.x, j, 4);
         if (sharded) {
             shard_norm_reduce(P, cx, G, tm, nrm, xoff, S->bc);

@@ -11,7 +11,7 @@
 // Tile schedule of step j (identical on the producer and the consumers of a CTA):
 //   [A chunks 0..nch-1]                 one slot = val (16 B / entry) | colind (4 B / entry) | rowptr segment
 //   [dots  : for cb in lo..hi step 8 : for k < ntk : for u < nb : basis tile (column cb+u, rows k)]
-//   [update: for k < ntk : for col = hi..ulo : basis tile (col, rows k)]
+//   [update: the same tiles in exactly the reverse order (batches, row tiles and columns descending; L2 reuse, see update_z)]
 // A basis tile holds <= 2048 complex rows (32 KB); the ring slots are sized to the tile (RingZ).  Two consumer lanes
 // share a CSR row (even / odd entries), so a chunk of <= 256 rows keeps all 512 consumer threads busy although a complex
 // entry needs 20 bytes of slot space.
@@ -155,15 +155,21 @@ __device__ void producer_z(const KrylovParamsZ &P, SmemTmaZ *S, RingZ &rg, const
                 }
             }
         }
-        for (int k = 0; k < G.ntk && !stopped; ++k) {
-            const int rows = min(G.TR, G.nrows - k * G.TR);
-            for (int col = hi; col >= ulo; --col) {
-                if (!prodz_acquire(S, rg)) { stopped = true; break; }
-                mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 16u);
-                bulk_g2s(rg.ptr(), P.V + (long long)col * ldv + G.r0 + (long long)k * G.TR, (uint32_t)rows * 16u,
-                         &S->full[rg.slot]);
-                rg.advance();
-                ++issued;
+        // update tiles: the exact reverse of the dots order (batches, tiles and columns descending) -- see update_z
+        const int nbatch = (hi - lo) / CB + 1;
+        for (int bi = nbatch - 1; bi >= 0 && !stopped; --bi) {
+            const int c0 = bi == 0 ? ulo : lo + bi * CB;
+            const int c1 = min(lo + bi * CB + CB - 1, hi);
+            for (int k = G.ntk - 1; k >= 0 && !stopped; --k) {
+                const int rows = min(G.TR, G.nrows - k * G.TR);
+                for (int col = c1; col >= c0; --col) {
+                    if (!prodz_acquire(S, rg)) { stopped = true; break; }
+                    mbar_arrive_expect_tx(&S->full[rg.slot], (uint32_t)rows * 16u);
+                    bulk_g2s(rg.ptr(), P.V + (long long)col * ldv + G.r0 + (long long)k * G.TR, (uint32_t)rows * 16u,
+                             &S->full[rg.slot]);
+                    rg.advance();
+                    ++issued;
+                }
             }
         }
     }
@@ -298,39 +304,58 @@ __device__ void dots_z(const KrylovParamsZ &P, ConsZ &cx, const TmaGeom &G, cons
     }
 }
 
-// w -= sum_c h_c v_c (c = hi..ulo), partial ||w||^2, unnormalised w to the gather buffer
-__device__ double update_z(const KrylovParamsZ &P, ConsZ &cx, const TmaGeom &G, int ulo, int hi, double2 *xout) {
+// w -= sum_c h_c v_c (c = hi..ulo), partial ||w||^2, unnormalised w to the gather buffer.
+// Traversal = the exact reverse of the dots phase at tile granularity (column batches descending, row tiles descending,
+// columns descending), so the update starts with what the dots phase touched last: under LRU everything among the last
+// ~100 MB of the dots traffic is an L2 hit (six 16 MB columns at n = 10^6).  A row-tile-outer loop (the real kernel's
+// order) lost almost all of that with four tiles per slice: L2 hit rate 8 %, DRAM traffic 18.1 GB of 19.0 GB algorithmic
+// (profiles/r2_ncu_full_complex_arnoldi_summary.json).  The price is one shared-memory load + store of the w tile per
+// (batch, tile) instead of per tile.
+__device__ double update_z(const KrylovParamsZ &P, ConsZ &cx, const TmaGeom &G, int lo, int ulo, int hi, double2 *xout) {
     SmemTmaZ *S = cx.S;
     const int tid = cx.tid;
     double nrm = 0.0;
-    for (int k = 0; k < G.ntk; ++k) {
-        const int rows = min(G.TR, G.nrows - k * G.TR);
-        const int rbase = k * G.TR;
-        double2 wr[PPTZ];
-#pragma unroll
-        for (int q = 0; q < PPTZ; ++q) {
-            const int idx = tid + q * NTC;
-            wr[q] = idx < rows ? cx.ws[rbase + idx] : make_double2(0.0, 0.0);
-        }
-        for (int col = hi; col >= ulo; --col) {
-            const double2 hc = S->hs[col - ulo];
-            const double2 mh = make_double2(-hc.x, -hc.y);
-            cx.wait_full();
-            const double2 *vt = reinterpret_cast<const double2 *>(cx.rg.ptr());
+    const int nbatch = (hi - lo) / CB + 1;
+    for (int bi = nbatch - 1; bi >= 0; --bi) {
+        const int c0 = bi == 0 ? ulo : lo + bi * CB;
+        const int c1 = min(lo + bi * CB + CB - 1, hi);
+        for (int k = G.ntk - 1; k >= 0; --k) {
+            const int rows = min(G.TR, G.nrows - k * G.TR);
+            const int rbase = k * G.TR;
+            double2 wr[PPTZ];
 #pragma unroll
             for (int q = 0; q < PPTZ; ++q) {
                 const int idx = tid + q * NTC;
-                if (idx < rows) wr[q] = zfma(mh, vt[idx], wr[q]);
+                wr[q] = idx < rows ? cx.ws[rbase + idx] : make_double2(0.0, 0.0);
             }
-            cx.release();
-        }
+            for (int col = c1; col >= c0; --col) {
+                const double2 hc = S->hs[col - ulo];
+                const double2 mh = make_double2(-hc.x, -hc.y);
+                cx.wait_full();
+                const double2 *vt = reinterpret_cast<const double2 *>(cx.rg.ptr());
 #pragma unroll
-        for (int q = 0; q < PPTZ; ++q) {
-            const int idx = tid + q * NTC;
-            if (idx < rows) {
-                cx.ws[rbase + idx] = wr[q];
-                xout[G.r0 + rbase + idx] = wr[q];
-                nrm = fma(wr[q].x, wr[q].x, fma(wr[q].y, wr[q].y, nrm));
+                for (int q = 0; q < PPTZ; ++q) {
+                    const int idx = tid + q * NTC;
+                    if (idx < rows) wr[q] = zfma(mh, vt[idx], wr[q]);
+                }
+                cx.release();
+            }
+            if (bi == 0) {  // last batch: the tile is final
+#pragma unroll
+                for (int q = 0; q < PPTZ; ++q) {
+                    const int idx = tid + q * NTC;
+                    if (idx < rows) {
+                        cx.ws[rbase + idx] = wr[q];
+                        xout[G.r0 + rbase + idx] = wr[q];
+                        nrm = fma(wr[q].x, wr[q].x, fma(wr[q].y, wr[q].y, nrm));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < PPTZ; ++q) {
+                    const int idx = tid + q * NTC;
+                    if (idx < rows) cx.ws[rbase + idx] = wr[q];
+                }
             }
         }
     }
@@ -414,7 +439,7 @@ __device__ void consumer_z(const KrylovParamsZ &P, ConsZ &cx, const TmaGeom &G, 
         if (P.lanczos && jc >= 1 && tid == 0) S->hs[0] = make_double2(beta_prev, 0.0);
         consumer_sync();
 
-        const double nrm = update_z(P, cx, G, ulo, hi, xout);
+        const double nrm = update_z(P, cx, G, lo, ulo, hi, xout);
         block_sum_to_zc(cx, nrm, partn + tm.rank);
         team_barrier_zc(tm);
         const double beta = sqrt(team_sum(partn, tm.C, lane));
