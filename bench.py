@@ -253,6 +253,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-reps", type=int, default=8)
     ap.add_argument("--also", default="auto", help="comma list of lanczos,c5,c2s,c3s,c4 or none / auto")
+    ap.add_argument("--pipe", type=int, default=4, help="requests in flight in the pipelined end-to-end measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -392,32 +393,36 @@ def main():
     launches = nonlocal_l[1] - nonlocal_l[0]
     ms_e2e_total = timed(step_e2e, args.steps, args.warmup)
 
-    # e2e with two requests in flight: two handles on two streams, so the PCIe copies of one request overlap the
-    # kernels of the other (b200k_expv_host_async).  Every step still does its own H2D(b) and D2H(w).
-    eng2 = [eng, eu.Engine(local_rank)]
-    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-    w_pins = [w_pin, torch.empty(n, dtype=torch.float64).pin_memory()]
-    b_pins = [b_pin, torch.from_numpy(b_host_np).pin_memory()]
+    # e2e with NPIPE requests in flight: one handle / stream each, so the PCIe copies of one request overlap the kernels
+    # of the others (b200k_expv_host_async).  Every step still does its own H2D(b) and D2H(w).  Four, not two: the
+    # persistent kernel of request i+1 may grab the SMs before the small tail kernels (small exp, projection) of request
+    # i; with two in flight the host then learns late that request i is done and the H2D of request i+2 lands on an
+    # idle GPU (same box, 36 steps: 578 / 588 / 613 / 620 expv/s with 2 / 3 / 4 / 6 in flight, resident 635).
+    NPIPE = max(1, args.pipe)
+    eng2 = [eng] + [eu.Engine(local_rank) for _ in range(NPIPE - 1)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NPIPE)]
+    w_pins = [w_pin] + [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(NPIPE - 1)]
+    b_pins = [b_pin] + [torch.from_numpy(b_host_np).pin_memory() for _ in range(NPIPE - 1)]
 
     def run_pipelined(steps):
         for i in range(steps):
-            k = i & 1
+            k = i % NPIPE
             with torch.cuda.stream(streams[k]):
-                if i >= 2:
-                    eng2[k].synchronize()  # the result of request i - 2 has landed: its buffers are free again
+                if i >= NPIPE:
+                    eng2[k].synchronize()  # the result of request i - NPIPE has landed: its buffers are free again
                 eu.expv_host_async(t_rank, op, b_pins[k], w_pins[k], m=M, ishermitian=herm, engine=eng2[k])
-        for k in (0, 1):
+        for k in range(NPIPE):
             with torch.cuda.stream(streams[k]):
                 eng2[k].synchronize()
 
-    run_pipelined(max(args.warmup, 4))
+    run_pipelined(max(args.warmup, 2 * NPIPE))
     barrier()
     t0 = time.perf_counter()
     run_pipelined(args.steps)
     torch.cuda.synchronize()
     ms_e2e_pipe_total = max_over_ranks((time.perf_counter() - t0) * 1e3)
     barrier()
-    pipe_check = relerr(w_pins[1].numpy(), w_pins[0].numpy())  # both requests computed the same expv
+    pipe_check = max(relerr(w_pins[k].numpy(), w_pins[0].numpy()) for k in range(1, NPIPE))  # all computed the same expv
     clocks = sampler.stop() if rank == 0 else None
 
     # kernel-only duration of the persistent Krylov kernel (events on the launching stream, in the library)
@@ -446,9 +451,10 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "e2e": {"value": e2e_value, "unit": "expv/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
                 "ms_per_step": ms_e2e_pipe_total / args.steps,
-                "mode": "two requests in flight (b200k_expv_host_async on two handles / streams): every step copies its "
+                "mode": "%d requests in flight (b200k_expv_host_async, one handle / stream each): every step copies its "
                         "own 8 MB b from pinned host memory and its own 8 MB w back; the copies of one request overlap "
-                        "the kernels of the other; host wall clock around the whole loop incl. the final synchronise",
+                        "the kernels of the others; host wall clock around the whole loop incl. the final synchronise" % NPIPE,
+                "requests_in_flight": NPIPE,
                 "one_call_at_a_time": {"value": e2e_sync_value, "ms_per_step": ms_e2e_total / args.steps,
                                        "note": "synchronous b200k_expv_host: H2D -> kernels -> D2H serialised per call "
                                                "(CUDA events)"},
