@@ -132,9 +132,12 @@ __device__ __forceinline__ void team_barrier_c(Team &tm, const KrylovParams &P, 
         if (pushed_to_peers) __threadfence_system();  // halo stores into peer memory are performed first
         else __threadfence();
         atomicAdd(tm.bar, 1u);
+        // acquire poll: orders everything after it (the other threads through the CTA barrier below) and invalidates the
+        // L1 (LDG.STRONG + CCTL.IVALL), which is what makes the L1-cached gathers of the next mat-vec safe.  No fence
+        // behind it: a trailing __threadfence cost 1.5 % of the C2 Arnoldi kernel (profiles/r2_s31_ab_barrier.log;
+        // release on the atomic itself -- red.release instead of fence + atomicAdd -- measured 2 % slower).
         while ((int)(ld_acquire_u32(tm.bar) - tm.target) < 0) {
         }
-        __threadfence();
     }
     consumer_sync();
 }
