@@ -373,17 +373,24 @@ def main():
         nonlocal_l[1] = eng.device_info()["launches"]
         return max_over_ranks(e0.elapsed_time(e1))
 
-    def kernel_times(fn, reps):
-        """(mean krylov-kernel ms, mean small-exp + projection ms) from the library's own events, this rank."""
+    def kernel_times(fn, reps, lockstep=False):
+        """(mean krylov-kernel ms, mean small-exp + projection ms) from the library's own events, this rank.
+        lockstep (row-sharded sections: one kernel spans all ranks): the ranks line up before every repetition and the
+        median is taken -- a rank that enters the kernel early waits inside it for its peers, which is launch skew, not
+        kernel time."""
         eng.set_timing(True)
         kms, pms = [], []
         for _ in range(reps):
+            if lockstep:
+                barrier()
             fn()
             torch.cuda.synchronize()
             tm = eng.last_timing()
             kms.append(tm["krylov_ms"])
             pms.append(tm["project_ms"])
         eng.set_timing(False)
+        if lockstep:
+            return float(np.median(kms)), float(np.median(pms))
         return float(np.mean(kms)), float(np.mean(pms))
 
     sampler = ClockSampler(local_rank)
@@ -628,7 +635,7 @@ def main():
                 return eu.expv(T, sop.op, bl, m=M, ishermitian=h2)
 
             ms2 = timed(step2, 20, 3) / 20
-            k2, _ = kernel_times(step2, 5)
+            k2, _ = kernel_times(step2, 7, lockstep=True)
             k2 = max_over_ranks(k2)
             wf = gather_rows(step2(), ranges)
             r = {"ms_per_expv": ms2, "expv_per_s": 1e3 / ms2, "kernel": kname.get(eng.last_kernel(), "?"),
@@ -730,7 +737,7 @@ def main():
                 return eu.expv(1.0, sop.op, bl, m=M, **kw)
 
             ms4 = timed(step4, 10, 3) / 10
-            k4, _ = kernel_times(step4, 5)
+            k4, _ = kernel_times(step4, 7, lockstep=True)
             k4 = max_over_ranks(k4)
             nnz_l, n_l = nnz4 / world, n4 / world
             step_bytes = (12 * nnz_l + 4 * n_l) + (24 * n_l if "lanczos" in name else 16 * n_l + 32 * n_l)
