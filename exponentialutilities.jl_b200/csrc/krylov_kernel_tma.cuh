@@ -16,7 +16,8 @@
 // Tile schedule of step j (identical on the producer and on the consumers of a CTA):
 //   [A chunks 0..nch-1]                       (CSR stream only; val | colind | rowptr segment per slot)
 //   [dots : for cb in lo..hi step 8 : for k in 0..ntk-1 : for u < nb : basis tile (col cb+u, rows k)]
-//   [update: for k in 0..ntk-1 : for col = uhi..ulo : basis tile (col, rows k)]
+//   [update: the same tiles in exactly the reverse order -- batches, row tiles and columns descending (L2 reuse under
+//            LRU, see update_phase_c); XL instance: for k in 0..ntk-1 : for col = uhi..ulo]
 // A basis tile of column c may only be fetched once the consumers have written that column
 // (cols_ready > c, published after a generic->async proxy fence).
 #pragma once
