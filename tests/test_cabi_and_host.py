@@ -171,3 +171,27 @@ def test_runtime_flags_match_header(eu):
     for name, val in flags.items():
         assert f'"{name}": {val}' in src, name
 
+
+
+def test_bench_contract_on_cpu():
+    """bench.py: the reference arm runs without a GPU and prints ONE JSON line with the contract's keys; the B200 arm
+    refuses to run without a CUDA device (no CPU fallback)."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-reps", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "expv/s" and line["unit"] == "expv/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["value"] > 0
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0 == line["e2e"]["d2h_bytes_per_step"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == line["value"]
+    assert "workload" in line["config"] and line["dtype"] == "f64"
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, timeout=600, cwd=root)
+        assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
