@@ -248,7 +248,7 @@ Geom single_geom(b200k_context *h, long long n) {
 // fixed part (two packet all-reduces, ~7000 + 40 C cycles for a team of C CTAs -- measured at C = 37 and 148) plus
 // ~3 cycles per row of the CTA's slice, so smaller teams (more problems in flight) win as long as the two slice
 // buffers and two ring slots still fit in shared memory.  B200K_BATCH_TEAM=C forces the team size (experiments).
-Geom batch_geom(b200k_context *h, long long n, int nb, bool short_window) {
+Geom batch_geom(b200k_context *h, long long n, int nb, bool short_window, int m) {
     if (const char *env = std::getenv("B200K_BATCH_TEAM")) {
         const int C = std::max(1, std::min(std::atoi(env), h->max_ctas));
         return make_geom(n, C, std::min(h->max_ctas / C, nb));
@@ -282,7 +282,16 @@ Geom batch_geom(b200k_context *h, long long n, int nb, bool short_window) {
         if (!g.w_in_smem) continue;
         if ((long long)g.slice * (C - 1) >= n && C > 1) continue;  // empty trailing CTAs
         const int rounds = (nb + nteams - 1) / nteams;
-        const double score = (double)nb / ((double)rounds * nteams) * ((double)nteams * C / h->max_ctas);
+        // problems per round x SM use, times two measured effects (C5 sweep over 16 team sizes, profiles/r2_c5_team_sweep.md):
+        // throughput grows linearly with the bytes of a basis tile (every tile costs one mbarrier round trip: 16.8 KB
+        // tiles 6.6 k, 32 KB tiles 8.8 k expv/s per fully used GPU), and it drops once the bases of the teams in flight
+        // (nteams x (m + 1) columns) exceed about twice the L2.
+        const int ntk0 = (g.slice + TILE_ROWS_MAX - 1) / TILE_ROWS_MAX;
+        const double tile_bytes = 8.0 * (double)round_up((g.slice + ntk0 - 1) / ntk0, 16);
+        const double ws_mb = (double)nteams * (double)(m + 1) * (double)n * 8.0 / 1e6;
+        const double l2pen = std::max(0.5, 1.0 - 0.0007 * std::max(0.0, ws_mb - 2.0 * (double)h->l2_bytes / 1e6));
+        const double score = (double)nb / ((double)rounds * nteams) * ((double)nteams * C / h->max_ctas) *
+                             (tile_bytes + 30720.0) / (32768.0 + 30720.0) * l2pen;
         if (score > best_score + 1e-12) {
             best_score = score;
             best = g;
@@ -1618,7 +1627,7 @@ int b200k_expv_batched(b200k_handle_t h, b200k_op_t op, int nb, const double *t,
     c.B = nullptr;
     c.ldb = 0;
     c.btail_host = nullptr;
-    c.g = batch_geom(h, n, nb, op->kind == 0 && (c.lanczos || c.iop > 0));
+    c.g = batch_geom(h, n, nb, op->kind == 0 && (c.lanczos || c.iop > 0), m);
     int st = B200K_OK;
     bool mv = false;
     if (c.lanczos && op->kind == 0 && !op->comm && h->no_mv != 1 && !h->no_xl && !h->force_ldg && nb >= 2 &&
